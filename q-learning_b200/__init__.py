@@ -1,0 +1,436 @@
+"""q-learning_b200 — B200-native (sm_100a) Breakout env + DQN replay hot path of bitmagier/q-learning.
+
+Host-side mirror of the reference's interfaces for this path, bound over the C ABI in include/ql_cuda.h:
+
+    reference (Rust)                                         here
+    -------------------------------------------------------  ------------------------------------------
+    ql::prelude::Environment            prelude.rs:21-63      BreakoutEnvironment (vectorised: N envs per GPU)
+    ql::prelude::Action / BreakoutAction prelude.rs:12-18     BreakoutAction
+    BreakoutState + ToMultiDimArray     breakout_environment.rs:24-78   BreakoutState
+    ReplayBuffer / BufferSample         replay_buffer.rs:53-146          ReplayBuffer / BufferSample
+    generate_distinct_random_ids        self_driving_tf_q_learner.rs:276-296   ReplayBuffer.generate_distinct_random_ids
+
+There is NO CPU fallback: everything that computes goes through libqlcuda.so and raises QlError when the
+library or a CUDA device is missing. (The package directory name contains a hyphen; import it with
+importlib.import_module("q-learning_b200").)
+"""
+import ctypes as C
+import enum
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+FRAME_W = 84
+FRAME_H = 84
+FRAME_BYTES = FRAME_W * FRAME_H
+NUM_FRAMES = 4
+
+LAYOUT_U8_BHYX = 0
+LAYOUT_F32_BXYH = 1
+
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_OUT_OF_RANGE, ERR_NO_DEVICE, ERR_NOT_ENOUGH = 0, 1, 2, 3, 4, 5
+
+ENVERR_WALL_DISTANCE, ENVERR_APPROX_RANGE, ENVERR_RECURSION, ENVERR_BISECTION, ENVERR_DEGENERATE, ENVERR_ACTION = 1, 2, 4, 8, 16, 32
+
+# every symbol include/ql_cuda.h declares (checked by tests/test_abi.py against the header and the built library)
+ABI_SYMBOLS = [
+    "qlc_version", "qlc_last_error_string", "qlc_device_count", "qlc_env_create", "qlc_env_destroy", "qlc_sync",
+    "qlc_env_reset", "qlc_env_step", "qlc_env_step_host", "qlc_env_obs", "qlc_env_obs_host", "qlc_env_state_view",
+    "qlc_env_read_state", "qlc_env_goal_mean", "qlc_env_time", "qlc_env_error_flags",
+    "qlc_replay_len", "qlc_replay_capacity", "qlc_replay_sample", "qlc_replay_gather", "qlc_replay_sample_host",
+    "qlc_replay_gather_host", "qlc_replay_action_counts",
+    "qlc_stats_read", "qlc_stats_export", "qlc_stats_push", "qlc_stats_mean", "qlc_stats_min", "qlc_stats_window",
+    "qlc_debug_collision_wall", "qlc_debug_collision_rect",
+]
+
+
+class QlError(Exception):
+    """Mirrors ql::prelude::QlError (prelude.rs:70-86); carries the C status code."""
+
+    def __init__(self, msg, code=ERR_INVALID_ARG):
+        super().__init__(msg)
+        self.code = code
+
+
+class QlcConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("n_envs", C.c_uint32), ("env_id_base", C.c_uint32),
+        ("frame_w", C.c_uint32), ("frame_h", C.c_uint32), ("seed", C.c_uint64), ("replay_capacity", C.c_uint64),
+        ("max_episode_steps", C.c_uint32), ("episode_window", C.c_uint32), ("auto_reset", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+class QlcStateHost(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ball_cx", "ball_cy", "ball_dx", "ball_dy", "pad_min_x", "pad_max_x", "pad_speed",
+        "bricks", "score", "episode_step", "episode", "err", "finished")]
+
+
+class QlcStateView(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ball_cx", "ball_cy", "ball_dx", "ball_dy", "pad_min_x", "pad_max_x", "pad_speed",
+        "bricks", "score", "episode_step", "episode", "err", "finished", "frames", "records")] + [
+        ("n_envs", C.c_uint32), ("time_slots", C.c_uint32), ("time", C.c_uint64)]
+
+
+class QlcEpisodeStats(C.Structure):
+    _fields_ = [("sum_return", C.c_uint64), ("episodes", C.c_uint64), ("steps", C.c_uint64),
+                ("min_return", C.c_uint32), ("max_return", C.c_uint32)]
+
+
+_LIB = None
+
+
+def library_path():
+    return _build.SO_PATH
+
+
+def load_library(build_if_missing=True):
+    """dlopen libqlcuda.so (building it first if it is missing or stale). Fails loudly; no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if build_if_missing:
+        _build.build()
+    if not os.path.exists(_build.SO_PATH):
+        raise QlError("libqlcuda.so is missing (run q-learning_b200/build.py); there is no CPU fallback", ERR_NO_DEVICE)
+    L = C.CDLL(_build.SO_PATH)
+    vp, i32, u32, u64 = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64
+    sig = {
+        "qlc_version": (i32, []),
+        "qlc_last_error_string": (C.c_char_p, []),
+        "qlc_device_count": (i32, [vp]),
+        "qlc_env_create": (i32, [C.POINTER(QlcConfig), C.POINTER(vp)]),
+        "qlc_env_destroy": (i32, [vp]),
+        "qlc_sync": (i32, [vp, vp]),
+        "qlc_env_reset": (i32, [vp, vp, vp]),
+        "qlc_env_step": (i32, [vp, vp, u32, vp, vp, vp]),
+        "qlc_env_step_host": (i32, [vp, vp, u32, vp, vp]),
+        "qlc_env_obs": (i32, [vp, i32, vp, vp]),
+        "qlc_env_obs_host": (i32, [vp, i32, vp]),
+        "qlc_env_state_view": (i32, [vp, C.POINTER(QlcStateView)]),
+        "qlc_env_read_state": (i32, [vp, C.POINTER(QlcStateHost)]),
+        "qlc_env_goal_mean": (C.c_float, []),
+        "qlc_env_time": (i32, [vp, C.POINTER(u64)]),
+        "qlc_env_error_flags": (i32, [vp, C.POINTER(u32)]),
+        "qlc_replay_len": (i32, [vp, C.POINTER(u64)]),
+        "qlc_replay_capacity": (i32, [vp, C.POINTER(u64)]),
+        "qlc_replay_sample": (i32, [vp, u32, u32, u64, vp, vp]),
+        "qlc_replay_gather": (i32, [vp, vp, u32, i32, vp, vp, vp, vp, vp, vp]),
+        "qlc_replay_sample_host": (i32, [vp, u32, u64, vp]),
+        "qlc_replay_gather_host": (i32, [vp, vp, u32, i32, vp, vp, vp, vp, vp]),
+        "qlc_replay_action_counts": (i32, [vp, vp]),
+        "qlc_stats_read": (i32, [vp, C.POINTER(QlcEpisodeStats)]),
+        "qlc_stats_export": (i32, [vp, vp, vp]),
+        "qlc_stats_push": (i32, [vp, C.c_float]),
+        "qlc_stats_mean": (i32, [vp, C.POINTER(C.c_float)]),
+        "qlc_stats_min": (i32, [vp, C.POINTER(C.c_float)]),
+        "qlc_stats_window": (i32, [vp, vp, u32, C.POINTER(u32)]),
+        "qlc_debug_collision_wall": (i32, [i32] + [C.c_float] * 5 + [vp] * 6),
+        "qlc_debug_collision_rect": (i32, [C.c_float] * 9 + [vp] * 6),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)   # AttributeError if the library lacks a declared symbol
+        f.restype = res
+        f.argtypes = args
+    _LIB = L
+    return L
+
+
+def _check(rc):
+    if rc != OK:
+        msg = load_library().qlc_last_error_string()
+        raise QlError((msg or b"").decode() or "ql_cuda error %d" % rc, rc)
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    n = C.c_int32(0)
+    rc = load_library().qlc_device_count(C.byref(n))
+    return n.value if rc == OK else 0
+
+
+class BreakoutAction(enum.IntEnum):
+    """BreakoutAction (breakout_environment.rs:94-120)."""
+    NONE = 0
+    LEFT = 1
+    RIGHT = 2
+
+    def numeric(self):
+        return int(self)
+
+    @staticmethod
+    def try_from_numeric(value):
+        if value in (0, 1, 2):
+            return BreakoutAction(value)
+        raise QlError("value out of range", ERR_OUT_OF_RANGE)
+
+
+BreakoutAction.ACTION_SPACE = 3
+
+
+class BreakoutState:
+    """Cheap handle on the current observation of all envs (BreakoutState, breakout_environment.rs:24-28).
+    Clone = copy of (time) — pixels stay in the HBM frame ring until tensorised."""
+
+    def __init__(self, env, time):
+        self._env = env
+        self.time = time
+
+    def dims(self):
+        return [FRAME_W, FRAME_H, NUM_FRAMES]                      # model_dims, breakout_environment.rs:148
+
+    def to_multi_dim_array(self):
+        """[n_envs][x][y][slot] f32 (ToMultiDimArray::to_multi_dim_array, breakout_environment.rs:42-54)."""
+        if self.time != self._env.time():
+            raise QlError("stale BreakoutState handle: the env has stepped since", ERR_INVALID_ARG)
+        return self._env.obs(LAYOUT_F32_BXYH)
+
+    def one_line_info(self):                                        # DebugVisualizer, breakout_environment.rs:81-89
+        s = self._env.read_state()
+        return "Breakout [%d bricks, ball_pos: [%.1f %.1f], panel_pos: [%.1f 570.0]]" % (
+            bin(int(s["bricks"][0])).count("1"), s["ball_cx"][0], s["ball_cy"][0], (s["pad_min_x"][0] + s["pad_max_x"][0]) / 2)
+
+
+class BreakoutEnvironment:
+    """N independent Breakout envs on one GPU behind the reference's Environment interface
+    (prelude.rs:21-63; BreakoutEnvironment, breakout_environment.rs:131-207)."""
+
+    def __init__(self, n_envs=1, frame_size_x=FRAME_W, frame_size_y=FRAME_H, device=0, seed=0, env_id_base=0,
+                 replay_capacity=0, max_episode_steps=0, episode_window=100, auto_reset=True):
+        self._L = load_library()
+        self.n_envs = int(n_envs)
+        cfg = QlcConfig(C.sizeof(QlcConfig), device, n_envs, env_id_base, frame_size_x, frame_size_y, seed,
+                        replay_capacity, max_episode_steps, episode_window, 1 if auto_reset else 0, 0)
+        h = C.c_void_p()
+        _check(self._L.qlc_env_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.device = device
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.qlc_env_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    # -- Environment trait
+    def reset(self, mask=None, dir_x=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        d = None if dir_x is None else np.ascontiguousarray(dir_x, dtype=np.float32)
+        if m is not None and m.shape != (self.n_envs,):
+            raise QlError("mask must have n_envs entries")
+        if d is not None and d.shape != (self.n_envs,):
+            raise QlError("dir_x must have n_envs entries")
+        _check(self._L.qlc_env_reset(self._h, None if m is None else _np_ptr(m), None if d is None else _np_ptr(d)))
+
+    def state(self):
+        return BreakoutState(self, self.time())
+
+    def step(self, actions):
+        """One step for all envs with HOST arrays: returns (state handle, reward f32[n], done u8[n])."""
+        a = np.ascontiguousarray(actions, dtype=np.uint8).reshape(1, self.n_envs)
+        r, d = self.step_many(a)
+        return self.state(), r[0], d[0]
+
+    def step_many(self, actions):
+        """actions u8 [n_steps][n_envs] (host) -> reward f32 [n_steps][n_envs], done u8 [n_steps][n_envs]."""
+        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        if a.ndim != 2 or a.shape[1] != self.n_envs:
+            raise QlError("actions must be [n_steps][n_envs]")
+        k = a.shape[0]
+        reward = np.empty((k, self.n_envs), dtype=np.float32)
+        done = np.empty((k, self.n_envs), dtype=np.uint8)
+        _check(self._L.qlc_env_step_host(self._h, _np_ptr(a), k, _np_ptr(reward), _np_ptr(done)))
+        return reward, done
+
+    def step_device(self, actions_ptr, n_steps, reward_ptr=None, done_ptr=None, stream=None):
+        """Asynchronous step on device buffers (raw device pointers, e.g. torch tensor .data_ptr())."""
+        _check(self._L.qlc_env_step(self._h, actions_ptr, n_steps, reward_ptr, done_ptr, stream))
+
+    def episode_reward_goal_mean(self):
+        return float(self._L.qlc_env_goal_mean())
+
+    # -- state access
+    def time(self):
+        t = C.c_uint64(0)
+        _check(self._L.qlc_env_time(self._h, C.byref(t)))
+        return t.value
+
+    def obs(self, layout=LAYOUT_U8_BHYX):
+        if layout == LAYOUT_U8_BHYX:
+            out = np.empty((self.n_envs, NUM_FRAMES, FRAME_H, FRAME_W), dtype=np.uint8)
+        elif layout == LAYOUT_F32_BXYH:
+            out = np.empty((self.n_envs, FRAME_W, FRAME_H, NUM_FRAMES), dtype=np.float32)
+        else:
+            raise QlError("unknown layout")
+        _check(self._L.qlc_env_obs_host(self._h, layout, _np_ptr(out)))
+        return out
+
+    def obs_device(self, layout, out_ptr, stream=None):
+        _check(self._L.qlc_env_obs(self._h, layout, out_ptr, stream))
+
+    def read_state(self):
+        n = self.n_envs
+        f = {k: np.empty(n, dtype=np.float32) for k in ("ball_cx", "ball_cy", "ball_dx", "ball_dy", "pad_min_x", "pad_max_x", "pad_speed")}
+        f["bricks"] = np.empty(n, dtype=np.uint64)
+        for k in ("score", "episode_step", "episode", "err"):
+            f[k] = np.empty(n, dtype=np.uint32)
+        f["finished"] = np.empty(n, dtype=np.uint8)
+        sh = QlcStateHost(*[f[name].ctypes.data for name, _ in QlcStateHost._fields_])
+        _check(self._L.qlc_env_read_state(self._h, C.byref(sh)))
+        return f
+
+    def state_view(self):
+        v = QlcStateView()
+        _check(self._L.qlc_env_state_view(self._h, C.byref(v)))
+        return v
+
+    def error_flags(self):
+        e = C.c_uint32(0)
+        _check(self._L.qlc_env_error_flags(self._h, C.byref(e)))
+        return e.value
+
+    def sync(self, stream=None):
+        _check(self._L.qlc_sync(self._h, stream))
+
+    # -- shard statistics
+    def stats(self):
+        s = QlcEpisodeStats()
+        _check(self._L.qlc_stats_read(self._h, C.byref(s)))
+        return dict(sum_return=s.sum_return, episodes=s.episodes, steps=s.steps, min_return=s.min_return, max_return=s.max_return)
+
+    def stats_export(self, out_ptr, stream=None):
+        _check(self._L.qlc_stats_export(self._h, out_ptr, stream))
+
+
+class BufferSample:
+    """BufferSample (replay_buffer.rs:140-146)."""
+
+    def __init__(self, state, state_next, reward, action, done):
+        self.state, self.state_next, self.reward, self.action, self.done = state, state_next, reward, action, done
+
+
+class ReplayBuffer:
+    """The replay shard of a BreakoutEnvironment behind ReplayBuffer's method set (replay_buffer.rs:53-137).
+    Frames are written once, by the step kernel, straight into the HBM frame ring; a transition is a 4-byte record."""
+
+    def __init__(self, env):
+        self._env = env
+        self._L = env._L
+        self._calls = 0
+
+    def len(self):
+        n = C.c_uint64(0)
+        _check(self._L.qlc_replay_len(self._env._h, C.byref(n)))
+        return n.value
+
+    __len__ = len
+
+    def capacity(self):
+        n = C.c_uint64(0)
+        _check(self._L.qlc_replay_capacity(self._env._h, C.byref(n)))
+        return n.value
+
+    def add(self, action=None, state=None, state_next=None, reward=None, done=None):
+        """ReplayBuffer::add (:85-98). The step kernel has already appended the transition(s) on the device
+        (frame ring + record); this keeps the reference's call site valid and checks the handles it is given."""
+        if state_next is not None and isinstance(state_next, BreakoutState) and state_next.time != self._env.time():
+            raise QlError("ReplayBuffer.add: state_next is not the env's latest state")
+
+    def add_episode_reward(self, episode_reward):
+        _check(self._L.qlc_stats_push(self._env._h, float(episode_reward)))
+
+    def avg_episode_reward(self):
+        v = C.c_float(0)
+        _check(self._L.qlc_stats_mean(self._env._h, C.byref(v)))
+        return v.value
+
+    def min_episode_reward(self):
+        v = C.c_float(0)
+        _check(self._L.qlc_stats_min(self._env._h, C.byref(v)))
+        return v.value
+
+    def episode_rewards(self):
+        n = C.c_uint32(0)
+        _check(self._L.qlc_stats_window(self._env._h, None, 0, C.byref(n)))
+        out = np.empty(max(n.value, 1), dtype=np.float32)
+        _check(self._L.qlc_stats_window(self._env._h, _np_ptr(out), out.size, C.byref(n)))
+        return out[:n.value]
+
+    def actions(self):
+        """Histogram of the stored actions (what the learner's log derives from actions(): :242-245)."""
+        out = np.zeros(3, dtype=np.uint64)
+        _check(self._L.qlc_replay_action_counts(self._env._h, _np_ptr(out)))
+        return out
+
+    def generate_distinct_random_ids(self, batch, call_index=None):
+        """BATCH distinct uniform indices in 0..len (self_driving_tf_q_learner.rs:276-296), host copy."""
+        if call_index is None:
+            call_index = self._calls
+            self._calls += 1
+        out = np.empty(batch, dtype=np.uint32)
+        _check(self._L.qlc_replay_sample_host(self._env._h, batch, call_index, _np_ptr(out)))
+        return out
+
+    def get_many(self, indices, layout=LAYOUT_F32_BXYH, want_state=True, want_next=True):
+        """get_many (:126-137) + batch_to_multi_dim_array for state and state_next, into host arrays."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        n = idx.size
+        if layout == LAYOUT_U8_BHYX:
+            shape, dt = (n, NUM_FRAMES, FRAME_H, FRAME_W), np.uint8
+        elif layout == LAYOUT_F32_BXYH:
+            shape, dt = (n, FRAME_W, FRAME_H, NUM_FRAMES), np.float32
+        else:
+            raise QlError("unknown layout")
+        s = np.empty(shape, dtype=dt) if want_state else None
+        sn = np.empty(shape, dtype=dt) if want_next else None
+        reward = np.empty(n, dtype=np.float32)
+        action = np.empty(n, dtype=np.uint8)
+        done = np.empty(n, dtype=np.uint8)
+        _check(self._L.qlc_replay_gather_host(self._env._h, _np_ptr(idx), n, layout, None if s is None else _np_ptr(s),
+                                              None if sn is None else _np_ptr(sn), _np_ptr(reward), _np_ptr(action), _np_ptr(done)))
+        return BufferSample(s, sn, reward, action, done)
+
+    # device-buffer forms
+    def sample_device(self, batch, n_batches, call_index, idx_ptr, stream=None):
+        _check(self._L.qlc_replay_sample(self._env._h, batch, n_batches, call_index, idx_ptr, stream))
+
+    def gather_device(self, idx_ptr, n, layout, state_ptr, next_ptr, reward_ptr=None, action_ptr=None, done_ptr=None, stream=None):
+        _check(self._L.qlc_replay_gather(self._env._h, idx_ptr, n, layout, state_ptr, next_ptr, reward_ptr, action_ptr, done_ptr, stream))
+
+
+def debug_collision_wall(which, center, radius, mv):
+    """Run the DEVICE wall test on the GPU: (some, way, approximation, nx, ny, err)."""
+    L = load_library()
+    some, err = C.c_int32(0), C.c_uint32(0)
+    f = [C.c_float(0) for _ in range(4)]
+    _check(L.qlc_debug_collision_wall({"left": 0, "right": 1, "top": 2}[which], center[0], center[1], radius, mv[0], mv[1],
+                                      C.addressof(some), *[C.addressof(x) for x in f], C.addressof(err)))
+    return some.value, f[0].value, f[1].value, f[2].value, f[3].value, err.value
+
+
+def debug_collision_rect(center, radius, mv, rmin, rmax):
+    """Run the DEVICE ball-vs-rectangle sweep on the GPU: (some, way, approximation, nx, ny, err)."""
+    L = load_library()
+    some, err = C.c_int32(0), C.c_uint32(0)
+    f = [C.c_float(0) for _ in range(4)]
+    _check(L.qlc_debug_collision_rect(center[0], center[1], radius, mv[0], mv[1], rmin[0], rmin[1], rmax[0], rmax[1],
+                                      C.addressof(some), *[C.addressof(x) for x in f], C.addressof(err)))
+    return some.value, f[0].value, f[1].value, f[2].value, f[3].value, err.value

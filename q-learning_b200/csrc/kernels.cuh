@@ -1,0 +1,547 @@
+// kernels.cuh — sm_100a kernels of the hot path: fused env step + rasterise + frame-ring append + replay record,
+// Philox distinct-index sampling, and the frame-stack gather (TMA bulk copies through shared memory).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "physics.cuh"
+
+namespace qlc {
+
+constexpr int FRAME_W = 84, FRAME_H = 84, FRAME_BYTES = FRAME_W * FRAME_H;   // 7056 = 441 * 16
+constexpr int FRAME_VEC16 = FRAME_BYTES / 16;
+constexpr int ENVS_PER_CTA = 32;          // one physics warp = one "env batch"
+
+// transition record, one u32 per (time slot, env) — ReplayBuffer::add (replay_buffer.rs:85-98) as a scalar write:
+//   bits 0-1 action | bit 2 done | bits 3-4 k mod 4 | bits 5-7 min(k,4) | bits 8-15 reward | bit 16 truncated
+// k = frames already in the episode's ring when the step was taken (episode_step before the step).
+__host__ __device__ __forceinline__ uint32_t pack_record(uint32_t action, bool done, uint32_t k, uint32_t reward, bool truncated) {
+    return (action & 3u) | (done ? 4u : 0u) | ((k & 3u) << 3) | ((k < 4u ? k : 4u) << 5) | ((reward & 0xFFu) << 8) | (truncated ? 0x10000u : 0u);
+}
+
+struct EnvArrays {
+    float *ball_cx, *ball_cy, *ball_dx, *ball_dy, *pad_min_x, *pad_max_x, *pad_speed;
+    uint64_t* bricks;
+    uint32_t *score, *episode_step, *episode, *err;
+    uint8_t* finished;
+};
+
+struct DeviceStats {                      // order-independent accumulators
+    unsigned long long sum_return, episodes;
+    unsigned int min_return, max_return;
+};
+
+struct StepParams {
+    uint32_t n_envs, env_id_base, time_slots, max_episode_steps, auto_reset, n_steps;
+    uint64_t t0, seed;
+    uint8_t* frames; uint32_t* records; DeviceStats* stats;
+    const uint8_t* actions; float* reward; uint8_t* done;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier, bulk async copies (TMA 1-D), proxy fence
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// shared -> global, completion tracked by the issuing thread's bulk groups
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// global -> shared, completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Raster tables (computed per CTA from the f32 raster spec, never hard-coded)
+// ---------------------------------------------------------------------------------------------------------
+struct RasterTables {
+    uint4 word_bits[FRAME_W / 4];   // per 4-pixel word of a brick row: the brick bit (1<<k) covering each pixel, 0 = gap
+    int grp_first[3], grp_count[3]; // pixel rows of brick row r
+    int pad_first, pad_count;       // pixel rows of the paddle
+    uint32_t col_bit[FRAME_W];
+    int8_t row_grp[FRAME_H];
+    int8_t row_pad[FRAME_H];
+};
+
+__device__ __forceinline__ float scale84(float pos) { return pos * 84.0f / 600.0f; }   // app_game_drawer.rs:21-36
+
+__device__ __forceinline__ void build_raster_tables(RasterTables& T, int tid, int nthreads) {
+    for (int i = tid; i < FRAME_W; i += nthreads) {
+        const float p = (float)i + 0.5f;
+        uint32_t bit = 0u;
+        for (int k = 0; k < 20; ++k) {
+            const float x0 = scale84(30.0f + 27.0f * (float)k), x1 = scale84(55.0f + 27.0f * (float)k);
+            if (p >= x0 && p < x1) bit = 1u << k;
+        }
+        T.col_bit[i] = bit;
+        int g = -1;
+        for (int r = 0; r < 3; ++r) {
+            const float y0 = scale84(35.0f + 27.0f * (float)r), y1 = scale84(60.0f + 27.0f * (float)r);
+            if (p >= y0 && p < y1) g = r;
+        }
+        T.row_grp[i] = (int8_t)g;
+        T.row_pad[i] = (int8_t)((p >= scale84(PAD_MIN_Y) && p < scale84(PAD_MAX_Y)) ? 1 : 0);
+    }
+    __syncthreads();
+    for (int w = tid; w < FRAME_W / 4; w += nthreads)
+        T.word_bits[w] = make_uint4(T.col_bit[4 * w], T.col_bit[4 * w + 1], T.col_bit[4 * w + 2], T.col_bit[4 * w + 3]);
+    if (tid < 3) {
+        int first = 0, count = 0;
+        for (int j = 0; j < FRAME_H; ++j) if (T.row_grp[j] == tid) { if (!count) first = j; ++count; }
+        T.grp_first[tid] = first; T.grp_count[tid] = count;
+    }
+    if (tid == 3) {
+        int first = 0, count = 0;
+        for (int j = 0; j < FRAME_H; ++j) if (T.row_pad[j]) { if (!count) first = j; ++count; }
+        T.pad_first = first; T.pad_count = count;
+    }
+    __syncthreads();
+}
+
+struct RenderRec { float cx, cy, pmin, pmax; uint64_t bricks; };
+
+// Draw one frame into a (clean) shared-memory frame buffer with one warp. Spec: DESIGN.md "Raster spec"
+// (bricks luma 96, ball ring luma 236, paddle luma 255; later overwrites earlier; pixel-centre coverage).
+__device__ __forceinline__ void draw_frame(uint8_t* buf, const RasterTables& T, const RenderRec& r, int lane, int& ball_i0, int& ball_j0) {
+    // bricks: 3 row patterns x 21 words, replicated over the rows of each brick row
+    uint32_t* wbuf = reinterpret_cast<uint32_t*>(buf);
+    for (int idx = lane; idx < 3 * (FRAME_W / 4); idx += 32) {
+        const int g = idx / (FRAME_W / 4), w = idx - g * (FRAME_W / 4);
+        const uint32_t m = (uint32_t)(r.bricks >> (20 * g)) & 0xFFFFFu;
+        const uint4 b = T.word_bits[w];
+        const uint32_t v = ((m & b.x) ? 96u : 0u) | ((m & b.y) ? 96u << 8 : 0u) | ((m & b.z) ? 96u << 16 : 0u) | ((m & b.w) ? 96u << 24 : 0u);
+        const int first = T.grp_first[g], count = T.grp_count[g];
+        for (int j = 0; j < count; ++j) wbuf[(first + j) * (FRAME_W / 4) + w] = v;
+    }
+    __syncwarp();
+    // ball: stroked circle, r_s = 10*84/600, stroke 2 px => (r_s-1)^2 <= d2 <= (r_s+1)^2
+    const float bx = scale84(r.cx), by = scale84(r.cy);
+    const float rs = scale84(BALL_R);
+    const float r_out = rs + 1.0f, r_in = rs - 1.0f;
+    const float out2 = r_out * r_out, in2 = r_in * r_in;
+    ball_i0 = (int)floorf(fminf(fmaxf(bx, -100.0f), 200.0f) - 2.9f);
+    ball_j0 = (int)floorf(fminf(fmaxf(by, -100.0f), 200.0f) - 2.9f);
+    for (int idx = lane; idx < 36; idx += 32) {
+        const int i = ball_i0 + idx % 6, j = ball_j0 + idx / 6;
+        if (i >= 0 && i < FRAME_W && j >= 0 && j < FRAME_H) {
+            const float dx = ((float)i + 0.5f) - bx, dy = ((float)j + 0.5f) - by;
+            const float d2 = dx * dx + dy * dy;
+            if (d2 <= out2 && d2 >= in2) buf[j * FRAME_W + i] = 236;
+        }
+    }
+    __syncwarp();
+    // paddle
+    const float x0 = scale84(r.pmin), x1 = scale84(r.pmax);
+    for (int i = lane; i < FRAME_W; i += 32) {
+        const float p = (float)i + 0.5f;
+        if (p >= x0 && p < x1)
+            for (int j = 0; j < T.pad_count; ++j) buf[(T.pad_first + j) * FRAME_W + i] = 255;
+    }
+}
+
+// Remove everything draw_frame wrote outside the brick band (the band is rewritten in full by the next draw).
+__device__ __forceinline__ void undraw_frame(uint8_t* buf, const RasterTables& T, int lane, int ball_i0, int ball_j0) {
+    for (int idx = lane; idx < 36; idx += 32) {
+        const int i = ball_i0 + idx % 6, j = ball_j0 + idx / 6;
+        if (i >= 0 && i < FRAME_W && j >= 0 && j < FRAME_H) buf[j * FRAME_W + i] = 0;
+    }
+    uint32_t* wbuf = reinterpret_cast<uint32_t*>(buf);
+    for (int idx = lane; idx < T.pad_count * (FRAME_W / 4); idx += 32) wbuf[T.pad_first * (FRAME_W / 4) + idx] = 0u;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Kernel 1: env_advance — n_steps of {time_step, rasterise, frame-ring append, replay record} for 32 envs per CTA.
+//   warp 0        : physics, one lane per env, state in registers across all n_steps; publishes a 24-byte render
+//                   record per env and step into a D-deep shared-memory queue (mbarrier full/empty).
+//   warps 1..R    : rasterise into NB private shared-memory frame buffers each and push them to the HBM frame
+//                   ring with cp.async.bulk (UBLKCP), 7,056 contiguous bytes per frame.
+// ---------------------------------------------------------------------------------------------------------
+template <int R, int NB, int D>
+struct AdvanceSmem {
+    RasterTables tables;
+    RenderRec queue[D][ENVS_PER_CTA];
+    uint64_t full[D], empty[D];
+    int prev_ball[R][NB][2];
+};
+
+template <int R, int NB, int D>
+__global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st, StepParams p) {
+    extern __shared__ __align__(128) uint8_t dyn_smem[];
+    __shared__ AdvanceSmem<R, NB, D> S;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t env0 = blockIdx.x * ENVS_PER_CTA;
+    const uint32_t n_here = min((uint32_t)ENVS_PER_CTA, p.n_envs - env0);
+
+    if (tid == 0) {
+        for (int q = 0; q < D; ++q) { mbar_init(&S.full[q], 1); mbar_init(&S.empty[q], R); }
+        fence_mbar_init();
+    }
+    build_raster_tables(S.tables, tid, blockDim.x);   // contains __syncthreads()
+
+    if (warp == 0) {
+        // ------------------------------- physics warp -------------------------------
+        const uint32_t e = env0 + lane;
+        const bool active = lane < n_here;
+        Env env; uint32_t k = 0, episode = 0;
+        if (active) {
+            env.cx = st.ball_cx[e]; env.cy = st.ball_cy[e]; env.dx = st.ball_dx[e]; env.dy = st.ball_dy[e];
+            env.pmin = st.pad_min_x[e]; env.pmax = st.pad_max_x[e]; env.pspeed = st.pad_speed[e];
+            env.bricks = st.bricks[e]; env.score = st.score[e]; env.err = st.err[e]; env.finished = st.finished[e] != 0;
+            k = st.episode_step[e]; episode = st.episode[e];
+        } else {
+            env_init(env, -0.25f); env.err = 0;
+        }
+        uint32_t action = active ? p.actions[e] : 0u;
+        for (uint32_t s = 0; s < p.n_steps; ++s) {
+            const int q = s % D;
+            uint32_t next_action = 0u;
+            if (active && s + 1 < p.n_steps) next_action = p.actions[(size_t)(s + 1) * p.n_envs + e];
+            if (action >= 3u) { env.err |= ENVERR_ACTION; action = 0u; }
+            const uint32_t score_before = env.score;
+            if (active) time_step(env, action);
+            if (s >= (uint32_t)D) mbar_wait(&S.empty[q], ((s / D) - 1) & 1);
+            if (active) {
+                RenderRec rr; rr.cx = env.cx; rr.cy = env.cy; rr.pmin = env.pmin; rr.pmax = env.pmax; rr.bricks = env.bricks;
+                S.queue[q][lane] = rr;
+                const uint32_t reward = env.score - score_before;
+                const bool done = env.finished;
+                const uint32_t k_before = k;
+                k += 1;
+                const bool truncated = !done && p.max_episode_steps != 0u && k >= p.max_episode_steps;
+                const uint32_t slot = (uint32_t)((p.t0 + s) % p.time_slots);
+                p.records[(size_t)slot * p.n_envs + e] = pack_record(action, done, k_before, reward, truncated);
+                if (p.reward) p.reward[(size_t)s * p.n_envs + e] = (float)reward;
+                if (p.done) p.done[(size_t)s * p.n_envs + e] = done ? 1 : 0;
+                if ((done || truncated) && p.auto_reset) {
+                    // episode end: shard statistics, then restart on device (learn_episode :142,:220)
+                    atomicAdd(&p.stats->sum_return, (unsigned long long)env.score);
+                    atomicAdd(&p.stats->episodes, 1ull);
+                    atomicMin(&p.stats->min_return, env.score);
+                    atomicMax(&p.stats->max_return, env.score);
+                    episode += 1;
+                    env_init(env, reset_dir_x(p.seed, p.env_id_base + e, episode));
+                    k = 0;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.full[q]);
+            action = next_action;
+        }
+        if (active) {
+            st.ball_cx[e] = env.cx; st.ball_cy[e] = env.cy; st.ball_dx[e] = env.dx; st.ball_dy[e] = env.dy;
+            st.pad_min_x[e] = env.pmin; st.pad_max_x[e] = env.pmax; st.pad_speed[e] = env.pspeed;
+            st.bricks[e] = env.bricks; st.score[e] = env.score; st.err[e] = env.err; st.finished[e] = env.finished ? 1 : 0;
+            st.episode_step[e] = k; st.episode[e] = episode;
+        }
+    } else {
+        // ------------------------------- render warps -------------------------------
+        const int rw = warp - 1;
+        uint8_t* my_bufs = dyn_smem + (size_t)rw * NB * FRAME_BYTES;
+        {   // zero the private frame buffers once
+            uint4* z = reinterpret_cast<uint4*>(my_bufs);
+            for (int i = lane; i < NB * FRAME_VEC16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+        }
+        uint32_t f = 0;   // frames drawn by this warp
+        for (uint32_t s = 0; s < p.n_steps; ++s) {
+            const int q = s % D;
+            mbar_wait(&S.full[q], (s / D) & 1);
+            const uint32_t slot = (uint32_t)((p.t0 + s) % p.time_slots);
+            uint8_t* slot_base = p.frames + ((size_t)slot * p.n_envs + env0) * FRAME_BYTES;
+            for (uint32_t j = rw; j < n_here; j += R) {
+                const RenderRec rr = S.queue[q][j];
+                const int b = f % NB;
+                uint8_t* buf = my_bufs + (size_t)b * FRAME_BYTES;
+                if (f >= (uint32_t)NB) {
+                    if (lane == 0) bulk_wait_read<NB - 1>();      // the store that last used this buffer has left smem
+                    __syncwarp();
+                    undraw_frame(buf, S.tables, lane, S.prev_ball[rw][b][0], S.prev_ball[rw][b][1]);
+                }
+                int bi0, bj0;
+                draw_frame(buf, S.tables, rr, lane, bi0, bj0);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    S.prev_ball[rw][b][0] = bi0; S.prev_ball[rw][b][1] = bj0;
+                    bulk_store(slot_base + (size_t)j * FRAME_BYTES, buf, FRAME_BYTES);
+                    bulk_commit();
+                }
+                ++f;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty[q]);
+        }
+        if (lane == 0) bulk_wait<0>();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Kernel 2: reset (Environment::reset): mechanics = default(dir_x), frame stack = zeros (episode_step = 0)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void env_reset_kernel(EnvArrays st, uint32_t n_envs, uint32_t env_id_base, uint64_t seed, const uint8_t* mask,
+                                 const float* dir_x, int first_time) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_envs) return;
+    if (mask && !mask[e]) return;
+    uint32_t episode = first_time ? 0u : st.episode[e] + 1u;
+    Env env; env.err = first_time ? 0u : st.err[e];
+    env_init(env, dir_x ? dir_x[e] : reset_dir_x(seed, env_id_base + e, episode));
+    st.ball_cx[e] = env.cx; st.ball_cy[e] = env.cy; st.ball_dx[e] = env.dx; st.ball_dy[e] = env.dy;
+    st.pad_min_x[e] = env.pmin; st.pad_max_x[e] = env.pmax; st.pad_speed[e] = env.pspeed;
+    st.bricks[e] = env.bricks; st.score[e] = 0u; st.err[e] = env.err; st.finished[e] = 0;
+    st.episode_step[e] = 0u; st.episode[e] = episode;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Kernel 3: distinct uniform index sampling (generate_distinct_random_ids) — one CTA per minibatch.
+// The sequential rejection loop of the reference keeps the FIRST OCCURRENCES of the accepted draws, in stream
+// order; that set is computed in parallel: 1024 raw Philox draws per round, a shared-memory hash table keeps the
+// smallest stream position per value, an ordered block scan compacts the first occurrences.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SAMPLE_THREADS = 256, SAMPLE_TABLE = 4096, SAMPLE_MAX_BATCH = 1024;
+
+__global__ void __launch_bounds__(SAMPLE_THREADS) replay_sample_kernel(uint32_t* out, uint32_t batch, uint32_t len, uint64_t seed, uint64_t call0) {
+    __shared__ uint32_t tval[SAMPLE_TABLE], tpos[SAMPLE_TABLE];
+    __shared__ uint32_t warp_tot[SAMPLE_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t call = call0 + blockIdx.x;
+    uint32_t* dst = out + (size_t)blockIdx.x * batch;
+    for (int i = tid; i < SAMPLE_TABLE; i += SAMPLE_THREADS) { tval[i] = 0xFFFFFFFFu; tpos[i] = 0xFFFFFFFFu; }
+    __syncthreads();
+    const uint32_t thresh = (uint32_t)((0x100000000ull - (uint64_t)len) % (uint64_t)len);   // Lemire rejection zone
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t kept = 0;
+    for (uint32_t round = 0; round < 65536u && kept < batch; ++round) {
+        const uint32_t ctr = round * SAMPLE_THREADS + tid;
+        const uint4 r = philox4x32_10(make_uint4(ctr, (uint32_t)call, (uint32_t)(call >> 32), STREAM_SAMPLE), key);
+        const uint32_t raw[4] = {r.x, r.y, r.z, r.w};
+        uint32_t val[4], slot[4]; bool valid[4];
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint64_t m = (uint64_t)raw[w] * (uint64_t)len;
+            valid[w] = !((uint32_t)m < thresh);
+            val[w] = (uint32_t)(m >> 32);
+            slot[w] = 0;
+            if (valid[w]) {
+                uint32_t h = (val[w] * 0x9E3779B1u) >> 20;          // 12-bit hash
+                for (;;) {
+                    const uint32_t old = atomicCAS(&tval[h], 0xFFFFFFFFu, val[w]);
+                    if (old == 0xFFFFFFFFu || old == val[w]) break;
+                    h = (h + 1) & (SAMPLE_TABLE - 1);
+                }
+                slot[w] = h;
+                atomicMin(&tpos[h], ctr * 4u + (uint32_t)w);
+            }
+        }
+        __syncthreads();
+        bool first[4]; uint32_t cnt = 0;
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) { first[w] = valid[w] && tpos[slot[w]] == ctr * 4u + (uint32_t)w; cnt += first[w] ? 1u : 0u; }
+        // ordered exclusive scan of cnt over the block
+        uint32_t incl = cnt;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t base = kept;
+        for (int w = 0; w < warp; ++w) base += warp_tot[w];
+        uint32_t total = 0;
+        for (int w = 0; w < SAMPLE_THREADS / 32; ++w) total += warp_tot[w];
+        uint32_t pos = base + incl - cnt;
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) if (first[w]) { if (pos < batch) dst[pos] = val[w]; ++pos; }
+        kept += total;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Kernel 4/5: frame-stack gather (ReplayBuffer::get_many + batch_to_multi_dim_array, and Environment::state).
+// A transition at time T of env e with k frames already in its episode uses frames F_{T-d}: state d=1..4,
+// next d=0..3, valid iff d <= k; F_{T-d} sits in ring slot (k-d) mod 4 of the reference's FrameRingBuffer.
+// ---------------------------------------------------------------------------------------------------------
+struct GatherParams {
+    const uint8_t* frames; const uint32_t* records; const uint32_t* episode_step;
+    const uint32_t* indices;   // NULL => observation mode: item b is env b at the current time (state only)
+    uint32_t n_items, n_envs, time_slots;
+    uint64_t t_now, t_oldest;  // replay holds transitions of times [t_oldest, t_now)
+    void* out_state; void* out_next;
+    float* reward; uint8_t* action; uint8_t* done;
+};
+
+__device__ __forceinline__ void locate(const GatherParams& g, uint32_t b, uint64_t& T, uint32_t& e, uint32_t& k, uint32_t& rec) {
+    if (g.indices) {
+        const uint32_t idx = g.indices[b];
+        T = g.t_oldest + idx / g.n_envs; e = idx % g.n_envs;
+        if (T >= g.t_now) { T = g.t_now; k = 0; rec = 0; return; }    // out of range: all-zero item
+        rec = g.records[(size_t)(T % g.time_slots) * g.n_envs + e];
+        const uint32_t kmin = (rec >> 5) & 7u, kmod = (rec >> 3) & 3u;
+        k = kmin < 4u ? kmin : 4u + kmod;    // any k' with k' mod 4 and min(k',4) preserved
+    } else {
+        T = g.t_now; e = b; rec = 0;
+        const uint32_t ks = g.episode_step[e];
+        k = ks < 4u ? ks : 4u + (ks & 3u);
+    }
+}
+
+// u8 [b][slot][y][x]: one warp per item; <= 5 distinct frames in, 8 frames out, all as 7,056-byte bulk copies.
+__global__ void __launch_bounds__(32) gather_u8_kernel(GatherParams g) {
+    extern __shared__ __align__(128) uint8_t sm[];     // 5 frames + 1 zero frame
+    __shared__ uint64_t bar;
+    const int lane = threadIdx.x;
+    const uint32_t b = blockIdx.x;
+    uint64_t T; uint32_t e, k, rec;
+    locate(g, b, T, e, k, rec);
+    uint8_t* zero = sm + 5 * FRAME_BYTES;
+    for (int i = lane; i < FRAME_VEC16; i += 32) reinterpret_cast<uint4*>(zero)[i] = make_uint4(0, 0, 0, 0);
+    if (lane == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        const int d_lo = g.out_next ? 0 : 1, d_hi = g.out_state ? 4 : 3;
+        uint32_t bytes = 0;
+        for (int d = d_lo; d <= d_hi; ++d) if ((uint32_t)d <= k) bytes += FRAME_BYTES;
+        mbar_expect_tx(&bar, bytes);
+        for (int d = d_lo; d <= d_hi; ++d)
+            if ((uint32_t)d <= k) {
+                const uint64_t Tf = T - (uint64_t)d;
+                bulk_load(sm + d * FRAME_BYTES, g.frames + ((size_t)(Tf % g.time_slots) * g.n_envs + e) * FRAME_BYTES, FRAME_BYTES, &bar);
+            }
+        mbar_wait(&bar, 0);
+        for (int h = 0; h < 4; ++h) {
+            if (g.out_state) {
+                const uint32_t d = ((k - h - 1u) & 3u) + 1u;
+                bulk_store((uint8_t*)g.out_state + ((size_t)b * 4 + h) * FRAME_BYTES, d <= k ? sm + d * FRAME_BYTES : zero, FRAME_BYTES);
+            }
+            if (g.out_next) {
+                const uint32_t d = (k - h) & 3u;
+                bulk_store((uint8_t*)g.out_next + ((size_t)b * 4 + h) * FRAME_BYTES, d <= k ? sm + d * FRAME_BYTES : zero, FRAME_BYTES);
+            }
+        }
+        bulk_commit();
+        if (g.reward) g.reward[b] = (float)((rec >> 8) & 0xFFu);
+        if (g.action) g.action[b] = (uint8_t)(rec & 3u);
+        if (g.done) g.done[b] = (uint8_t)((rec >> 2) & 1u);
+        bulk_wait<0>();
+    }
+}
+
+// f32 [b][x][y][slot]: one CTA per (item, which); 4 frames staged in shared memory by bulk copies, then a
+// conflict-free transposing read (row stride 84 B = 21 words) and one coalesced float4 store per pixel.
+constexpr int GATHER_F32_THREADS = 256;
+__global__ void __launch_bounds__(GATHER_F32_THREADS) gather_f32_kernel(GatherParams g) {
+    extern __shared__ __align__(128) uint8_t sm[];     // 4 slot frames
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    const uint32_t b = blockIdx.x >> 1, which = blockIdx.x & 1u;   // 0 = state, 1 = next
+    float4* out = reinterpret_cast<float4*>(which ? g.out_next : g.out_state);
+    if (!out) return;
+    uint64_t T; uint32_t e, k, rec;
+    locate(g, b, T, e, k, rec);
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    // zero-fill the slots that have no frame yet
+    uint32_t dsl[4];
+    #pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        dsl[h] = which ? ((k - h) & 3u) : (((k - h - 1u) & 3u) + 1u);
+        if (dsl[h] > k)
+            for (int i = tid; i < FRAME_VEC16; i += GATHER_F32_THREADS) reinterpret_cast<uint4*>(sm + h * FRAME_BYTES)[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t bytes = 0;
+        for (int h = 0; h < 4; ++h) if (dsl[h] <= k) bytes += FRAME_BYTES;
+        mbar_expect_tx(&bar, bytes);
+        for (int h = 0; h < 4; ++h)
+            if (dsl[h] <= k) {
+                const uint64_t Tf = T - (uint64_t)dsl[h];
+                bulk_load(sm + h * FRAME_BYTES, g.frames + ((size_t)(Tf % g.time_slots) * g.n_envs + e) * FRAME_BYTES, FRAME_BYTES, &bar);
+            }
+        if (which == 0 || !g.out_state) {
+            if (g.reward) g.reward[b] = (float)((rec >> 8) & 0xFFu);
+            if (g.action) g.action[b] = (uint8_t)(rec & 3u);
+            if (g.done) g.done[b] = (uint8_t)((rec >> 2) & 1u);
+        }
+    }
+    mbar_wait(&bar, 0);
+    float4* o = out + (size_t)b * FRAME_BYTES;
+    for (int idx = tid; idx < FRAME_BYTES; idx += GATHER_F32_THREADS) {
+        const int x = idx / FRAME_H, y = idx - x * FRAME_H;
+        const int src = y * FRAME_W + x;
+        o[idx] = make_float4((float)sm[src], (float)sm[FRAME_BYTES + src], (float)sm[2 * FRAME_BYTES + src], (float)sm[3 * FRAME_BYTES + src]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small utility kernels
+// ---------------------------------------------------------------------------------------------------------
+__global__ void action_histogram_kernel(const uint32_t* records, uint32_t n_envs, uint32_t time_slots, uint64_t t_oldest, uint64_t t_now,
+                                        unsigned long long* counts) {
+    const uint64_t total = (t_now - t_oldest) * n_envs;
+    unsigned long long c0 = 0, c1 = 0, c2 = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t T = t_oldest + i / n_envs; const uint32_t e = (uint32_t)(i % n_envs);
+        const uint32_t a = records[(size_t)(T % time_slots) * n_envs + e] & 3u;
+        c0 += a == 0; c1 += a == 1; c2 += a == 2;
+    }
+    for (int o = 16; o; o >>= 1) { c0 += __shfl_down_sync(~0u, c0, o); c1 += __shfl_down_sync(~0u, c1, o); c2 += __shfl_down_sync(~0u, c2, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&counts[0], c0); atomicAdd(&counts[1], c1); atomicAdd(&counts[2], c2); }
+}
+
+__global__ void stats_export_kernel(const DeviceStats* s, uint64_t steps, double* out) {
+    out[0] = (double)s->sum_return; out[1] = (double)s->episodes; out[2] = (double)steps;
+    out[3] = s->episodes ? -(double)s->min_return : -1.0e300; out[4] = s->episodes ? (double)s->max_return : -1.0e300;
+}
+
+__global__ void err_or_kernel(const uint32_t* err, uint32_t n, uint32_t* out) {
+    uint32_t v = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v |= err[i];
+    for (int o = 16; o; o >>= 1) v |= __shfl_down_sync(~0u, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicOr(out, v);
+}
+
+// known-answer entry points (device collision routines, one thread)
+__global__ void debug_collision_kernel(int which, float cx, float cy, float r, float mvx, float mvy, float minx, float miny, float maxx, float maxy,
+                                       float* out /* some, way, approx, nx, ny */, uint32_t* err_out) {
+    uint32_t err = 0; Surface s; s.way = s.approx = s.nx = s.ny = 0.0f; bool some = false;
+    if (which == 3) {
+        const float len = length2(mvx, mvy);
+        some = sweep_ball_box(cx, cy, r, mvx, mvy, len, (minx + maxx) / 2.0f, (miny + maxy) / 2.0f, (maxx - minx) / 2.0f, (maxy - miny) / 2.0f, s, err);
+    } else {
+        float d; bool hit; float f;
+        if (which == 0)      { d = cx - r;          hit = !(d + mvx > 0.0f); f = d / fabsf(mvx); s.nx = 1.0f; }
+        else if (which == 1) { d = GRID_X - cx - r; hit = !(mvx < d);        f = d / fabsf(mvx); s.nx = -1.0f; }
+        else                 { d = cy - r - 0.0f;   hit = !(d + mvy > 0.0f); f = d / fabsf(mvy); s.ny = 1.0f; }
+        if (!(d >= 0.0f)) err |= ENVERR_WALL_DISTANCE;
+        some = hit;
+        if (hit) s.way = length2(mvx * f, mvy * f);
+    }
+    out[0] = some ? 1.0f : 0.0f; out[1] = s.way; out[2] = s.approx; out[3] = s.nx; out[4] = s.ny; *err_out = err;
+}
+
+}  // namespace qlc

@@ -1,0 +1,508 @@
+// qlc_api.cu — C ABI (include/ql_cuda.h) over the sm_100a kernels. No CPU fallback: every entry point that
+// computes needs a CUDA device and fails with QLC_ERR_NO_DEVICE / QLC_ERR_CUDA otherwise.
+#include "../../include/ql_cuda.h"
+#include "kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+
+using namespace qlc;
+
+static thread_local std::string g_last_error;
+
+static int32_t fail(int32_t code, const std::string& msg) { g_last_error = msg; return code; }
+#define CUDA_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return fail(QLC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+    } while (0)
+
+struct qlc_env {
+    qlc_config cfg;
+    EnvArrays st{};
+    uint8_t* frames = nullptr;
+    uint32_t* records = nullptr;
+    DeviceStats* stats = nullptr;
+    unsigned long long* scratch = nullptr;     // 8 x u64 device scratch (histogram, err OR)
+    uint32_t time_slots = 0;                   // frame/record ring length in time steps (= t_cap + 4)
+    uint32_t t_cap = 0;                        // replay capacity in time steps
+    uint64_t t = 0;                            // env-steps taken per env (global time)
+    cudaStream_t own_stream = nullptr;         // used by the *_host entry points
+    // pinned staging for the host-buffer entry points
+    void* pin = nullptr; size_t pin_bytes = 0;
+    void* dev_stage = nullptr; size_t dev_stage_bytes = 0;
+    // episode reward window (replay_buffer.rs:100-124) — host side, fed by the caller like the reference
+    std::deque<float> window;
+    int advance_cfg = 0;
+    std::vector<void*> allocs;
+};
+
+static int32_t ensure_pin(qlc_env* env, size_t bytes) {
+    if (bytes <= env->pin_bytes) return QLC_OK;
+    if (env->pin) cudaFreeHost(env->pin);
+    env->pin = nullptr; env->pin_bytes = 0;
+    CUDA_TRY(cudaMallocHost(&env->pin, bytes));
+    env->pin_bytes = bytes;
+    return QLC_OK;
+}
+static int32_t ensure_dev_stage(qlc_env* env, size_t bytes) {
+    if (bytes <= env->dev_stage_bytes) return QLC_OK;
+    if (env->dev_stage) cudaFree(env->dev_stage);
+    env->dev_stage = nullptr; env->dev_stage_bytes = 0;
+    CUDA_TRY(cudaMalloc(&env->dev_stage, bytes));
+    env->dev_stage_bytes = bytes;
+    return QLC_OK;
+}
+
+template <typename T>
+static int32_t dev_alloc(qlc_env* env, T** p, size_t count, bool zero) {
+    void* q = nullptr;
+    CUDA_TRY(cudaMalloc(&q, count * sizeof(T)));
+    env->allocs.push_back(q);
+    if (zero) CUDA_TRY(cudaMemset(q, 0, count * sizeof(T)));
+    *p = reinterpret_cast<T*>(q);
+    return QLC_OK;
+}
+
+extern "C" {
+
+int32_t qlc_version(void) { return QLC_VERSION; }
+const char* qlc_last_error_string(void) { return g_last_error.c_str(); }
+
+int32_t qlc_device_count(int32_t* count) {
+    if (!count) return fail(QLC_ERR_INVALID_ARG, "count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return fail(QLC_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    *count = n;
+    return QLC_OK;
+}
+
+float qlc_env_goal_mean(void) { return 59.0f; }   // (bricks.len() - 1) as f32, breakout_environment.rs:203-206
+
+static int32_t set_device(const qlc_env* env) { CUDA_TRY(cudaSetDevice(env->cfg.device)); return QLC_OK; }
+
+static int32_t launch_reset(qlc_env* env, const uint8_t* mask_dev, const float* dir_dev, int first_time, cudaStream_t s) {
+    const uint32_t n = env->cfg.n_envs;
+    env_reset_kernel<<<(n + 255) / 256, 256, 0, s>>>(env->st, n, env->cfg.env_id_base, env->cfg.seed, mask_dev, dir_dev, first_time);
+    CUDA_TRY(cudaGetLastError());
+    return QLC_OK;
+}
+
+int32_t qlc_env_create(const qlc_config* cfg, qlc_env** out) {
+    if (!cfg || !out) return fail(QLC_ERR_INVALID_ARG, "cfg/out is null");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(qlc_config)) return fail(QLC_ERR_INVALID_ARG, "qlc_config.struct_size mismatch");
+    if (cfg->n_envs == 0) return fail(QLC_ERR_INVALID_ARG, "n_envs must be > 0");
+    if (cfg->frame_w != QLC_FRAME_W || cfg->frame_h != QLC_FRAME_H) return fail(QLC_ERR_INVALID_ARG, "only 84x84 frames are supported");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(QLC_ERR_NO_DEVICE, "no CUDA device: ql_cuda has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(QLC_ERR_INVALID_ARG, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(QLC_ERR_NO_DEVICE, "ql_cuda is built for sm_100a (B200) only");
+
+    qlc_env* env = new qlc_env();
+    env->cfg = *cfg;
+    if (env->cfg.episode_window == 0) env->cfg.episode_window = 100;
+    int32_t rc = set_device(env);
+    if (rc) { delete env; return rc; }
+    const uint32_t n = cfg->n_envs;
+    uint64_t t_cap = cfg->replay_capacity / n;
+    if (t_cap == 0) t_cap = 1;
+    if (t_cap > 0x7FFFFFF0ull) { delete env; return fail(QLC_ERR_INVALID_ARG, "replay_capacity too large"); }
+    env->t_cap = (uint32_t)t_cap;
+    env->time_slots = env->t_cap + 4;
+    if (const char* c = getenv("QLC_ADVANCE_CFG")) env->advance_cfg = atoi(c);
+
+#define TRY_ALLOC(x) do { rc = (x); if (rc) { qlc_env_destroy(env); return rc; } } while (0)
+    TRY_ALLOC(dev_alloc(env, &env->st.ball_cx, n, false));
+    TRY_ALLOC(dev_alloc(env, &env->st.ball_cy, n, false));
+    TRY_ALLOC(dev_alloc(env, &env->st.ball_dx, n, false));
+    TRY_ALLOC(dev_alloc(env, &env->st.ball_dy, n, false));
+    TRY_ALLOC(dev_alloc(env, &env->st.pad_min_x, n, false));
+    TRY_ALLOC(dev_alloc(env, &env->st.pad_max_x, n, false));
+    TRY_ALLOC(dev_alloc(env, &env->st.pad_speed, n, false));
+    TRY_ALLOC(dev_alloc(env, &env->st.bricks, n, false));
+    TRY_ALLOC(dev_alloc(env, &env->st.score, n, true));
+    TRY_ALLOC(dev_alloc(env, &env->st.episode_step, n, true));
+    TRY_ALLOC(dev_alloc(env, &env->st.episode, n, true));
+    TRY_ALLOC(dev_alloc(env, &env->st.err, n, true));
+    TRY_ALLOC(dev_alloc(env, &env->st.finished, n, true));
+    TRY_ALLOC(dev_alloc(env, &env->frames, (size_t)env->time_slots * n * FRAME_BYTES, false));
+    TRY_ALLOC(dev_alloc(env, &env->records, (size_t)env->time_slots * n, true));
+    TRY_ALLOC(dev_alloc(env, &env->stats, 1, false));
+    TRY_ALLOC(dev_alloc(env, &env->scratch, 8, true));
+#undef TRY_ALLOC
+    cudaError_t ce = cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { qlc_env_destroy(env); return fail(QLC_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(ce)); }
+    DeviceStats init{0ull, 0ull, 0xFFFFFFFFu, 0u};
+    ce = cudaMemcpy(env->stats, &init, sizeof init, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { qlc_env_destroy(env); return fail(QLC_ERR_CUDA, std::string("stats init: ") + cudaGetErrorString(ce)); }
+    rc = launch_reset(env, nullptr, nullptr, 1, nullptr);
+    if (rc) { qlc_env_destroy(env); return rc; }
+    ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) { qlc_env_destroy(env); return fail(QLC_ERR_CUDA, std::string("create sync: ") + cudaGetErrorString(ce)); }
+    *out = env;
+    return QLC_OK;
+}
+
+int32_t qlc_env_destroy(qlc_env* env) {
+    if (!env) return QLC_OK;
+    cudaSetDevice(env->cfg.device);
+    cudaDeviceSynchronize();
+    for (void* p : env->allocs) cudaFree(p);
+    if (env->pin) cudaFreeHost(env->pin);
+    if (env->dev_stage) cudaFree(env->dev_stage);
+    if (env->own_stream) cudaStreamDestroy(env->own_stream);
+    delete env;
+    return QLC_OK;
+}
+
+int32_t qlc_sync(qlc_env* env, void* stream) {
+    if (!env) return fail(QLC_ERR_INVALID_ARG, "env is null");
+    int32_t rc = set_device(env); if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return QLC_OK;
+}
+
+int32_t qlc_env_reset(qlc_env* env, const uint8_t* mask_host, const float* dir_x_host) {
+    if (!env) return fail(QLC_ERR_INVALID_ARG, "env is null");
+    int32_t rc = set_device(env); if (rc) return rc;
+    const uint32_t n = env->cfg.n_envs;
+    CUDA_TRY(cudaDeviceSynchronize());
+    rc = ensure_dev_stage(env, (size_t)n * 8); if (rc) return rc;
+    uint8_t* mask_dev = nullptr; float* dir_dev = nullptr;
+    if (mask_host) { mask_dev = (uint8_t*)env->dev_stage + (size_t)n * 4; CUDA_TRY(cudaMemcpy(mask_dev, mask_host, n, cudaMemcpyHostToDevice)); }
+    if (dir_x_host) { dir_dev = (float*)env->dev_stage; CUDA_TRY(cudaMemcpy(dir_dev, dir_x_host, (size_t)n * 4, cudaMemcpyHostToDevice)); }
+    rc = launch_reset(env, mask_dev, dir_dev, 0, nullptr); if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    return QLC_OK;
+}
+
+}  // extern "C"
+
+template <int R, int NB, int D>
+static int32_t launch_advance(qlc_env* env, const StepParams& p, cudaStream_t s) {
+    static bool configured[64] = {};
+    const size_t dyn = (size_t)R * NB * FRAME_BYTES;
+    auto kern = env_advance_kernel<R, NB, D>;
+    if (!configured[env->cfg.device & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        configured[env->cfg.device & 63] = true;
+    }
+    const uint32_t grid = (p.n_envs + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
+    kern<<<grid, 32 * (R + 1), dyn, s>>>(env->st, p);
+    CUDA_TRY(cudaGetLastError());
+    return QLC_OK;
+}
+
+extern "C" {
+
+int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps, float* reward_dev, uint8_t* done_dev, void* stream) {
+    if (!env || !actions_dev) return fail(QLC_ERR_INVALID_ARG, "env/actions is null");
+    if (n_steps == 0) return QLC_OK;
+    int32_t rc = set_device(env); if (rc) return rc;
+    StepParams p{};
+    p.n_envs = env->cfg.n_envs; p.env_id_base = env->cfg.env_id_base; p.time_slots = env->time_slots;
+    p.max_episode_steps = env->cfg.max_episode_steps; p.auto_reset = env->cfg.auto_reset; p.n_steps = n_steps;
+    p.t0 = env->t; p.seed = env->cfg.seed; p.frames = env->frames; p.records = env->records; p.stats = env->stats;
+    p.actions = actions_dev; p.reward = reward_dev; p.done = done_dev;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (env->advance_cfg) {
+        case 1: rc = launch_advance<4, 2, 2>(env, p, s); break;
+        case 2: rc = launch_advance<4, 4, 2>(env, p, s); break;
+        case 3: rc = launch_advance<7, 2, 2>(env, p, s); break;
+        case 4: rc = launch_advance<8, 3, 2>(env, p, s); break;
+        default: rc = launch_advance<8, 2, 2>(env, p, s); break;
+    }
+    if (rc) return rc;
+    env->t += n_steps;
+    return QLC_OK;
+}
+
+int32_t qlc_env_step_host(qlc_env* env, const uint8_t* actions_host, uint32_t n_steps, float* reward_host, uint8_t* done_host) {
+    if (!env || !actions_host) return fail(QLC_ERR_INVALID_ARG, "env/actions is null");
+    if (n_steps == 0) return QLC_OK;
+    int32_t rc = set_device(env); if (rc) return rc;
+    const size_t n = (size_t)env->cfg.n_envs * n_steps;
+    for (size_t i = 0; i < n; ++i)
+        if (actions_host[i] >= QLC_ACTION_SPACE) return fail(QLC_ERR_OUT_OF_RANGE, "value out of range");   // QlError, breakout_environment.rs:117
+    const size_t off_r = (n + 15) & ~(size_t)15, off_d = off_r + n * 4, total = off_d + n;
+    rc = ensure_pin(env, total); if (rc) return rc;
+    rc = ensure_dev_stage(env, total); if (rc) return rc;
+    uint8_t* pin = (uint8_t*)env->pin; uint8_t* dev = (uint8_t*)env->dev_stage;
+    memcpy(pin, actions_host, n);
+    cudaStream_t s = env->own_stream;
+    CUDA_TRY(cudaMemcpyAsync(dev, pin, n, cudaMemcpyHostToDevice, s));
+    rc = qlc_env_step(env, dev, n_steps, (float*)(dev + off_r), dev + off_d, s); if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(pin + off_r, dev + off_r, n * 5, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (reward_host) memcpy(reward_host, pin + off_r, n * 4);
+    if (done_host) memcpy(done_host, pin + off_d, n);
+    return QLC_OK;
+}
+
+static void fill_gather(const qlc_env* env, GatherParams& g) {
+    g.frames = env->frames; g.records = env->records; g.episode_step = env->st.episode_step;
+    g.n_envs = env->cfg.n_envs; g.time_slots = env->time_slots;
+    g.t_now = env->t; g.t_oldest = env->t > env->t_cap ? env->t - env->t_cap : 0;
+}
+
+static int32_t launch_gather(qlc_env* env, const GatherParams& g, int32_t layout, cudaStream_t s) {
+    if (g.n_items == 0) return QLC_OK;
+    if (layout == QLC_LAYOUT_U8_BHYX) {
+        gather_u8_kernel<<<g.n_items, 32, 6 * FRAME_BYTES, s>>>(g);
+    } else if (layout == QLC_LAYOUT_F32_BXYH) {
+        gather_f32_kernel<<<g.n_items * 2, GATHER_F32_THREADS, 4 * FRAME_BYTES, s>>>(g);
+    } else {
+        return fail(QLC_ERR_INVALID_ARG, "unknown layout");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return QLC_OK;
+}
+
+static size_t item_bytes(int32_t layout) { return layout == QLC_LAYOUT_F32_BXYH ? (size_t)FRAME_BYTES * 4 * sizeof(float) : (size_t)FRAME_BYTES * 4; }
+
+int32_t qlc_env_obs(qlc_env* env, int32_t layout, void* out_dev, void* stream) {
+    if (!env || !out_dev) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    if (((uintptr_t)out_dev & 15) != 0) return fail(QLC_ERR_INVALID_ARG, "output must be 16-byte aligned");
+    int32_t rc = set_device(env); if (rc) return rc;
+    GatherParams g{}; fill_gather(env, g);
+    g.indices = nullptr; g.n_items = env->cfg.n_envs; g.out_state = out_dev;
+    return launch_gather(env, g, layout, (cudaStream_t)stream);
+}
+
+int32_t qlc_env_obs_host(qlc_env* env, int32_t layout, void* out_host) {
+    if (!env || !out_host) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    if (layout != QLC_LAYOUT_U8_BHYX && layout != QLC_LAYOUT_F32_BXYH) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
+    int32_t rc = set_device(env); if (rc) return rc;
+    const size_t bytes = item_bytes(layout) * env->cfg.n_envs;
+    rc = ensure_dev_stage(env, bytes); if (rc) return rc;
+    rc = qlc_env_obs(env, layout, env->dev_stage, env->own_stream); if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_host, env->dev_stage, bytes, cudaMemcpyDeviceToHost, env->own_stream));
+    CUDA_TRY(cudaStreamSynchronize(env->own_stream));
+    return QLC_OK;
+}
+
+int32_t qlc_env_state_view(qlc_env* env, qlc_state_view* out) {
+    if (!env || !out) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    out->ball_cx = env->st.ball_cx; out->ball_cy = env->st.ball_cy; out->ball_dx = env->st.ball_dx; out->ball_dy = env->st.ball_dy;
+    out->pad_min_x = env->st.pad_min_x; out->pad_max_x = env->st.pad_max_x; out->pad_speed = env->st.pad_speed;
+    out->bricks = env->st.bricks; out->score = env->st.score; out->episode_step = env->st.episode_step; out->episode = env->st.episode;
+    out->err = env->st.err; out->finished = env->st.finished; out->frames = env->frames; out->records = env->records;
+    out->n_envs = env->cfg.n_envs; out->time_slots = env->time_slots; out->time = env->t;
+    return QLC_OK;
+}
+
+int32_t qlc_env_read_state(qlc_env* env, const qlc_state_host* o) {
+    if (!env || !o) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    int32_t rc = set_device(env); if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    const size_t n = env->cfg.n_envs;
+#define RD(dst, src, T) do { if (o->dst) CUDA_TRY(cudaMemcpy(o->dst, env->st.src, n * sizeof(T), cudaMemcpyDeviceToHost)); } while (0)
+    RD(ball_cx, ball_cx, float); RD(ball_cy, ball_cy, float); RD(ball_dx, ball_dx, float); RD(ball_dy, ball_dy, float);
+    RD(pad_min_x, pad_min_x, float); RD(pad_max_x, pad_max_x, float); RD(pad_speed, pad_speed, float);
+    RD(bricks, bricks, uint64_t); RD(score, score, uint32_t); RD(episode_step, episode_step, uint32_t);
+    RD(episode, episode, uint32_t); RD(err, err, uint32_t); RD(finished, finished, uint8_t);
+#undef RD
+    return QLC_OK;
+}
+
+int32_t qlc_env_time(qlc_env* env, uint64_t* t) {
+    if (!env || !t) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    *t = env->t; return QLC_OK;
+}
+
+int32_t qlc_env_error_flags(qlc_env* env, uint32_t* out) {
+    if (!env || !out) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    int32_t rc = set_device(env); if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemset(env->scratch, 0, 8));
+    err_or_kernel<<<64, 256>>>(env->st.err, env->cfg.n_envs, (uint32_t*)env->scratch);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, env->scratch, 4, cudaMemcpyDeviceToHost));
+    return QLC_OK;
+}
+
+// ---------------- replay ----------------
+static uint64_t replay_len(const qlc_env* env) {
+    const uint64_t steps = env->t < env->t_cap ? env->t : env->t_cap;
+    return env->cfg.replay_capacity == 0 ? 0 : steps * env->cfg.n_envs;
+}
+
+int32_t qlc_replay_len(qlc_env* env, uint64_t* len) {
+    if (!env || !len) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    *len = replay_len(env); return QLC_OK;
+}
+int32_t qlc_replay_capacity(qlc_env* env, uint64_t* cap) {
+    if (!env || !cap) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    *cap = env->cfg.replay_capacity == 0 ? 0 : (uint64_t)env->t_cap * env->cfg.n_envs; return QLC_OK;
+}
+
+int32_t qlc_replay_sample(qlc_env* env, uint32_t batch, uint32_t n_batches, uint64_t call_index, uint32_t* idx_dev, void* stream) {
+    if (!env || !idx_dev) return fail(QLC_ERR_INVALID_ARG, "env/idx is null");
+    if (batch == 0 || batch > SAMPLE_MAX_BATCH) return fail(QLC_ERR_INVALID_ARG, "batch must be in 1..1024");
+    if (n_batches == 0) return QLC_OK;
+    const uint64_t len = replay_len(env);
+    if (len < batch) return fail(QLC_ERR_NOT_ENOUGH, "replay holds fewer transitions than the batch size");
+    if (len >= 0xFFFFFFFFull) return fail(QLC_ERR_INVALID_ARG, "replay longer than 2^32-1 transitions");
+    int32_t rc = set_device(env); if (rc) return rc;
+    replay_sample_kernel<<<n_batches, SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(idx_dev, batch, (uint32_t)len, env->cfg.seed, call_index);
+    CUDA_TRY(cudaGetLastError());
+    return QLC_OK;
+}
+
+int32_t qlc_replay_gather(qlc_env* env, const uint32_t* idx_dev, uint32_t n, int32_t layout, void* state_dev, void* next_dev,
+                          float* reward_dev, uint8_t* action_dev, uint8_t* done_dev, void* stream) {
+    if (!env || !idx_dev) return fail(QLC_ERR_INVALID_ARG, "env/idx is null");
+    if ((((uintptr_t)state_dev) | ((uintptr_t)next_dev)) & 15) return fail(QLC_ERR_INVALID_ARG, "outputs must be 16-byte aligned");
+    int32_t rc = set_device(env); if (rc) return rc;
+    GatherParams g{}; fill_gather(env, g);
+    g.indices = idx_dev; g.n_items = n; g.out_state = state_dev; g.out_next = next_dev;
+    g.reward = reward_dev; g.action = action_dev; g.done = done_dev;
+    return launch_gather(env, g, layout, (cudaStream_t)stream);
+}
+
+int32_t qlc_replay_sample_host(qlc_env* env, uint32_t batch, uint64_t call_index, uint32_t* idx_host) {
+    if (!env || !idx_host) return fail(QLC_ERR_INVALID_ARG, "env/idx is null");
+    int32_t rc = set_device(env); if (rc) return rc;
+    rc = ensure_dev_stage(env, (size_t)batch * 4); if (rc) return rc;
+    rc = qlc_replay_sample(env, batch, 1, call_index, (uint32_t*)env->dev_stage, env->own_stream); if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(idx_host, env->dev_stage, (size_t)batch * 4, cudaMemcpyDeviceToHost, env->own_stream));
+    CUDA_TRY(cudaStreamSynchronize(env->own_stream));
+    return QLC_OK;
+}
+
+int32_t qlc_replay_gather_host(qlc_env* env, const uint32_t* idx_host, uint32_t n, int32_t layout, void* state_host, void* next_host,
+                               float* reward_host, uint8_t* action_host, uint8_t* done_host) {
+    if (!env || !idx_host) return fail(QLC_ERR_INVALID_ARG, "env/idx is null");
+    if (layout != QLC_LAYOUT_U8_BHYX && layout != QLC_LAYOUT_F32_BXYH) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
+    if (n == 0) return QLC_OK;
+    const uint64_t len = replay_len(env);
+    for (uint32_t i = 0; i < n; ++i) if (idx_host[i] >= len) return fail(QLC_ERR_OUT_OF_RANGE, "replay index out of range");
+    int32_t rc = set_device(env); if (rc) return rc;
+    const size_t ib = item_bytes(layout);
+    // device staging: idx | state | next | reward | action | done
+    const size_t o_idx = 0, o_s = ((size_t)n * 4 + 255) & ~(size_t)255, o_n = o_s + ib * n, o_r = o_n + ib * n, o_a = o_r + (size_t)n * 4, o_d = o_a + n;
+    const size_t total = o_d + n;
+    rc = ensure_dev_stage(env, total); if (rc) return rc;
+    rc = ensure_pin(env, total); if (rc) return rc;
+    uint8_t* dev = (uint8_t*)env->dev_stage; uint8_t* pin = (uint8_t*)env->pin;
+    cudaStream_t s = env->own_stream;
+    memcpy(pin + o_idx, idx_host, (size_t)n * 4);
+    CUDA_TRY(cudaMemcpyAsync(dev + o_idx, pin + o_idx, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    rc = qlc_replay_gather(env, (const uint32_t*)(dev + o_idx), n, layout, state_host ? dev + o_s : nullptr, next_host ? dev + o_n : nullptr,
+                           (float*)(dev + o_r), dev + o_a, dev + o_d, s);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(pin + o_s, dev + o_s, total - o_s, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (state_host) memcpy(state_host, pin + o_s, ib * n);
+    if (next_host) memcpy(next_host, pin + o_n, ib * n);
+    if (reward_host) memcpy(reward_host, pin + o_r, (size_t)n * 4);
+    if (action_host) memcpy(action_host, pin + o_a, n);
+    if (done_host) memcpy(done_host, pin + o_d, n);
+    return QLC_OK;
+}
+
+int32_t qlc_replay_action_counts(qlc_env* env, uint64_t counts[3]) {
+    if (!env || !counts) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    int32_t rc = set_device(env); if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemset(env->scratch, 0, 3 * sizeof(unsigned long long)));
+    counts[0] = counts[1] = counts[2] = 0;
+    if (replay_len(env) == 0) return QLC_OK;
+    const uint64_t t_old = env->t > env->t_cap ? env->t - env->t_cap : 0;
+    action_histogram_kernel<<<296, 256>>>(env->records, env->cfg.n_envs, env->time_slots, t_old, env->t, env->scratch);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long h[3];
+    CUDA_TRY(cudaMemcpy(h, env->scratch, sizeof h, cudaMemcpyDeviceToHost));
+    counts[0] = h[0]; counts[1] = h[1]; counts[2] = h[2];
+    return QLC_OK;
+}
+
+// ---------------- episode statistics ----------------
+int32_t qlc_stats_read(qlc_env* env, qlc_episode_stats* out) {
+    if (!env || !out) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    int32_t rc = set_device(env); if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    DeviceStats d;
+    CUDA_TRY(cudaMemcpy(&d, env->stats, sizeof d, cudaMemcpyDeviceToHost));
+    out->sum_return = d.sum_return; out->episodes = d.episodes; out->steps = env->t * env->cfg.n_envs;
+    out->min_return = d.min_return; out->max_return = d.max_return;
+    return QLC_OK;
+}
+int32_t qlc_stats_export(qlc_env* env, double* out_dev, void* stream) {
+    if (!env || !out_dev) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    int32_t rc = set_device(env); if (rc) return rc;
+    stats_export_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->stats, env->t * env->cfg.n_envs, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return QLC_OK;
+}
+int32_t qlc_stats_push(qlc_env* env, float r) {                      // Buffer::add (replay_buffer.rs:21-29)
+    if (!env) return fail(QLC_ERR_INVALID_ARG, "env is null");
+    if (env->window.size() >= env->cfg.episode_window) env->window.pop_front();
+    env->window.push_back(r);
+    return QLC_OK;
+}
+int32_t qlc_stats_mean(qlc_env* env, float* out) {                   // avg_episode_reward :107-111
+    if (!env || !out) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    if (env->window.empty()) return fail(QLC_ERR_NOT_ENOUGH, "episode reward history is empty");
+    float sum = 0.0f;
+    for (float v : env->window) sum = sum + v;
+    *out = sum / (float)env->window.size();
+    return QLC_OK;
+}
+int32_t qlc_stats_min(qlc_env* env, float* out) {                    // min_episode_reward :113-120
+    if (!env || !out) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    if (env->window.empty()) return fail(QLC_ERR_NOT_ENOUGH, "episode reward history is empty");
+    float mn = env->window.front();
+    for (float v : env->window) if (v < mn) mn = v;
+    *out = mn;
+    return QLC_OK;
+}
+int32_t qlc_stats_window(qlc_env* env, float* out, uint32_t cap, uint32_t* n) {   // episode_rewards :124
+    if (!env || !n) return fail(QLC_ERR_INVALID_ARG, "env/n is null");
+    uint32_t i = 0;
+    for (float v : env->window) { if (out && i < cap) out[i] = v; ++i; }
+    *n = i;
+    return QLC_OK;
+}
+
+// ---------------- debug / known-answer ----------------
+static int32_t run_debug(int which, float cx, float cy, float r, float mvx, float mvy, float minx, float miny, float maxx, float maxy,
+                         int32_t* some, float* way, float* approx, float* nx, float* ny, uint32_t* err) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(QLC_ERR_NO_DEVICE, "no CUDA device: ql_cuda has no CPU fallback");
+    float* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 8 * sizeof(float)));
+    debug_collision_kernel<<<1, 1>>>(which, cx, cy, r, mvx, mvy, minx, miny, maxx, maxy, d, (uint32_t*)(d + 6));
+    cudaError_t e = cudaGetLastError();
+    float h[8];
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("debug kernel: ") + cudaGetErrorString(e));
+    if (some) *some = h[0] != 0.0f;
+    if (way) *way = h[1];
+    if (approx) *approx = h[2];
+    if (nx) *nx = h[3];
+    if (ny) *ny = h[4];
+    if (err) memcpy(err, &h[6], 4);
+    return QLC_OK;
+}
+int32_t qlc_debug_collision_wall(int32_t which, float cx, float cy, float radius, float mvx, float mvy, int32_t* some, float* way,
+                                 float* approximation, float* nx, float* ny, uint32_t* err) {
+    if (which < 0 || which > 2) return fail(QLC_ERR_INVALID_ARG, "which must be 0..2");
+    return run_debug(which, cx, cy, radius, mvx, mvy, 0, 0, 0, 0, some, way, approximation, nx, ny, err);
+}
+int32_t qlc_debug_collision_rect(float cx, float cy, float radius, float mvx, float mvy, float min_x, float min_y, float max_x, float max_y,
+                                 int32_t* some, float* way, float* approximation, float* nx, float* ny, uint32_t* err) {
+    return run_debug(3, cx, cy, radius, mvx, mvy, min_x, min_y, max_x, max_y, some, way, approximation, nx, ny, err);
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+Bar: bit-exact for bricks / score / done / reward / episode counters / pixels / gathered batches / sampled
+indices; ball and paddle f32 state is compared bit-exactly too (north_star allows 1e-6 relative; we hold 0)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+STATE_F32 = ("ball_cx", "ball_cy", "ball_dx", "ball_dy", "pad_min_x", "pad_max_x", "pad_speed")
+STATE_INT = ("bricks", "score", "episode_step")
+
+
+def _assert_state_equal(gs, os_, ctx=""):
+    for k in STATE_INT:
+        assert np.array_equal(gs[k], os_[k]), "%s %s differs at envs %s" % (ctx, k, np.nonzero(gs[k] != os_[k])[0][:8])
+    assert np.array_equal(gs["finished"] != 0, os_["finished"] != 0), ctx + " finished differs"
+    for k in STATE_F32:
+        a, b = gs[k], os_[k]
+        rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-30)
+        assert np.all((a == b) | (rel <= 1e-6)), "%s %s beyond 1e-6 relative" % (ctx, k)   # north_star tolerance
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "%s %s not bit-identical (max rel %.3g)" % (ctx, k, rel.max())
+
+
+# ---- the reference's own known-answer vectors, replayed through the DEVICE collision code ----
+def test_device_collision_known_answers(qlb):
+    """mechanics.rs:659-693 (walls, exact) and :708-752 (rectangle, normal +-0.01, way +-0.1, 0 <= approx < 0.8)."""
+    W = 600.0
+    assert qlb.debug_collision_wall("left", (10.0, 10.0), 5.0, (-2.0, 2.0))[0] == 0
+    assert qlb.debug_collision_wall("left", (5.0, 10.0), 5.0, (-5.0, 0.0))[:5] == (1, 0.0, 0.0, 1.0, 0.0)
+    assert qlb.debug_collision_wall("left", (7.0, 7.0), 5.0, (-5.0, 0.0))[:5] == (1, 2.0, 0.0, 1.0, 0.0)
+    assert qlb.debug_collision_wall("right", (W - 10.0, 10.0), 5.0, (2.0, 2.0))[0] == 0
+    assert qlb.debug_collision_wall("right", (W - 5.0, 10.0), 5.0, (5.0, 0.0))[:5] == (1, 0.0, 0.0, -1.0, 0.0)
+    assert qlb.debug_collision_wall("right", (W - 7.0, 7.0), 5.0, (5.0, 0.0))[:5] == (1, 2.0, 0.0, -1.0, 0.0)
+    s = 0.5 ** 0.5
+    cases = [
+        ((10.0, 0.0), (150.0, 90.0), (170.0, 110.0), None),
+        ((5.0, 0.0), (110.0, 90.0), (130.0, 110.0), (5.0, -1.0, 0.0)),
+        ((3.0, -3.0), (100.0, 70.0), (120.0, 93.0), (2.83, 0.0, 1.0)),
+        ((-8.0, -8.0), (70.0, 80.0), (90.0, 100.0), (7.07, 1.0, 0.0)),
+        ((-1.46, -1.46), (80.0, 80.0), (95.0, 95.0), (2.07, s, s)),
+        ((-5.0, -5.0), (80.0, 80.0), (95.0, 95.0), (2.07, s, s)),
+        ((-4.2, -4.2), (80.0, 80.0), (90.0, 90.0), None),
+    ]
+    for mv, rmin, rmax, exp in cases:
+        some, way, approx, nx, ny, err = qlb.debug_collision_rect((100.0, 100.0), 5.0, mv, rmin, rmax)
+        assert bool(some) == (exp is not None), (mv, some)
+        if exp:
+            assert abs(nx - exp[1]) <= 0.01 and abs(ny - exp[2]) <= 0.01 and abs(way - exp[0]) <= 0.1
+            assert 0.0 <= approx < 0.8
+
+
+def test_device_collision_matches_oracle_bitwise(qlb, O):
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        c = (float(np.float32(rng.uniform(20, 580))), float(np.float32(rng.uniform(20, 580))))
+        ang = rng.uniform(0, 2 * np.pi)
+        mv = (float(np.float32(4 * np.cos(ang))), float(np.float32(4 * np.sin(ang))))
+        off = rng.uniform(-16, 16, size=2)
+        rmin = (float(np.float32(c[0] + off[0])), float(np.float32(c[1] + off[1])))
+        rmax = (float(np.float32(rmin[0] + 25)), float(np.float32(rmin[1] + 25)))
+        g = qlb.debug_collision_rect(c, 10.0, mv, rmin, rmax)
+        o = O.collision_rect(c, 10.0, mv, rmin, rmax)
+        assert g[0] == o[0]
+        if g[0]:
+            assert np.array_equal(np.float32(g[1:5]).view(np.uint32), np.float32(o[1:5]).view(np.uint32)), (c, mv, rmin, g, o)
+        assert g[5] == o[5]
+
+
+# ---- trajectories ----
+@pytest.mark.parametrize("n_envs,chunks,seed", [(256, [1, 3, 64, 200, 500, 32], 11), (37, [5, 1, 1, 90, 300], 3), (1, [400, 400], 9)])
+def test_trajectory_parity(qlb, O, n_envs, chunks, seed):
+    """step+render+frame-stack+auto-reset for N envs, several launch sizes, vs the oracle step by step."""
+    env = qlb.BreakoutEnvironment(n_envs=n_envs, seed=seed, replay_capacity=0)
+    ora = O.VecEnv(n_envs, seed=seed)
+    _assert_state_equal(env.read_state(), ora.state(), "initial")
+    t = 0
+    for k in chunks:
+        acts = O.synthetic_actions(seed, 0, n_envs, t, k)
+        reward, done = env.step_many(acts)
+        for s in range(k):
+            r, d = ora.step(acts[s])
+            assert np.array_equal(r, reward[s]), "reward differs at step %d" % (t + s)
+            assert np.array_equal(d, done[s]), "done differs at step %d" % (t + s)
+        t += k
+        _assert_state_equal(env.read_state(), ora.state(), "t=%d" % t)
+        assert np.array_equal(env.obs(qlb.LAYOUT_U8_BHYX), ora.obs_u8()), "frame stacks differ at t=%d" % t
+    assert np.array_equal(env.obs(qlb.LAYOUT_F32_BXYH), ora.obs_f32())
+    gs, os_ = env.stats(), ora.stats()
+    assert gs["episodes"] == os_["episodes"] and gs["sum_return"] == int(os_["sum_return"]) and gs["steps"] == os_["steps"]
+    if gs["episodes"]:
+        assert gs["min_return"] == int(os_["min_return"]) and gs["max_return"] == int(os_["max_return"])
+    assert env.error_flags() == 0 and not ora.state()["err"].any()
+    env.close()
+
+
+def test_skilled_play_hits_many_bricks(qlb, O):
+    """A paddle that tracks the ball keeps episodes alive for thousands of steps: bounces off paddle, walls and
+    bricks (multi-contact, bisection paths) must stay bit-identical."""
+    n = 64
+    seed = 21
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=seed)
+    ora = O.VecEnv(n, seed=seed)
+    rng = np.random.default_rng(0)
+    for it in range(1500):
+        st = ora.state()
+        centre = (st["pad_min_x"] + st["pad_max_x"]) / 2
+        target = st["ball_cx"] + rng.uniform(-25, 25, size=n).astype(np.float32)
+        a = np.where(target < centre - 4, 1, np.where(target > centre + 4, 2, 0)).astype(np.uint8)
+        r, d = ora.step(a)
+        _, gr, gd = env.step(a)
+        assert np.array_equal(r, gr) and np.array_equal(d, gd), "step %d" % it
+        if it % 100 == 99:
+            _assert_state_equal(env.read_state(), ora.state(), "it=%d" % it)
+    _assert_state_equal(env.read_state(), ora.state(), "final")
+    assert np.array_equal(env.obs(), ora.obs_u8())
+    assert ora.state()["score"].max() >= 3 or ora.stats()["max_return"] >= 3, "controller never hit bricks; test too weak"
+    assert env.error_flags() & ~qlb.ENVERR_DEGENERATE == 0
+    env.close()
+
+
+def test_explicit_reset_and_no_auto_reset(qlb, O):
+    """Reference behaviour: no auto reset, the caller resets (learn_episode :142); dir_x is an explicit input."""
+    n = 8
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=1, auto_reset=False)
+    dirs = np.linspace(-0.35, -0.15, n, endpoint=False).astype(np.float32)
+    env.reset(dir_x=dirs)
+    st = env.read_state()
+    assert np.array_equal(st["ball_dx"], dirs) and np.all(st["ball_dy"] == -1.0) and np.all(st["episode_step"] == 0)
+    assert np.all(st["bricks"] == (1 << 60) - 1) and np.all(st["pad_min_x"] == 270) and np.all(st["pad_max_x"] == 330)
+    # oracle: single envs with the same explicit directions, stepped past the end of the episode
+    ora = O.VecEnv(n, seed=1, max_episode_steps=0)
+    # the oracle driver auto-resets, so compare only until the first done
+    for e in range(n):
+        ora.reset_env(e, float(dirs[e]))
+    acts = O.synthetic_actions(1, 0, n, 0, 400)
+    reward, done = env.step_many(acts)
+    alive = np.ones(n, dtype=bool)
+    for s in range(400):
+        r, d = ora.step(acts[s])
+        assert np.array_equal(r[alive], reward[s][alive]) and np.array_equal(d[alive], done[s][alive])
+        alive &= d == 0
+        # once finished, the GPU env stays finished (sticky) and keeps reporting done
+        assert np.all(done[s][~alive] == 1)
+    assert not alive.all(), "no episode ended in 400 steps"
+    # masked reset restarts only the selected envs
+    mask = np.zeros(n, dtype=np.uint8); mask[::2] = 1
+    before = env.read_state()
+    env.reset(mask=mask)
+    after = env.read_state()
+    assert np.all(after["episode_step"][::2] == 0) and np.all(after["finished"][::2] == 0)
+    assert np.array_equal(after["ball_cx"][1::2], before["ball_cx"][1::2])
+    assert np.array_equal(after["episode"][::2], before["episode"][::2] + 1)
+    for e in range(0, n, 2):   # Philox reset direction of (env, episode)
+        assert after["ball_dx"][e] == np.float32(O.lib().orc_reset_dir_x(1, e, int(after["episode"][e])))
+    env.close()
+
+
+def test_truncation(qlb, O):
+    n = 16
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=4, max_episode_steps=50)
+    ora = O.VecEnv(n, seed=4, max_episode_steps=50)
+    acts = O.synthetic_actions(4, 0, n, 0, 260)
+    reward, done = env.step_many(acts)
+    for s in range(260):
+        r, d = ora.step(acts[s])
+        assert np.array_equal(r, reward[s]) and np.array_equal(d, done[s])
+    _assert_state_equal(env.read_state(), ora.state())
+    assert env.read_state()["episode_step"].max() < 50
+    assert env.stats()["episodes"] == ora.stats()["episodes"] >= n * 5
+    env.close()
+
+
+def test_invalid_action_is_an_error(qlb):
+    env = qlb.BreakoutEnvironment(n_envs=4)
+    with pytest.raises(qlb.QlError) as ei:
+        env.step(np.array([0, 1, 3, 2], dtype=np.uint8))
+    assert ei.value.code == qlb.ERR_OUT_OF_RANGE and "out of range" in str(ei.value)
+    with pytest.raises(qlb.QlError):
+        qlb.BreakoutAction.try_from_numeric(3)
+    env.close()
+
+
+# ---- replay ----
+@pytest.mark.parametrize("n_envs,capacity,steps", [(1, 300, 700), (8, 8 * 40, 333), (64, 64 * 16, 100)])
+def test_replay_parity(qlb, O, n_envs, capacity, steps):
+    """FIFO semantics (index 0 = oldest, eviction when full), get_many + batch_to_multi_dim_array in both layouts."""
+    seed = 17
+    env = qlb.BreakoutEnvironment(n_envs=n_envs, seed=seed, replay_capacity=capacity)
+    rb = qlb.ReplayBuffer(env)
+    ora = O.VecEnv(n_envs, seed=seed, replay_capacity=capacity)
+    rng = np.random.default_rng(1)
+    t = 0
+    for chunk in (1, 2, 5, 17, steps):
+        acts = O.synthetic_actions(seed, 0, n_envs, t, chunk)
+        env.step_many(acts)
+        for s in range(chunk):
+            ora.step(acts[s])
+        t += chunk
+        assert rb.len() == ora.replay_len()
+        ln = rb.len()
+        idx = rng.integers(0, ln, size=min(48, ln)).astype(np.uint32)
+        idx[0] = 0; idx[-1] = ln - 1
+        for layout, name in ((qlb.LAYOUT_U8_BHYX, "u8"), (qlb.LAYOUT_F32_BXYH, "f32")):
+            g = rb.get_many(idx, layout)
+            o = ora.get_many(idx, name)
+            assert np.array_equal(g.reward, o["reward"]) and np.array_equal(g.action, o["action"]) and np.array_equal(g.done, o["done"])
+            assert np.array_equal(g.state, o["state"]), "state differs (%s) at t=%d" % (name, t)
+            assert np.array_equal(g.state_next, o["state_next"]), "state_next differs (%s) at t=%d" % (name, t)
+    assert rb.capacity() == capacity
+    assert np.array_equal(rb.actions(), ora.action_histogram())
+    with pytest.raises(qlb.QlError) as ei:
+        rb.get_many(np.array([rb.len()], dtype=np.uint32))
+    assert ei.value.code == qlb.ERR_OUT_OF_RANGE
+    env.close()
+
+
+@pytest.mark.parametrize("length_steps,batch", [(40, 32), (5, 32), (200, 512), (33, 1024)])
+def test_sampler_parity(qlb, O, length_steps, batch):
+    """generate_distinct_random_ids: distinct, in range (the reference's own property test :346-361) and equal to
+    the oracle's sequential rejection on the same Philox stream — including ranges barely larger than the batch."""
+    n_envs = 32
+    env = qlb.BreakoutEnvironment(n_envs=n_envs, seed=99, replay_capacity=n_envs * 256)
+    rb = qlb.ReplayBuffer(env)
+    env.step_many(np.zeros((length_steps, n_envs), dtype=np.uint8))
+    ln = rb.len()
+    assert ln == length_steps * n_envs
+    if ln < batch:
+        with pytest.raises(qlb.QlError) as ei:
+            rb.generate_distinct_random_ids(batch, 0)
+        assert ei.value.code == qlb.ERR_NOT_ENOUGH
+        env.close()
+        return
+    for call in (0, 1, 2, 1 << 33):
+        g = rb.generate_distinct_random_ids(batch, call)
+        assert len(set(g.tolist())) == batch and g.max() < ln
+        assert np.array_equal(g, O.sample_distinct(99, call, ln, batch))
+    env.close()
+
+
+def test_sampler_many_batches_device(qlb, O):
+    torch = pytest.importorskip("torch")
+    n_envs, batch, nb = 64, 32, 100
+    env = qlb.BreakoutEnvironment(n_envs=n_envs, seed=5, replay_capacity=n_envs * 64)
+    rb = qlb.ReplayBuffer(env)
+    env.step_many(np.zeros((2, n_envs), dtype=np.uint8))      # len = 128: collisions are frequent
+    idx = torch.empty((nb, batch), dtype=torch.int32, device="cuda")
+    rb.sample_device(batch, nb, 7, idx.data_ptr())
+    torch.cuda.synchronize()
+    got = idx.cpu().numpy().view(np.uint32)
+    for i in range(nb):
+        assert np.array_equal(got[i], O.sample_distinct(5, 7 + i, rb.len(), batch))
+    env.close()
+
+
+def test_full_size_properties(qlb, O):
+    """BASELINE configs[1] size (4,096 envs) with a 64-step replay: size-independent checks — a spot-checked subset
+    of envs against the oracle, frame-stack consistency between the env observation and the replay gather,
+    pixel value set, statistics identities."""
+    n, seed, T = 4096, 123, 96
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=seed, replay_capacity=n * 64)
+    rb = qlb.ReplayBuffer(env)
+    sub = np.arange(0, n, 97)
+    acts = np.empty((T, n), dtype=np.uint8)
+    lib = O.lib()
+    # actions: oracle stream on the spot-checked envs, cheap numpy stream elsewhere
+    acts[:] = np.random.default_rng(0).integers(0, 3, size=(T, n), dtype=np.uint8)
+    for e in sub:
+        for t in range(T):
+            acts[t, e] = lib.orc_synthetic_action(seed, int(e), t)
+    reward, done = env.step_many(acts)
+    # spot check vs oracle: env e of the GPU run == oracle env with global id e
+    for e in sub[:12]:
+        o = O.VecEnv(1, seed=seed, env_id_base=int(e))
+        for t in range(T):
+            r, d = o.step(acts[t, e:e + 1])
+            assert r[0] == reward[t, e] and d[0] == done[t, e]
+        so = o.state(); sg = env.read_state()
+        for k in STATE_F32 + STATE_INT:
+            assert so[k][0] == sg[k][e], (k, e)
+    obs = env.obs()
+    assert set(np.unique(obs).tolist()) <= {0, 96, 236, 255}
+    # the newest transition of every env: its state_next stack must equal the env's current observation unless the
+    # episode ended on that step (then the env has been reset and shows an empty stack)
+    ln = rb.len()
+    assert ln == n * 64
+    newest = np.arange(ln - n, ln, dtype=np.uint32)
+    g = rb.get_many(newest[:512], qlb.LAYOUT_U8_BHYX)
+    ended = (g.done != 0)
+    assert np.array_equal(g.state_next[~ended], obs[:512][~ended])
+    assert not obs[:512][ended].any()
+    assert np.array_equal(g.reward, reward[-1, :512]) and np.array_equal(g.done, done[-1, :512]) and np.array_equal(g.action, acts[-1, :512])
+    st = env.stats()
+    assert st["steps"] == n * T and st["episodes"] == int(done.sum())
+    assert st["sum_return"] + int(env.read_state()["score"].sum()) == int(reward.sum())
+    assert env.error_flags() == 0
+    env.close()
