@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json): Breakout env-steps/s
+(step + render + 84x84 u8 preprocess + 4-frame stack append + replay insert) and replay-sampled transitions/s.
+
+    python bench.py --gpus 1 --steps K --warmup W                  # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps K --warmup W # the restated reference CPU path (oracle)
+    torchrun ... bench.py --gpus N ...                             # one rank per GPU, env shards, no data-path collective
+
+One bench "step" = ONE launch of the fused kernel advancing every env of the shard by STEPS_PER_LAUNCH env-steps
+on a synthetic action stream (config.workload says which). Prints ONE JSON line (rank 0).
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+ENVS_PER_GPU = 4096            # BASELINE.json configs[1]
+STEPS_PER_LAUNCH = 64          # env-steps per env per launch: 4096*64*7056 B = 1.85 GB of frames per bench step (>> 126 MB L2)
+REPLAY_CAPACITY = 1 << 20      # 1M transitions (configs[2]) = 256 time steps of 4096 envs, 7.4 GB of frames
+BYTES_PER_ENV_STEP = 7154      # 7056 frame + 41+41 state + 1 action + 4 reward + 1 done + ~10 record
+BYTES_PER_SAMPLE_U8 = 91744    # 5 frames read + 2 x 4 frames written + 16 B scalars
+BYTES_PER_SAMPLE_F32 = 261088  # 5 frames read + 2 x 4 f32 frames written + 16 B scalars
+SEED = 20261018
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _ncu_traffic(kernel):
+    """dram bytes per launch from the committed ncu --set full capture, if one exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the GPU is under load (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, c[4:8]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path. The Rust crate cannot be built in this image
+    (no cargo/rustc; its renderer is unimplemented!()), so this times the oracle port on all host cores."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    sample_envs, sample_steps = ENVS_PER_GPU, 8            # bounded sample of one bench step: 4096 envs x 8 env-steps
+    for _ in range(args.warmup):
+        O.bench_env_steps(sample_envs, 2, SEED, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += O.bench_env_steps(sample_envs, sample_steps, SEED, cores)
+    units = sample_envs * sample_steps * args.steps
+    value = units / t
+    sample = "each step = %d envs x %d env-steps of the same workload (1/8 of a GPU bench step), %d OpenMP threads" % (sample_envs, sample_steps, cores)
+    line = {
+        "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "4096 Breakout envs: step+render+84x84 grayscale+4-frame stack+per-step state clone, random policy (CPU, oracle port of the reference path)",
+                   "envs": sample_envs, "steps_per_launch": sample_steps},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    q = importlib.import_module("q-learning_b200")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    n_envs, k_inner = args.envs, args.steps_per_launch
+    env = q.BreakoutEnvironment(n_envs=n_envs, seed=SEED, env_id_base=rank * n_envs, replay_capacity=args.replay_capacity, device=local_rank)
+    rb = q.ReplayBuffer(env)
+    gen = torch.Generator(device=dev); gen.manual_seed(SEED + rank)
+    actions = torch.randint(0, 3, (k_inner, n_envs), dtype=torch.uint8, device=dev, generator=gen)   # synthetic action stream, resident in HBM
+    reward = torch.empty((k_inner, n_envs), dtype=torch.float32, device=dev)
+    done = torch.empty((k_inner, n_envs), dtype=torch.uint8, device=dev)
+    stats_vec = torch.zeros(5, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def launch():
+        env.step_device(actions.data_ptr(), k_inner, reward.data_ptr(), done.data_ptr(), stream)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_stats():
+        """per-step-path-free episode-stat reduction: sum {return, episodes, steps}, max {-min, max} (NCCL)."""
+        env.stats_export(stats_vec.data_ptr(), stream)
+        if distributed:
+            a, b = stats_vec[:3].clone(), stats_vec[3:].clone()
+            dist.all_reduce(a, op=dist.ReduceOp.SUM); dist.all_reduce(b, op=dist.ReduceOp.MAX)
+            return torch.cat([a, b]).cpu().numpy()
+        return stats_vec.cpu().numpy()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        launch()
+    reduce_stats()
+    # ---- timed region: exactly K launches, device resident inputs ----
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        launch()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if distributed:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # keep the GPU loaded for the clock sampler if the timed region was short (untimed, same launches)
+    t_load = time.time()
+    while sampler and time.time() - t_load < 1.0:
+        for _ in range(20):
+            launch()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    stats = reduce_stats()
+
+    units_per_step = n_envs * k_inner * world
+    value = units_per_step * args.steps / (ms * 1e-3)
+
+    # ---- e2e: the same metric through the host-buffer C-ABI call (pinned staging, H2D actions, D2H reward+done) ----
+    a_host = actions.cpu().numpy()
+    e2e_steps = max(3, min(args.steps, 20))
+    env.step_many(a_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r_host, d_host = env.step_many(a_host)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if distributed:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_value = units_per_step * e2e_steps / dt
+
+    extra = {}
+    cpu_baseline = None
+    if rank == 0:
+        peak, peak_src = _peaks()
+        launch_ms = ms / args.steps
+        achieved = BYTES_PER_ENV_STEP * n_envs * k_inner / (launch_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "env_advance_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "peak_source": peak_src, "traffic": _ncu_traffic("env_advance_kernel"),
+                    "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n_envs * k_inner}
+        if not args.no_extra:
+            extra = measure_extras(q, torch, env, rb, dev, stream, peak)
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            O.build()
+            cores = os.cpu_count() or 1
+            s_envs, s_steps = n_envs, min(k_inner, 64)
+            secs = O.bench_env_steps(s_envs, s_steps, SEED, cores)
+            cpu_baseline = {"value": s_envs * s_steps / secs, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                            "sample": "one bench step on the CPU oracle: %d envs x %d env-steps, %d OpenMP threads, %.1f s" % (s_envs, s_steps, cores, secs)}
+        line = {
+            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%d Breakout envs per GPU: step+render+84x84 u8 frame+4-frame stack append+replay insert, %d env-steps per launch, uniform random action stream" % (n_envs, k_inner),
+                       "envs_per_gpu": n_envs, "steps_per_launch": k_inner, "replay_capacity": args.replay_capacity,
+                       "l2": "each step writes %.2f GB of frames (> 126 MB L2); ring of %.1f GB" % (n_envs * k_inner * 7056 / 1e9, (args.replay_capacity // n_envs + 4) * n_envs * 7056 / 1e9),
+                       "parallelism": "env-sharded x%d, no data-path collective" % world},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(a_host.nbytes), "d2h_bytes_per_step": int(r_host.nbytes + d_host.nbytes),
+                    "timing": "perf_counter around the synchronous host-buffer C-ABI call, max over ranks, %d steps" % e2e_steps},
+            "gpu_launches": args.steps,
+            "episode_stats": {"sum_return": float(stats[0]), "episodes": float(stats[1]), "env_steps": float(stats[2]),
+                              "min_return": -float(stats[3]), "max_return": float(stats[4]), "reduced_with": "nccl all_reduce" if distributed else "single rank"},
+            "env_error_flags": env.error_flags(),
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    env.close()
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure_extras(q, torch, env, rb, dev, stream, peak):
+    """Secondary numbers in the same run: replay sampling (configs[2]) and the 65,536-env shard (configs[3])."""
+    out = {}
+    per = 4 * 84 * 84
+    res = {}
+    for batch, n_batches in ((32, 1), (32, 256), (512, 16)):
+        for layout, name, bps, dt in ((q.LAYOUT_U8_BHYX, "u8", BYTES_PER_SAMPLE_U8, torch.uint8), (q.LAYOUT_F32_BXYH, "f32", BYTES_PER_SAMPLE_F32, torch.float32)):
+            n = batch * n_batches
+            idx = torch.empty((n,), dtype=torch.int32, device=dev)
+            st = torch.empty((n, per), dtype=dt, device=dev); nx = torch.empty((n, per), dtype=dt, device=dev)
+            r = torch.empty((n,), dtype=torch.float32, device=dev); a = torch.empty((n,), dtype=torch.uint8, device=dev); d = torch.empty((n,), dtype=torch.uint8, device=dev)
+
+            def once(c):
+                rb.sample_device(batch, n_batches, c, idx.data_ptr(), stream)
+                rb.gather_device(idx.data_ptr(), n, layout, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
+            for c in range(3):
+                once(c)
+            torch.cuda.synchronize()
+            reps = 30
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for c in range(reps):
+                once(10 + c)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            rate = n / (ms * 1e-3)
+            res["batch%d_x%d_%s" % (batch, n_batches, name)] = {
+                "transitions_per_sec": rate, "ms_per_call": ms, "achieved_gbs": rate * bps / 1e9, "frac_of_peak": rate * bps / 1e9 / peak,
+                "bytes_per_transition": bps, "kernels_per_call": 2}
+            del idx, st, nx
+    out["replay_sample"] = {"metric": "sampled_transitions_per_sec", "replay_len": rb.len(), "results": res,
+                            "note": "sample (Philox distinct ids) + gather (s and s' stacks) on device buffers; minibatches per call = the x factor"}
+    # 65,536 envs on this GPU (configs[3] shard size), 16 env-steps per launch
+    try:
+        big = q.BreakoutEnvironment(n_envs=65536, seed=SEED + 1, replay_capacity=65536 * 32, device=dev.index)
+        k = 16
+        acts = torch.randint(0, 3, (k, 65536), dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            big.step_device(acts.data_ptr(), k, None, None, stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            big.step_device(acts.data_ptr(), k, None, None, stream)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        rate = 65536 * k / (ms * 1e-3)
+        out["envs_65536"] = {"env_steps_per_sec": rate, "ms_per_launch": ms, "steps_per_launch": k, "achieved_gbs": rate * BYTES_PER_ENV_STEP / 1e9,
+                             "frac_of_peak": rate * BYTES_PER_ENV_STEP / 1e9 / peak}
+        big.close()
+    except Exception as ex:  # e.g. not enough free HBM next to the main shard
+        out["envs_65536"] = {"error": str(ex)}
+    # one env-step per launch (the learner-driven mode: actions depend on the previous state)
+    acts1 = torch.randint(0, 3, (1, env.n_envs), dtype=torch.uint8, device=dev)
+    for _ in range(10):
+        env.step_device(acts1.data_ptr(), 1, None, None, stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(500):
+        env.step_device(acts1.data_ptr(), 1, None, None, stream)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 500
+    out["single_step_launch"] = {"env_steps_per_sec": env.n_envs / (ms * 1e-3), "us_per_launch": ms * 1e3}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--steps-per-launch", type=int, default=STEPS_PER_LAUNCH)
+    ap.add_argument("--replay-capacity", type=int, default=REPLAY_CAPACITY)
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py: --gpus %d needs torchrun (one rank per GPU)" % args.gpus)
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,8 @@ struct DeviceStats {                      // order-independent accumulators
 
 struct StepParams {
     uint32_t n_envs, env_id_base, time_slots, max_episode_steps, auto_reset, n_steps;
+    uint32_t debug_skip;       // profiling aid (QLC_DEBUG_SKIP): 1 = no physics, 2 = no frame stores; 0 in production
+    uint32_t epc;              // envs per CTA (<= R*NE), chosen by the host so that the grid fills all SMs evenly
     uint64_t t0, seed;
     uint8_t* frames; uint32_t* records; DeviceStats* stats;
     const uint8_t* actions; float* reward; uint8_t* done;
@@ -122,84 +124,51 @@ __device__ __forceinline__ void build_raster_tables(RasterTables& T, int tid, in
     __syncthreads();
 }
 
-struct RenderRec { float cx, cy, pmin, pmax; uint64_t bricks; };
-
-// Draw one frame into a (clean) shared-memory frame buffer with one warp. Spec: DESIGN.md "Raster spec"
-// (bricks luma 96, ball ring luma 236, paddle luma 255; later overwrites earlier; pixel-centre coverage).
-__device__ __forceinline__ void draw_frame(uint8_t* buf, const RasterTables& T, const RenderRec& r, int lane, int& ball_i0, int& ball_j0) {
-    // bricks: 3 row patterns x 21 words, replicated over the rows of each brick row
-    uint32_t* wbuf = reinterpret_cast<uint32_t*>(buf);
-    for (int idx = lane; idx < 3 * (FRAME_W / 4); idx += 32) {
-        const int g = idx / (FRAME_W / 4), w = idx - g * (FRAME_W / 4);
-        const uint32_t m = (uint32_t)(r.bricks >> (20 * g)) & 0xFFFFFu;
-        const uint4 b = T.word_bits[w];
-        const uint32_t v = ((m & b.x) ? 96u : 0u) | ((m & b.y) ? 96u << 8 : 0u) | ((m & b.z) ? 96u << 16 : 0u) | ((m & b.w) ? 96u << 24 : 0u);
-        const int first = T.grp_first[g], count = T.grp_count[g];
-        for (int j = 0; j < count; ++j) wbuf[(first + j) * (FRAME_W / 4) + w] = v;
-    }
-    __syncwarp();
-    // ball: stroked circle, r_s = 10*84/600, stroke 2 px => (r_s-1)^2 <= d2 <= (r_s+1)^2
-    const float bx = scale84(r.cx), by = scale84(r.cy);
-    const float rs = scale84(BALL_R);
-    const float r_out = rs + 1.0f, r_in = rs - 1.0f;
-    const float out2 = r_out * r_out, in2 = r_in * r_in;
-    ball_i0 = (int)floorf(fminf(fmaxf(bx, -100.0f), 200.0f) - 2.9f);
-    ball_j0 = (int)floorf(fminf(fmaxf(by, -100.0f), 200.0f) - 2.9f);
-    for (int idx = lane; idx < 36; idx += 32) {
-        const int i = ball_i0 + idx % 6, j = ball_j0 + idx / 6;
-        if (i >= 0 && i < FRAME_W && j >= 0 && j < FRAME_H) {
-            const float dx = ((float)i + 0.5f) - bx, dy = ((float)j + 0.5f) - by;
-            const float d2 = dx * dx + dy * dy;
-            if (d2 <= out2 && d2 >= in2) buf[j * FRAME_W + i] = 236;
-        }
-    }
-    __syncwarp();
-    // paddle
-    const float x0 = scale84(r.pmin), x1 = scale84(r.pmax);
-    for (int i = lane; i < FRAME_W; i += 32) {
-        const float p = (float)i + 0.5f;
-        if (p >= x0 && p < x1)
-            for (int j = 0; j < T.pad_count; ++j) buf[(T.pad_first + j) * FRAME_W + i] = 255;
-    }
-}
-
-// Remove everything draw_frame wrote outside the brick band (the band is rewritten in full by the next draw).
-__device__ __forceinline__ void undraw_frame(uint8_t* buf, const RasterTables& T, int lane, int ball_i0, int ball_j0) {
-    for (int idx = lane; idx < 36; idx += 32) {
-        const int i = ball_i0 + idx % 6, j = ball_j0 + idx / 6;
-        if (i >= 0 && i < FRAME_W && j >= 0 && j < FRAME_H) buf[j * FRAME_W + i] = 0;
-    }
-    uint32_t* wbuf = reinterpret_cast<uint32_t*>(buf);
-    for (int idx = lane; idx < T.pad_count * (FRAME_W / 4); idx += 32) wbuf[T.pad_first * (FRAME_W / 4) + idx] = 0u;
-    __syncwarp();
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Kernel 1: env_advance — n_steps of {time_step, rasterise, frame-ring append, replay record} for 32 envs per CTA.
-//   warp 0        : physics, one lane per env, state in registers across all n_steps; publishes a 24-byte render
-//                   record per env and step into a D-deep shared-memory queue (mbarrier full/empty).
-//   warps 1..R    : rasterise into NB private shared-memory frame buffers each and push them to the HBM frame
-//                   ring with cp.async.bulk (UBLKCP), 7,056 contiguous bytes per frame.
-// ---------------------------------------------------------------------------------------------------------
-template <int R, int NB, int D>
-struct AdvanceSmem {
-    RasterTables tables;
-    RenderRec queue[D][ENVS_PER_CTA];
-    uint64_t full[D], empty[D];
-    int prev_ball[R][NB][2];
+// What a render warp needs to draw one frame; the scaled coordinates are computed once per env by the physics lane
+// (pos * 84 / 600, app_game_drawer.rs:21-36) instead of redundantly by all 32 lanes of a render warp.
+struct __align__(16) RenderRec {
+    float bx, by;        // ball centre, frame coordinates
+    float x0, x1;        // paddle [min.x, max.x), frame coordinates
+    uint64_t bricks;
+    int32_t box;         // top-left pixel of the 6x6 ball box: (j0 << 16) | (i0 & 0xFFFF)
+    uint32_t pad;
 };
 
-template <int R, int NB, int D>
+// ---------------------------------------------------------------------------------------------------------
+// Kernel 1: env_advance — n_steps of {time_step, rasterise, frame-ring append, replay record} for R*NE envs per CTA.
+//   warp 0     : physics, one lane per env, state in registers across all n_steps; publishes a 24-byte render
+//                record per env and step into a D-deep shared-memory queue (mbarrier full/empty).
+//   warps 1..R : each owns NE envs and ONE private 7,056-byte shared-memory frame per env that stays resident for
+//                the whole launch. Per step only what changed is redrawn (old ball box cleared, paddle row
+//                rewritten, ball drawn; the brick band only when a brick vanished or the ball left it), then the
+//                frame goes to the HBM frame ring as one cp.async.bulk (UBLKCP) of 7,056 contiguous bytes.
+// Raster spec: DESIGN.md "Raster spec" (bricks luma 96, ball ring luma 236, paddle luma 255; later overwrites
+// earlier; pixel-centre coverage) — identical pixels to drawing every frame from scratch.
+// ---------------------------------------------------------------------------------------------------------
+template <int D, int EPC_MAX>
+struct AdvanceSmem {
+    RasterTables tables;
+    RenderRec queue[D][EPC_MAX];
+    uint64_t full[D], empty[D];
+};
+
+template <int R, int NE, int D>
 __global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st, StepParams p) {
+    static_assert(R * NE <= ENVS_PER_CTA, "one physics lane per env");
+    const uint32_t EPC = p.epc;                       // envs per CTA (<= R*NE)
     extern __shared__ __align__(128) uint8_t dyn_smem[];
-    __shared__ AdvanceSmem<R, NB, D> S;
+    __shared__ AdvanceSmem<D, R * NE> S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t env0 = blockIdx.x * ENVS_PER_CTA;
-    const uint32_t n_here = min((uint32_t)ENVS_PER_CTA, p.n_envs - env0);
+    const uint32_t env0 = blockIdx.x * EPC;
+    const uint32_t n_here = min(EPC, p.n_envs - env0);
 
     if (tid == 0) {
         for (int q = 0; q < D; ++q) { mbar_init(&S.full[q], 1); mbar_init(&S.empty[q], R); }
         fence_mbar_init();
+    }
+    if (warp != 0) {   // zero the resident frames while the tables are being built
+        uint4* z = reinterpret_cast<uint4*>(dyn_smem + (size_t)(warp - 1) * NE * FRAME_BYTES);
+        for (int i = lane; i < NE * FRAME_VEC16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
     }
     build_raster_tables(S.tables, tid, blockDim.x);   // contains __syncthreads()
 
@@ -216,6 +185,7 @@ __global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st,
         } else {
             env_init(env, -0.25f); env.err = 0;
         }
+        MoveCache mc; move_cache_update(mc, env);
         uint32_t action = active ? p.actions[e] : 0u;
         for (uint32_t s = 0; s < p.n_steps; ++s) {
             const int q = s % D;
@@ -223,10 +193,14 @@ __global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st,
             if (active && s + 1 < p.n_steps) next_action = p.actions[(size_t)(s + 1) * p.n_envs + e];
             if (action >= 3u) { env.err |= ENVERR_ACTION; action = 0u; }
             const uint32_t score_before = env.score;
-            if (active) time_step(env, action);
+            if (active && p.debug_skip != 1u) time_step(env, action, mc);
             if (s >= (uint32_t)D) mbar_wait(&S.empty[q], ((s / D) - 1) & 1);
             if (active) {
-                RenderRec rr; rr.cx = env.cx; rr.cy = env.cy; rr.pmin = env.pmin; rr.pmax = env.pmax; rr.bricks = env.bricks;
+                RenderRec rr;
+                rr.bx = scale84(env.cx); rr.by = scale84(env.cy); rr.x0 = scale84(env.pmin); rr.x1 = scale84(env.pmax); rr.bricks = env.bricks;
+                const int i0 = (int)floorf(fminf(fmaxf(rr.bx, -100.0f), 200.0f) - 2.9f);   // ring radius 2.4 + half a pixel
+                const int j0 = (int)floorf(fminf(fmaxf(rr.by, -100.0f), 200.0f) - 2.9f);
+                rr.box = (j0 << 16) | (i0 & 0xFFFF); rr.pad = 0u;
                 S.queue[q][lane] = rr;
                 const uint32_t reward = env.score - score_before;
                 const bool done = env.finished;
@@ -245,6 +219,7 @@ __global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st,
                     atomicMax(&p.stats->max_return, env.score);
                     episode += 1;
                     env_init(env, reset_dir_x(p.seed, p.env_id_base + e, episode));
+                    move_cache_update(mc, env);
                     k = 0;
                 }
             }
@@ -261,40 +236,131 @@ __global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st,
     } else {
         // ------------------------------- render warps -------------------------------
         const int rw = warp - 1;
-        uint8_t* my_bufs = dyn_smem + (size_t)rw * NB * FRAME_BYTES;
-        {   // zero the private frame buffers once
-            uint4* z = reinterpret_cast<uint4*>(my_bufs);
-            for (int i = lane; i < NB * FRAME_VEC16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
-            __syncwarp();
-        }
-        uint32_t f = 0;   // frames drawn by this warp
+        const RasterTables& T = S.tables;
+        uint8_t* my_bufs = dyn_smem + (size_t)rw * NE * FRAME_BYTES;
+        // per-lane constants: which pixel(s) of a 6x6 ball box and which word(s) of the brick band this lane owns
+        const int bdi0 = lane % 6, bdj0 = lane / 6, bdi1 = (lane + 32) % 6, bdj1 = (lane + 32) / 6;   // 2nd only for lanes 0..3
+        constexpr int WPR = FRAME_W / 4;   // 21 words per pixel row
+        const int bg0 = lane / WPR, bw0 = lane % WPR, bg1 = (lane + 32) / WPR, bw1 = (lane + 32) % WPR;   // 2nd only for lanes 0..30
+        const int band_lo = T.grp_first[0], band_hi = T.grp_first[2] + T.grp_count[2] - 1;
+        const int pad_first = T.pad_first, pad_count = T.pad_count;
+        const float rs = scale84(BALL_R);
+        const float r_out = rs + 1.0f, r_in = rs - 1.0f;
+        const float out2 = r_out * r_out, in2 = r_in * r_in;
+        uint64_t prev_bricks[NE]; int prev_box[NE];
+        #pragma unroll
+        for (int i = 0; i < NE; ++i) { prev_bricks[i] = 0ull; prev_box[i] = (int)0x80008000u; }   // box far outside the frame
+
+        constexpr int G = NE >= 2 ? 2 : 1;          // bulk groups per step: one half drains while the other is drawn
+        constexpr int FPG = NE / G;                 // frames per group
+        static_assert(NE % G == 0, "NE must be 1 or even");
         for (uint32_t s = 0; s < p.n_steps; ++s) {
             const int q = s % D;
             mbar_wait(&S.full[q], (s / D) & 1);
-            const uint32_t slot = (uint32_t)((p.t0 + s) % p.time_slots);
-            uint8_t* slot_base = p.frames + ((size_t)slot * p.n_envs + env0) * FRAME_BYTES;
-            for (uint32_t j = rw; j < n_here; j += R) {
-                const RenderRec rr = S.queue[q][j];
-                const int b = f % NB;
-                uint8_t* buf = my_bufs + (size_t)b * FRAME_BYTES;
-                if (f >= (uint32_t)NB) {
-                    if (lane == 0) bulk_wait_read<NB - 1>();      // the store that last used this buffer has left smem
-                    __syncwarp();
-                    undraw_frame(buf, S.tables, lane, S.prev_ball[rw][b][0], S.prev_ball[rw][b][1]);
-                }
-                int bi0, bj0;
-                draw_frame(buf, S.tables, rr, lane, bi0, bj0);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    S.prev_ball[rw][b][0] = bi0; S.prev_ball[rw][b][1] = bj0;
-                    bulk_store(slot_base + (size_t)j * FRAME_BYTES, buf, FRAME_BYTES);
-                    bulk_commit();
-                }
-                ++f;
+            RenderRec rr[NE];
+            #pragma unroll
+            for (int i = 0; i < NE; ++i) {
+                const uint32_t j = (uint32_t)(i * R + rw);
+                if (j < n_here) rr[i] = S.queue[q][j];
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty[q]);
+            if (lane == 0) mbar_arrive(&S.empty[q]);      // records are in registers: hand the queue slot back early
+            const uint32_t slot = (uint32_t)((p.t0 + s) % p.time_slots);
+            uint8_t* slot_base = p.frames + ((size_t)slot * p.n_envs + env0) * FRAME_BYTES;
+            #pragma unroll
+            for (int g = 0; g < G; ++g) {
+                // this group's frames were last stored G groups ago: that store must have left shared memory
+                if (s > 0 && lane == 0) bulk_wait_read<G - 1>();
+                __syncwarp();
+                // ---- phase 1: clear the old ball boxes, rewrite the paddle rows, rewrite the brick band where needed ----
+                #pragma unroll
+                for (int f = 0; f < FPG; ++f) {
+                    const int i = g * FPG + f;
+                    const uint32_t j = (uint32_t)(i * R + rw);
+                    if (j < n_here) {
+                        uint8_t* buf = my_bufs + (size_t)i * FRAME_BYTES;
+                        uint32_t* wbuf = reinterpret_cast<uint32_t*>(buf);
+                        const int pi0 = (int)(short)(prev_box[i] & 0xFFFF), pj0 = prev_box[i] >> 16;
+                        // old ball pixels outside the paddle rows (rewritten below) and outside the brick rows (the band
+                        // is rewritten whenever the old box touched it)
+                        {
+                            int x = pi0 + bdi0, y = pj0 + bdj0;
+                            if (x >= 0 && x < FRAME_W && y >= 0 && y < FRAME_H && !T.row_pad[y] && T.row_grp[y] < 0) buf[y * FRAME_W + x] = 0;
+                            if (lane < 4) {
+                                x = pi0 + bdi1; y = pj0 + bdj1;
+                                if (x >= 0 && x < FRAME_W && y >= 0 && y < FRAME_H && !T.row_pad[y] && T.row_grp[y] < 0) buf[y * FRAME_W + x] = 0;
+                            }
+                        }
+                        // paddle row(s): every word rewritten (255 inside [x0, x1), else 0)
+                        if (lane < WPR) {
+                            const float x0 = rr[i].x0, x1 = rr[i].x1;
+                            uint32_t v = 0u;
+                            #pragma unroll
+                            for (int b = 0; b < 4; ++b) { const float pc = (float)(4 * lane + b) + 0.5f; if (pc >= x0 && pc < x1) v |= 255u << (8 * b); }
+                            for (int r = 0; r < pad_count; ++r) wbuf[(pad_first + r) * WPR + lane] = v;
+                        }
+                        // brick band: 3 row patterns x 21 words, replicated over the pixel rows of each brick row
+                        const uint64_t bricks = rr[i].bricks;
+                        if ((bricks != prev_bricks[i]) || (pj0 + 5 >= band_lo && pj0 <= band_hi)) {
+                            {
+                                const uint32_t m = (uint32_t)(bricks >> (20 * bg0)) & 0xFFFFFu;
+                                const uint4 b = T.word_bits[bw0];
+                                const uint32_t v = ((m & b.x) ? 96u : 0u) | ((m & b.y) ? 96u << 8 : 0u) | ((m & b.z) ? 96u << 16 : 0u) | ((m & b.w) ? 96u << 24 : 0u);
+                                const int first = T.grp_first[bg0], count = T.grp_count[bg0];
+                                for (int r = 0; r < count; ++r) wbuf[(first + r) * WPR + bw0] = v;
+                            }
+                            if (lane < 3 * WPR - 32) {
+                                const uint32_t m = (uint32_t)(bricks >> (20 * bg1)) & 0xFFFFFu;
+                                const uint4 b = T.word_bits[bw1];
+                                const uint32_t v = ((m & b.x) ? 96u : 0u) | ((m & b.y) ? 96u << 8 : 0u) | ((m & b.z) ? 96u << 16 : 0u) | ((m & b.w) ? 96u << 24 : 0u);
+                                const int first = T.grp_first[bg1], count = T.grp_count[bg1];
+                                for (int r = 0; r < count; ++r) wbuf[(first + r) * WPR + bw1] = v;
+                            }
+                        }
+                        prev_bricks[i] = bricks; prev_box[i] = rr[i].box;
+                    }
+                }
+                __syncwarp();
+                // ---- phase 2: ball ring on top of bricks, under the paddle ----
+                #pragma unroll
+                for (int f = 0; f < FPG; ++f) {
+                    const int i = g * FPG + f;
+                    const uint32_t j = (uint32_t)(i * R + rw);
+                    if (j < n_here) {
+                        uint8_t* buf = my_bufs + (size_t)i * FRAME_BYTES;
+                        const float bx = rr[i].bx, by = rr[i].by, x0 = rr[i].x0, x1 = rr[i].x1;
+                        const int i0 = (int)(short)(rr[i].box & 0xFFFF), j0 = rr[i].box >> 16;
+                        int x = i0 + bdi0, y = j0 + bdj0;
+                        if (x >= 0 && x < FRAME_W && y >= 0 && y < FRAME_H) {
+                            const float px = (float)x + 0.5f, dx = px - bx, dy = ((float)y + 0.5f) - by;
+                            const float d2 = dx * dx + dy * dy;
+                            if (d2 <= out2 && d2 >= in2 && !(T.row_pad[y] && px >= x0 && px < x1)) buf[y * FRAME_W + x] = 236;
+                        }
+                        if (lane < 4) {
+                            x = i0 + bdi1; y = j0 + bdj1;
+                            if (x >= 0 && x < FRAME_W && y >= 0 && y < FRAME_H) {
+                                const float px = (float)x + 0.5f, dx = px - bx, dy = ((float)y + 0.5f) - by;
+                                const float d2 = dx * dx + dy * dy;
+                                if (d2 <= out2 && d2 >= in2 && !(T.row_pad[y] && px >= x0 && px < x1)) buf[y * FRAME_W + x] = 236;
+                            }
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                // ---- the group's frames leave as one bulk group (committed even when empty, so the count stays uniform) ----
+                if (lane == 0) {
+                    if (p.debug_skip != 2u) {
+                        #pragma unroll
+                        for (int f = 0; f < FPG; ++f) {
+                            const int i = g * FPG + f;
+                            const uint32_t j = (uint32_t)(i * R + rw);
+                            if (j < n_here) bulk_store(slot_base + (size_t)j * FRAME_BYTES, my_bufs + (size_t)i * FRAME_BYTES, FRAME_BYTES);
+                        }
+                    }
+                    bulk_commit();
+                }
+            }
         }
         if (lane == 0) bulk_wait<0>();
     }

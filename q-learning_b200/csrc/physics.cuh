@@ -196,11 +196,13 @@ struct Candidates {
     }
 };
 
-// proceed_ball_with (mechanics.rs:137-184) without recursion.
-__device__ __forceinline__ void advance_ball(Env& e, float mvx, float mvy) {
+// proceed_ball_with (mechanics.rs:137-184) without recursion. len0 = |mv| of the first leg (cached by the caller:
+// it is a pure function of the direction). Returns true when the direction changed (a reflection happened).
+__device__ __forceinline__ bool advance_ball(Env& e, float mvx, float mvy, float len0) {
+    bool bounced = false;
     for (int bounce = 0;; ++bounce) {
-        const float len_mv = length2(mvx, mvy);
-        if (len_mv < SPACE_GRANULARITY) return;
+        const float len_mv = bounce == 0 ? len0 : length2(mvx, mvy);
+        if (len_mv < SPACE_GRANULARITY) return bounced;
         Candidates cs; cs.n = 0;
         Surface s;
         // walls (mechanics.rs:260-315), insertion order left, right, top
@@ -228,13 +230,19 @@ __device__ __forceinline__ void advance_ball(Env& e, float mvx, float mvy) {
                 s.way = length2(mvx * f, mvy * f); s.approx = 0.0f; s.nx = 0.0f; s.ny = 1.0f; cs.push(s, -1, e.err);
             }
         }
-        // paddle
-        if (sweep_ball_box(e.cx, e.cy, BALL_R, mvx, mvy, len_mv, (e.pmin + e.pmax) / 2.0f, (PAD_MIN_Y + PAD_MAX_Y) / 2.0f,
-                           (e.pmax - e.pmin) / 2.0f, (PAD_MAX_Y - PAD_MIN_Y) / 2.0f, s, e.err))
-            cs.push(s, -1, e.err);
+        // paddle: the sweep starts with a contact query at the end point, which answers None unless that point is
+        // within r + prediction (10.8) of the box — skip the query when it is not even within 11.5
+        {
+            const float ex = e.cx + mvx, ey = e.cy + mvy;
+            if (ey > PAD_MIN_Y - 11.5f && ey < PAD_MAX_Y + 11.5f && ex > e.pmin - 11.5f && ex < e.pmax + 11.5f) {
+                if (sweep_ball_box(e.cx, e.cy, BALL_R, mvx, mvy, len_mv, (e.pmin + e.pmax) / 2.0f, (PAD_MIN_Y + PAD_MAX_Y) / 2.0f,
+                                   (e.pmax - e.pmin) / 2.0f, (PAD_MAX_Y - PAD_MIN_Y) / 2.0f, s, e.err))
+                    cs.push(s, -1, e.err);
+            }
+        }
         // bricks: only the grid cells whose box, grown by r + prediction (+ slack), contains the end point can
         // return a contact at all; every other brick answers None in the reference too.
-        {
+        if (e.cy + mvy < 126.0f) {     // lowest brick edge 114 + 11.x
             const float ex = e.cx + mvx, ey = e.cy + mvy;
             int k0 = (int)ceilf((ex - 66.0f) / 27.0f), k1 = (int)floorf((ex - 19.0f) / 27.0f);
             int r0 = (int)ceilf((ey - 71.0f) / 27.0f), r1 = (int)floorf((ey - 24.0f) / 27.0f);
@@ -249,7 +257,7 @@ __device__ __forceinline__ void advance_ball(Env& e, float mvx, float mvy) {
                     }
                 }
         }
-        if (cs.n == 0) { e.cx = e.cx + mvx; e.cy = e.cy + mvy; return; }
+        if (cs.n == 0) { e.cx = e.cx + mvx; e.cy = e.cy + mvy; return bounced; }
 
         // ContactCandidates::consider (:496-516): the surviving set is {way+approx <= min + 0.001}, insertion order kept
         float way, nx, ny;
@@ -278,14 +286,24 @@ __device__ __forceinline__ void advance_ball(Env& e, float mvx, float mvy) {
         float rx = e.dx - nx * f, ry = e.dy - ny * f;
         normalize2(rx, ry);
         e.cx = ncx; e.cy = ncy; e.dx = rx; e.dy = ry;
+        bounced = true;
         mvx = rx * remaining; mvy = ry * remaining;
-        if (!(length2(mvx, mvy) > 0.0f)) return;
-        if (bounce >= MAX_REFLECTIONS) { e.err |= ENVERR_RECURSION; return; }
+        if (!(length2(mvx, mvy) > 0.0f)) return bounced;
+        if (bounce >= MAX_REFLECTIONS) { e.err |= ENVERR_RECURSION; return bounced; }
     }
 }
 
+// Ball::move_vector (:258): ((normalized(dir) * speed) * dt) and its length — pure functions of the direction, so they
+// are cached in registers and recomputed only after a reflection or a reset (bit-identical to recomputing each step).
+struct MoveCache { float mvx, mvy, len; };
+__device__ __forceinline__ void move_cache_update(MoveCache& m, const Env& e) {
+    float ux = e.dx, uy = e.dy; normalize2(ux, uy);
+    m.mvx = ux * BALL_SPEED * DT; m.mvy = uy * BALL_SPEED * DT;
+    m.len = length2(m.mvx, m.mvy);
+}
+
 // BreakoutMechanics::time_step (mechanics.rs:119-129)
-__device__ __forceinline__ void time_step(Env& e, uint32_t action) {
+__device__ __forceinline__ void time_step(Env& e, uint32_t action, MoveCache& mc) {
     // Panel::proceed (:571-587) with the speed chosen on the previous step
     {
         const float d = e.pspeed * DT;
@@ -294,11 +312,7 @@ __device__ __forceinline__ void time_step(Env& e, uint32_t action) {
         else if (nmax >= GRID_X) { const float s = GRID_X - nmax; e.pmin = nmin + s; e.pmax = nmax + s; e.pspeed = 0.0f; }
         else { e.pmin = nmin; e.pmax = nmax; }
     }
-    // Ball::move_vector (:258): ((normalized * speed) * dt)
-    {
-        float ux = e.dx, uy = e.dy; normalize2(ux, uy);
-        advance_ball(e, ux * BALL_SPEED * DT, uy * BALL_SPEED * DT);
-    }
+    if (advance_ball(e, mc.mvx, mc.mvy, mc.len)) move_cache_update(mc, e);
     if (e.cy >= PAD_MAX_Y || e.bricks == 0ull) e.finished = true;               // :131-135
     if (!e.finished) {                                                           // Panel::process_input :553-566
         const float v = e.pspeed;

@@ -38,7 +38,10 @@ struct qlc_env {
     void* dev_stage = nullptr; size_t dev_stage_bytes = 0;
     // episode reward window (replay_buffer.rs:100-124) — host side, fed by the caller like the reference
     std::deque<float> window;
-    int advance_cfg = 0;
+    int advance_cfg = 0;                       // QLC_ADVANCE_CFG: force a CTA shape (0 = auto)
+    int epc_override = 0;                      // QLC_EPC: force envs per CTA (0 = auto)
+    int sm_count = 148;
+    int debug_skip = 0;                        // QLC_DEBUG_SKIP (profiling aid)
     std::vector<void*> allocs;
 };
 
@@ -119,6 +122,9 @@ int32_t qlc_env_create(const qlc_config* cfg, qlc_env** out) {
     env->t_cap = (uint32_t)t_cap;
     env->time_slots = env->t_cap + 4;
     if (const char* c = getenv("QLC_ADVANCE_CFG")) env->advance_cfg = atoi(c);
+    if (const char* c = getenv("QLC_EPC")) env->epc_override = atoi(c);
+    if (const char* c = getenv("QLC_DEBUG_SKIP")) env->debug_skip = atoi(c);
+    env->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
 
 #define TRY_ALLOC(x) do { rc = (x); if (rc) { qlc_env_destroy(env); return rc; } } while (0)
     TRY_ALLOC(dev_alloc(env, &env->st.ball_cx, n, false));
@@ -187,16 +193,27 @@ int32_t qlc_env_reset(qlc_env* env, const uint8_t* mask_host, const float* dir_x
 
 }  // extern "C"
 
-template <int R, int NB, int D>
-static int32_t launch_advance(qlc_env* env, const StepParams& p, cudaStream_t s) {
+// Grid shaping (measured on B200, profiles/r01_notes.md): up to one wave of 32-env CTAs the fastest split is full
+// 32-env CTAs (1 per SM, 32 resident frames); shards too small to give every SM 16 envs are spread evenly instead;
+// larger shards use 8-env CTAs, several resident per SM, so that prologues/tails of different CTAs overlap.
+static uint32_t pick_epc(uint32_t n_envs, uint32_t sms, uint32_t max_epc) {
+    if (n_envs >= sms * (max_epc / 2)) return max_epc;
+    uint32_t epc = (n_envs + sms - 1) / sms;
+    return epc < 1 ? 1 : epc;
+}
+
+template <int R, int NE, int D>
+static int32_t launch_advance(qlc_env* env, StepParams& p, cudaStream_t s) {
     static bool configured[64] = {};
-    const size_t dyn = (size_t)R * NB * FRAME_BYTES;
-    auto kern = env_advance_kernel<R, NB, D>;
+    const size_t dyn = (size_t)R * NE * FRAME_BYTES;
+    auto kern = env_advance_kernel<R, NE, D>;
     if (!configured[env->cfg.device & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         configured[env->cfg.device & 63] = true;
     }
-    const uint32_t grid = (p.n_envs + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
+    p.epc = env->epc_override ? (uint32_t)env->epc_override : pick_epc(p.n_envs, (uint32_t)env->sm_count, R * NE);
+    if (p.epc > (uint32_t)(R * NE)) p.epc = R * NE;
+    const uint32_t grid = (p.n_envs + p.epc - 1) / p.epc;
     kern<<<grid, 32 * (R + 1), dyn, s>>>(env->st, p);
     CUDA_TRY(cudaGetLastError());
     return QLC_OK;
@@ -213,13 +230,18 @@ int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps,
     p.max_episode_steps = env->cfg.max_episode_steps; p.auto_reset = env->cfg.auto_reset; p.n_steps = n_steps;
     p.t0 = env->t; p.seed = env->cfg.seed; p.frames = env->frames; p.records = env->records; p.stats = env->stats;
     p.actions = actions_dev; p.reward = reward_dev; p.done = done_dev;
+    p.debug_skip = (uint32_t)env->debug_skip;
     cudaStream_t s = (cudaStream_t)stream;
-    switch (env->advance_cfg) {
-        case 1: rc = launch_advance<4, 2, 2>(env, p, s); break;
-        case 2: rc = launch_advance<4, 4, 2>(env, p, s); break;
-        case 3: rc = launch_advance<7, 2, 2>(env, p, s); break;
-        case 4: rc = launch_advance<8, 3, 2>(env, p, s); break;
-        default: rc = launch_advance<8, 2, 2>(env, p, s); break;
+    int cfg = env->advance_cfg;
+    if (cfg == 0) cfg = (p.n_envs <= (uint32_t)env->sm_count * 32u) ? 1 : 5;
+    switch (cfg) {
+        case 1: rc = launch_advance<8, 4, 4>(env, p, s); break;    // <= 32 envs / CTA, 1 CTA / SM
+        case 2: rc = launch_advance<8, 2, 2>(env, p, s); break;    // <= 16 envs / CTA, 2 CTAs / SM
+        case 3: rc = launch_advance<4, 4, 4>(env, p, s); break;    // <= 16 envs / CTA, fewer warps
+        case 4: rc = launch_advance<4, 2, 4>(env, p, s); break;    // <=  8 envs / CTA
+        case 5: rc = launch_advance<8, 1, 4>(env, p, s); break;    // <=  8 envs / CTA, 3 CTAs / SM
+        case 6: rc = launch_advance<16, 2, 4>(env, p, s); break;   // <= 32 envs / CTA, 16 render warps
+        default: return fail(QLC_ERR_INVALID_ARG, "unknown QLC_ADVANCE_CFG");
     }
     if (rc) return rc;
     env->t += n_steps;

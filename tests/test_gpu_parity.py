@@ -93,6 +93,28 @@ def test_trajectory_parity(qlb, O, n_envs, chunks, seed):
     env.close()
 
 
+@pytest.mark.parametrize("cfg,epc", [(1, 0), (2, 0), (3, 0), (4, 0), (5, 0), (6, 0), (1, 28), (1, 5), (2, 13), (6, 31), (5, 1)])
+def test_all_kernel_shapes_agree(qlb, O, cfg, epc, monkeypatch):
+    """Every instantiated CTA shape of the fused kernel (render warps x resident frames per warp) and any
+    envs-per-CTA split gives the same bits."""
+    monkeypatch.setenv("QLC_ADVANCE_CFG", str(cfg))
+    monkeypatch.setenv("QLC_EPC", str(epc))
+    n, seed = 77, 31
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=seed, replay_capacity=n * 8)
+    ora = O.VecEnv(n, seed=seed)
+    t = 0
+    for k in (1, 1, 2, 37, 150):
+        acts = O.synthetic_actions(seed, 0, n, t, k)
+        reward, done = env.step_many(acts)
+        for s in range(k):
+            r, d = ora.step(acts[s])
+            assert np.array_equal(r, reward[s]) and np.array_equal(d, done[s])
+        t += k
+        assert np.array_equal(env.obs(qlb.LAYOUT_U8_BHYX), ora.obs_u8()), "frame stacks differ at t=%d (cfg %d)" % (t, cfg)
+    _assert_state_equal(env.read_state(), ora.state(), "cfg %d" % cfg)
+    env.close()
+
+
 def test_skilled_play_hits_many_bricks(qlb, O):
     """A paddle that tracks the ball keeps episodes alive for thousands of steps: bounces off paddle, walls and
     bricks (multi-contact, bisection paths) must stay bit-identical."""
