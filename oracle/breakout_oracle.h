@@ -97,6 +97,7 @@ typedef struct {
     uint32_t episode;        /* episodes started so far - 1 */
     uint32_t episode_step;   /* steps taken in the current episode */
     float    episode_return;
+    uint32_t sticky_err;     /* OR of the error flags of all finished episodes (mechanics.err restarts at 0) */
 } orc_env;
 
 void  orc_env_reset_with(orc_env* e, float dir_x);                          /* breakout_environment.rs:177-180 */

@@ -75,6 +75,7 @@ void orc_frame_ring_add(orc_frame_ring* r, const uint8_t* frame) {
 }
 
 void orc_env_reset_with(orc_env* e, float dir_x) {
+    e->sticky_err |= e->state.mechanics.err;
     orc_mechanics_new(&e->state.mechanics, dir_x);
     orc_frame_ring_new(&e->state.frame_buffer);
     e->episode_step = 0;

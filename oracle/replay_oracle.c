@@ -235,7 +235,7 @@ void orc_vec_read_state(const orc_vec* v, float* ball_cx, float* ball_cy, float*
         ball_dx[e] = m->ball_direction.x; ball_dy[e] = m->ball_direction.y;
         pad_min_x[e] = m->panel_shape.min.x; pad_max_x[e] = m->panel_shape.max.x; pad_speed[e] = m->panel_speed_per_sec;
         bricks[e] = orc_mechanics_brick_mask(m); score[e] = m->score; finished[e] = (uint8_t)m->finished;
-        episode_step[e] = v->envs[e].episode_step; err[e] = m->err;
+        episode_step[e] = v->envs[e].episode_step; err[e] = m->err | v->envs[e].sticky_err;
     }
 }
 /* current observation stacks, u8 [n][4][84][84] slot-indexed */

@@ -488,6 +488,12 @@ __global__ void __launch_bounds__(32) gather_u8_kernel(GatherParams g) {
     if (lane == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     fence_proxy_async_smem();
     __syncwarp();
+    if (lane == 0 && !g.out_state && !g.out_next) {      // scalars only (get_many without tensorisation)
+        if (g.reward) g.reward[b] = (float)((rec >> 8) & 0xFFu);
+        if (g.action) g.action[b] = (uint8_t)(rec & 3u);
+        if (g.done) g.done[b] = (uint8_t)((rec >> 2) & 1u);
+        return;
+    }
     if (lane == 0) {
         const int d_lo = g.out_next ? 0 : 1, d_hi = g.out_state ? 4 : 3;
         uint32_t bytes = 0;

@@ -316,3 +316,116 @@ def test_full_size_properties(qlb, O):
     assert st["sum_return"] + int(env.read_state()["score"].sum()) == int(reward.sum())
     assert env.error_flags() == 0
     env.close()
+
+
+# ---- committed golden fixtures (tests/golden/oracle_trace_v1.json) straight against the CUDA path ----
+import hashlib
+import json
+import os
+
+_GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_trace_v1.json")))
+_GKEYS = ("ball_cx", "ball_cy", "ball_dx", "ball_dy", "pad_min_x", "pad_max_x", "pad_speed", "bricks", "score", "episode_step")
+
+
+def test_golden_single_env_10k(qlb, O):
+    """BASELINE configs[0]: single env, fixed seed, random policy, 10k steps — per-step state bits, frame stacks and
+    reward/done hashed exactly like tests/golden/make_golden.py did with the oracle."""
+    g = _GOLD["single_env_10k"]
+    env = qlb.BreakoutEnvironment(n_envs=1, seed=g["seed"])
+    acts = O.synthetic_actions(g["seed"], 0, 1, 0, g["steps"])
+    hs, hf, hr = hashlib.sha256(), hashlib.sha256(), hashlib.sha256()
+    for t in range(g["steps"]):
+        _, r, d = env.step(acts[t])
+        hr.update(r.tobytes()); hr.update(d.tobytes())
+        st = env.read_state()
+        for k in _GKEYS:
+            hs.update(st[k].tobytes())
+        hf.update(env.obs(qlb.LAYOUT_U8_BHYX).tobytes())
+    assert hr.hexdigest() == g["sha256_reward_done_every_step"]
+    assert hs.hexdigest() == g["sha256_state_bits_every_step"]
+    assert hf.hexdigest() == g["sha256_obs_u8_every_step"]
+    s = env.stats()
+    assert float(s["episodes"]) == g["stats"]["episodes"] and float(s["sum_return"]) == g["stats"]["sum_return"]
+    env.close()
+
+
+def test_golden_multi_env_replay(qlb, O):
+    g = _GOLD["multi_env_replay"]
+    env = qlb.BreakoutEnvironment(n_envs=g["n_envs"], seed=g["seed"], replay_capacity=g["replay_capacity"])
+    rb = qlb.ReplayBuffer(env)
+    acts = O.synthetic_actions(g["seed"], 0, g["n_envs"], 0, g["steps"])
+    env.step_many(acts)
+    r = g["replay"]
+    assert rb.len() == r["len"]
+    idx = rb.generate_distinct_random_ids(32, 0)
+    assert [int(x) for x in idx] == r["indices_call0_batch32"]
+    got = rb.get_many(idx, qlb.LAYOUT_U8_BHYX)
+    assert hashlib.sha256(got.state.tobytes()).hexdigest() == r["sha256_state_u8"]
+    assert hashlib.sha256(got.state_next.tobytes()).hexdigest() == r["sha256_next_u8"]
+    assert [float(x) for x in got.reward] == r["reward"] and [int(x) for x in got.action] == r["action"] and [int(x) for x in got.done] == r["done"]
+    assert hashlib.sha256(rb.get_many(idx, qlb.LAYOUT_F32_BXYH).state.tobytes()).hexdigest() == r["sha256_state_f32"]
+    st = env.read_state()
+    for k in _GKEYS:
+        bits = st[k].view(np.uint32 if st[k].dtype == np.float32 else st[k].dtype)
+        assert [int(x) for x in bits] == g["checkpoints"][str(g["steps"])][k], k
+    env.close()
+
+
+def test_golden_tracking_policy(qlb):
+    """Skilled play (returns up to 20+ per episode) against the golden hashes — no oracle involved at run time: the
+    policy reads the GPU state, so any divergence changes the action stream hash as well."""
+    g = _GOLD["tracking_policy"]
+    n = g["n_envs"]
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=g["seed"])
+    hs, ha, hf = hashlib.sha256(), hashlib.sha256(), hashlib.sha256()
+    st = env.read_state()
+    for t in range(g["steps"]):
+        centre = (st["pad_min_x"] + st["pad_max_x"]) / 2
+        off = (((np.arange(n) * 37 + t * 11) % 51) - 25).astype(np.float32)
+        target = st["ball_cx"] + off
+        a = np.where(target < centre - 4, 1, np.where(target > centre + 4, 2, 0)).astype(np.uint8)
+        ha.update(a.tobytes())
+        env.step(a)
+        st = env.read_state()
+        for k in _GKEYS:
+            hs.update(st[k].tobytes())
+        if t % 16 == 15:
+            hf.update(env.obs(qlb.LAYOUT_U8_BHYX).tobytes())
+    assert ha.hexdigest() == g["sha256_actions"]
+    assert hs.hexdigest() == g["sha256_state_bits_every_step"]
+    assert hf.hexdigest() == g["sha256_obs_u8_every_16_steps"]
+    assert [int(x) for x in st["score"]] == g["final_score"] and [int(x) for x in st["bricks"]] == g["final_bricks"]
+    s = env.stats()
+    assert float(s["episodes"]) == g["stats"]["episodes"] and float(s["sum_return"]) == g["stats"]["sum_return"]
+    assert float(s["min_return"]) == g["stats"]["min_return"] and float(s["max_return"]) == g["stats"]["max_return"]
+    env.close()
+
+
+def test_rare_events_parity(qlb, O):
+    """~3e8 env-steps of random play on the GPU; every env whose sticky error flags fired (situations in which the
+    reference would panic or recurse without bound: mechanics.rs:265,284,303,361-389) is replayed from t = 0 on the
+    oracle with the same action history and must agree bit for bit, flags included. Also replays unflagged envs."""
+    n, chunk, n_chunks, seed = 16384, 500, 40, 4242
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=seed)
+    rng = np.random.default_rng(99)
+    history = []
+    for _ in range(n_chunks):
+        a = rng.integers(0, 3, size=(chunk, n), dtype=np.uint8)
+        # a sideways-sweeping paddle makes the rare paddle/ball side hits much more likely
+        a[:, : n // 2] = np.where(rng.random((chunk, n // 2)) < 0.85, (np.arange(chunk)[:, None] // 40 % 2 + 1), a[:, : n // 2]).astype(np.uint8)
+        history.append(a)
+        env.step_many(a)
+    st = env.read_state()
+    flagged = np.nonzero(st["err"])[0]
+    print("flagged envs: %d of %d after %d steps; flags OR = %d" % (flagged.size, n, chunk * n_chunks, int(np.bitwise_or.reduce(st["err"]))))
+    pick = list(flagged[:6]) + [0, 1, n // 2, n - 1]
+    acts = np.concatenate(history, axis=0)
+    for e in pick:
+        o = O.VecEnv(1, seed=seed, env_id_base=int(e))
+        for t in range(acts.shape[0]):
+            o.step(acts[t, e:e + 1])
+        so = o.state()
+        for k in STATE_F32 + STATE_INT + ("err",):
+            assert so[k][0] == st[k][e] or (so[k][0] != so[k][0] and st[k][e] != st[k][e]), (k, int(e), so[k][0], st[k][e])
+        o.close()
+    env.close()
