@@ -144,11 +144,14 @@ def run_b200(args, rank, local_rank, world):
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if not os.environ.get("QLC_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
     n_envs, k_inner = args.envs, args.steps_per_launch
-    env = q.BreakoutEnvironment(n_envs=n_envs, seed=SEED, env_id_base=rank * n_envs, replay_capacity=args.replay_capacity, device=local_rank)
+    env = q.BreakoutEnvironment(n_envs=n_envs, seed=SEED, env_id_base=rank * n_envs,   # = sharding.shard_range(rank, world, world * n_envs)[0]
+                                replay_capacity=args.replay_capacity, device=local_rank)
     rb = q.ReplayBuffer(env)
     gen = torch.Generator(device=dev); gen.manual_seed(SEED + rank)
     actions = torch.randint(0, 3, (k_inner, n_envs), dtype=torch.uint8, device=dev, generator=gen)   # synthetic action stream, resident in HBM
@@ -165,14 +168,12 @@ def run_b200(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sharding = importlib.import_module("q-learning_b200.sharding")
+
     def reduce_stats():
-        """per-step-path-free episode-stat reduction: sum {return, episodes, steps}, max {-min, max} (NCCL)."""
+        """episode-stat reduction, off the step path: sum {return, episodes, steps}, max {-min, max} over ranks (NCCL)."""
         env.stats_export(stats_vec.data_ptr(), stream)
-        if distributed:
-            a, b = stats_vec[:3].clone(), stats_vec[3:].clone()
-            dist.all_reduce(a, op=dist.ReduceOp.SUM); dist.all_reduce(b, op=dist.ReduceOp.MAX)
-            return torch.cat([a, b]).cpu().numpy()
-        return stats_vec.cpu().numpy()
+        return sharding.reduce_episode_stats(stats_vec, dist if distributed else None)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -206,13 +207,17 @@ def run_b200(args, rank, local_rank, world):
     value = units_per_step * args.steps / (ms * 1e-3)
 
     # ---- e2e: the same metric through the host-buffer C-ABI call (pinned staging, H2D actions, D2H reward+done) ----
-    a_host = actions.cpu().numpy()
-    e2e_steps = max(3, min(args.steps, 20))
-    env.step_many(a_host)
+    # Every step copies that step's actions host->device from page-locked memory and reads reward + done back.
+    pa, pr, pd = q.PinnedArray((k_inner, n_envs), np.uint8), q.PinnedArray((k_inner, n_envs), np.float32), q.PinnedArray((k_inner, n_envs), np.uint8)
+    pa.array[:] = actions.cpu().numpy()
+    a_host, r_host, d_host = pa.array, pr.array, pd.array
+    e2e_steps = max(3, min(args.steps, 50))
+    for _ in range(3):
+        env.step_many(a_host, out=(r_host, d_host))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        r_host, d_host = env.step_many(a_host)
+        env.step_many(a_host, out=(r_host, d_host))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if distributed:
@@ -220,6 +225,8 @@ def run_b200(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     e2e_value = units_per_step * e2e_steps / dt
+    e2e_bytes = (int(a_host.nbytes), int(r_host.nbytes + d_host.nbytes))
+    e2e_check = float(r_host.sum())          # the read-back result is consumed on the host
 
     extra = {}
     cpu_baseline = None
@@ -249,11 +256,11 @@ def run_b200(args, rank, local_rank, world):
                        "l2": "each step writes %.2f GB of frames (> 126 MB L2); ring of %.1f GB" % (n_envs * k_inner * 7056 / 1e9, (args.replay_capacity // n_envs + 4) * n_envs * 7056 / 1e9),
                        "parallelism": "env-sharded x%d, no data-path collective" % world},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(a_host.nbytes), "d2h_bytes_per_step": int(r_host.nbytes + d_host.nbytes),
-                    "timing": "perf_counter around the synchronous host-buffer C-ABI call, max over ranks, %d steps" % e2e_steps},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": e2e_bytes[0], "d2h_bytes_per_step": e2e_bytes[1],
+                    "timing": "perf_counter around the synchronous host-buffer C-ABI call qlc_env_step_host (page-locked buffers), max over ranks, %d steps" % e2e_steps,
+                    "reward_sum_last_step": e2e_check},
             "gpu_launches": args.steps,
-            "episode_stats": {"sum_return": float(stats[0]), "episodes": float(stats[1]), "env_steps": float(stats[2]),
-                              "min_return": -float(stats[3]), "max_return": float(stats[4]), "reduced_with": "nccl all_reduce" if distributed else "single rank"},
+            "episode_stats": dict(stats, reduced_with="nccl all_reduce (2 tiny calls, off the step path)" if distributed else "single rank"),
             "env_error_flags": env.error_flags(),
         }
         line.update(extra)

@@ -1,0 +1,95 @@
+//! Raw bindings, 1:1 with include/ql_cuda.h.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_void};
+
+pub const QLC_OK: i32 = 0;
+pub const QLC_ERR_OUT_OF_RANGE: i32 = 3;
+pub const QLC_LAYOUT_U8_BHYX: i32 = 0;
+pub const QLC_LAYOUT_F32_BXYH: i32 = 1;
+pub const QLC_FRAME_W: usize = 84;
+pub const QLC_FRAME_H: usize = 84;
+pub const QLC_NUM_FRAMES: usize = 4;
+
+#[repr(C)]
+pub struct qlc_env {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct qlc_config {
+    pub struct_size: u32,
+    pub device: i32,
+    pub n_envs: u32,
+    pub env_id_base: u32,
+    pub frame_w: u32,
+    pub frame_h: u32,
+    pub seed: u64,
+    pub replay_capacity: u64,
+    pub max_episode_steps: u32,
+    pub episode_window: u32,
+    pub auto_reset: u32,
+    pub reserved: u32,
+}
+
+#[repr(C)]
+pub struct qlc_state_host {
+    pub ball_cx: *mut f32,
+    pub ball_cy: *mut f32,
+    pub ball_dx: *mut f32,
+    pub ball_dy: *mut f32,
+    pub pad_min_x: *mut f32,
+    pub pad_max_x: *mut f32,
+    pub pad_speed: *mut f32,
+    pub bricks: *mut u64,
+    pub score: *mut u32,
+    pub episode_step: *mut u32,
+    pub episode: *mut u32,
+    pub err: *mut u32,
+    pub finished: *mut u8,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct qlc_episode_stats {
+    pub sum_return: u64,
+    pub episodes: u64,
+    pub steps: u64,
+    pub min_return: u32,
+    pub max_return: u32,
+}
+
+extern "C" {
+    pub fn qlc_version() -> i32;
+    pub fn qlc_last_error_string() -> *const c_char;
+    pub fn qlc_device_count(count: *mut i32) -> i32;
+    pub fn qlc_env_create(cfg: *const qlc_config, out: *mut *mut qlc_env) -> i32;
+    pub fn qlc_env_destroy(env: *mut qlc_env) -> i32;
+    pub fn qlc_sync(env: *mut qlc_env, stream: *mut c_void) -> i32;
+    pub fn qlc_host_alloc(bytes: usize, out: *mut *mut c_void) -> i32;
+    pub fn qlc_host_free(p: *mut c_void) -> i32;
+    pub fn qlc_env_reset(env: *mut qlc_env, mask_host: *const u8, dir_x_host: *const f32) -> i32;
+    pub fn qlc_env_step(env: *mut qlc_env, actions_dev: *const u8, n_steps: u32, reward_dev: *mut f32, done_dev: *mut u8, stream: *mut c_void) -> i32;
+    pub fn qlc_env_step_host(env: *mut qlc_env, actions_host: *const u8, n_steps: u32, reward_host: *mut f32, done_host: *mut u8) -> i32;
+    pub fn qlc_env_obs(env: *mut qlc_env, layout: i32, out_dev: *mut c_void, stream: *mut c_void) -> i32;
+    pub fn qlc_env_obs_host(env: *mut qlc_env, layout: i32, out_host: *mut c_void) -> i32;
+    pub fn qlc_env_read_state(env: *mut qlc_env, out: *const qlc_state_host) -> i32;
+    pub fn qlc_env_goal_mean() -> f32;
+    pub fn qlc_env_time(env: *mut qlc_env, steps_taken: *mut u64) -> i32;
+    pub fn qlc_env_error_flags(env: *mut qlc_env, or_of_all: *mut u32) -> i32;
+    pub fn qlc_replay_len(env: *mut qlc_env, len: *mut u64) -> i32;
+    pub fn qlc_replay_capacity(env: *mut qlc_env, capacity: *mut u64) -> i32;
+    pub fn qlc_replay_sample(env: *mut qlc_env, batch: u32, n_batches: u32, call_index: u64, idx_dev: *mut u32, stream: *mut c_void) -> i32;
+    pub fn qlc_replay_gather(env: *mut qlc_env, idx_dev: *const u32, n: u32, layout: i32, state_dev: *mut c_void, next_dev: *mut c_void,
+                             reward_dev: *mut f32, action_dev: *mut u8, done_dev: *mut u8, stream: *mut c_void) -> i32;
+    pub fn qlc_replay_sample_host(env: *mut qlc_env, batch: u32, call_index: u64, idx_host: *mut u32) -> i32;
+    pub fn qlc_replay_gather_host(env: *mut qlc_env, idx_host: *const u32, n: u32, layout: i32, state_host: *mut c_void, next_host: *mut c_void,
+                                  reward_host: *mut f32, action_host: *mut u8, done_host: *mut u8) -> i32;
+    pub fn qlc_replay_action_counts(env: *mut qlc_env, counts: *mut u64) -> i32;
+    pub fn qlc_stats_read(env: *mut qlc_env, out: *mut qlc_episode_stats) -> i32;
+    pub fn qlc_stats_export(env: *mut qlc_env, out_dev: *mut f64, stream: *mut c_void) -> i32;
+    pub fn qlc_stats_push(env: *mut qlc_env, episode_reward: f32) -> i32;
+    pub fn qlc_stats_mean(env: *mut qlc_env, out: *mut f32) -> i32;
+    pub fn qlc_stats_min(env: *mut qlc_env, out: *mut f32) -> i32;
+    pub fn qlc_stats_window(env: *mut qlc_env, out: *mut f32, cap: u32, n: *mut u32) -> i32;
+}

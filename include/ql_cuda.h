@@ -115,6 +115,10 @@ int32_t qlc_device_count(int32_t* count);
 int32_t qlc_env_create(const qlc_config* cfg, qlc_env** out);         /* BreakoutEnvironment::new + ReplayBuffer::new */
 int32_t qlc_env_destroy(qlc_env* env);
 int32_t qlc_sync(qlc_env* env, void* stream);
+/* page-locked host memory for the *_host entry points: buffers from here (or cudaHostRegister'ed ones) are copied
+ * to / from the device in place, without the library's internal staging copy. */
+int32_t qlc_host_alloc(size_t bytes, void** out);
+int32_t qlc_host_free(void* p);
 
 /* ---- Environment (prelude.rs:21-63) ---- */
 /* reset(): mask_host NULL = all envs, else n_envs bytes (non-zero = reset). dir_x_host NULL = draw the initial

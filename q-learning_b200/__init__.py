@@ -39,6 +39,7 @@ ENVERR_WALL_DISTANCE, ENVERR_APPROX_RANGE, ENVERR_RECURSION, ENVERR_BISECTION, E
 # every symbol include/ql_cuda.h declares (checked by tests/test_abi.py against the header and the built library)
 ABI_SYMBOLS = [
     "qlc_version", "qlc_last_error_string", "qlc_device_count", "qlc_env_create", "qlc_env_destroy", "qlc_sync",
+    "qlc_host_alloc", "qlc_host_free",
     "qlc_env_reset", "qlc_env_step", "qlc_env_step_host", "qlc_env_obs", "qlc_env_obs_host", "qlc_env_state_view",
     "qlc_env_read_state", "qlc_env_goal_mean", "qlc_env_time", "qlc_env_error_flags",
     "qlc_replay_len", "qlc_replay_capacity", "qlc_replay_sample", "qlc_replay_gather", "qlc_replay_sample_host",
@@ -107,6 +108,8 @@ def load_library(build_if_missing=True):
         "qlc_env_create": (i32, [C.POINTER(QlcConfig), C.POINTER(vp)]),
         "qlc_env_destroy": (i32, [vp]),
         "qlc_sync": (i32, [vp, vp]),
+        "qlc_host_alloc": (i32, [C.c_size_t, C.POINTER(vp)]),
+        "qlc_host_free": (i32, [vp]),
         "qlc_env_reset": (i32, [vp, vp, vp]),
         "qlc_env_step": (i32, [vp, vp, u32, vp, vp, vp]),
         "qlc_env_step_host": (i32, [vp, vp, u32, vp, vp]),
@@ -149,6 +152,34 @@ def _check(rc):
 
 def _np_ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class PinnedArray:
+    """numpy view on page-locked host memory from qlc_host_alloc: the *_host entry points copy such buffers in place
+    (no internal staging copy). Keep the object alive while the array is in use."""
+
+    def __init__(self, shape, dtype):
+        L = load_library()
+        self._L = L
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        p = C.c_void_p()
+        _check(L.qlc_host_alloc(max(n, 1), C.byref(p)))
+        self._p = p
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            self._L.qlc_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def device_count():
@@ -249,14 +280,21 @@ class BreakoutEnvironment:
         r, d = self.step_many(a)
         return self.state(), r[0], d[0]
 
-    def step_many(self, actions):
-        """actions u8 [n_steps][n_envs] (host) -> reward f32 [n_steps][n_envs], done u8 [n_steps][n_envs]."""
+    def step_many(self, actions, out=None):
+        """actions u8 [n_steps][n_envs] (host) -> reward f32 [n_steps][n_envs], done u8 [n_steps][n_envs].
+        `out=(reward, done)` reuses caller arrays (page-locked ones, see PinnedArray, avoid the staging copy)."""
         a = np.ascontiguousarray(actions, dtype=np.uint8)
         if a.ndim != 2 or a.shape[1] != self.n_envs:
             raise QlError("actions must be [n_steps][n_envs]")
         k = a.shape[0]
-        reward = np.empty((k, self.n_envs), dtype=np.float32)
-        done = np.empty((k, self.n_envs), dtype=np.uint8)
+        if out is not None:
+            reward, done = out
+            if reward.shape != (k, self.n_envs) or reward.dtype != np.float32 or done.shape != (k, self.n_envs) or done.dtype != np.uint8 \
+                    or not reward.flags.c_contiguous or not done.flags.c_contiguous:
+                raise QlError("out arrays must be C-contiguous f32 / u8 [n_steps][n_envs]")
+        else:
+            reward = np.empty((k, self.n_envs), dtype=np.float32)
+            done = np.empty((k, self.n_envs), dtype=np.uint8)
         _check(self._L.qlc_env_step_host(self._h, _np_ptr(a), k, _np_ptr(reward), _np_ptr(done)))
         return reward, done
 

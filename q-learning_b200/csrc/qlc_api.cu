@@ -248,25 +248,54 @@ int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps,
     return QLC_OK;
 }
 
+static bool is_pinned(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int32_t qlc_env_step_host(qlc_env* env, const uint8_t* actions_host, uint32_t n_steps, float* reward_host, uint8_t* done_host) {
     if (!env || !actions_host) return fail(QLC_ERR_INVALID_ARG, "env/actions is null");
     if (n_steps == 0) return QLC_OK;
     int32_t rc = set_device(env); if (rc) return rc;
     const size_t n = (size_t)env->cfg.n_envs * n_steps;
-    for (size_t i = 0; i < n; ++i)
-        if (actions_host[i] >= QLC_ACTION_SPACE) return fail(QLC_ERR_OUT_OF_RANGE, "value out of range");   // QlError, breakout_environment.rs:117
+    uint8_t bad = 0;
+    for (size_t i = 0; i < n; ++i) bad |= (uint8_t)(actions_host[i] >= QLC_ACTION_SPACE);
+    if (bad) return fail(QLC_ERR_OUT_OF_RANGE, "value out of range");   // QlError, breakout_environment.rs:117
     const size_t off_r = (n + 15) & ~(size_t)15, off_d = off_r + n * 4, total = off_d + n;
-    rc = ensure_pin(env, total); if (rc) return rc;
     rc = ensure_dev_stage(env, total); if (rc) return rc;
-    uint8_t* pin = (uint8_t*)env->pin; uint8_t* dev = (uint8_t*)env->dev_stage;
-    memcpy(pin, actions_host, n);
+    uint8_t* dev = (uint8_t*)env->dev_stage;
     cudaStream_t s = env->own_stream;
-    CUDA_TRY(cudaMemcpyAsync(dev, pin, n, cudaMemcpyHostToDevice, s));
+    // page-locked caller buffers (qlc_host_alloc / cudaHostRegister) are used in place; pageable ones are staged
+    const bool pin_a = is_pinned(actions_host), pin_r = !reward_host || is_pinned(reward_host), pin_d = !done_host || is_pinned(done_host);
+    uint8_t* pin = nullptr;
+    if (!(pin_a && pin_r && pin_d)) { rc = ensure_pin(env, total); if (rc) return rc; pin = (uint8_t*)env->pin; }
+    if (pin_a) {
+        CUDA_TRY(cudaMemcpyAsync(dev, actions_host, n, cudaMemcpyHostToDevice, s));
+    } else {
+        memcpy(pin, actions_host, n);
+        CUDA_TRY(cudaMemcpyAsync(dev, pin, n, cudaMemcpyHostToDevice, s));
+    }
     rc = qlc_env_step(env, dev, n_steps, (float*)(dev + off_r), dev + off_d, s); if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(pin + off_r, dev + off_r, n * 5, cudaMemcpyDeviceToHost, s));
+    if (reward_host) CUDA_TRY(cudaMemcpyAsync(pin_r ? (void*)reward_host : (void*)(pin + off_r), dev + off_r, n * 4, cudaMemcpyDeviceToHost, s));
+    if (done_host) CUDA_TRY(cudaMemcpyAsync(pin_d ? (void*)done_host : (void*)(pin + off_d), dev + off_d, n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    if (reward_host) memcpy(reward_host, pin + off_r, n * 4);
-    if (done_host) memcpy(done_host, pin + off_d, n);
+    if (reward_host && !pin_r) memcpy(reward_host, pin + off_r, n * 4);
+    if (done_host && !pin_d) memcpy(done_host, pin + off_d, n);
+    return QLC_OK;
+}
+
+int32_t qlc_host_alloc(size_t bytes, void** out) {
+    if (!out || bytes == 0) return fail(QLC_ERR_INVALID_ARG, "out is null or bytes == 0");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(QLC_ERR_NO_DEVICE, "no CUDA device: ql_cuda has no CPU fallback");
+    CUDA_TRY(cudaMallocHost(out, bytes));
+    return QLC_OK;
+}
+int32_t qlc_host_free(void* p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
     return QLC_OK;
 }
 
