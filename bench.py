@@ -180,6 +180,12 @@ def run_b200(args, rank, local_rank, world):
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         launch()
+    torch.cuda.synchronize()
+    t_warm = time.time()                      # a few launches are ~1 ms: keep warming (untimed) until clocks have settled
+    while time.time() - t_warm < 0.25:
+        for _ in range(10):
+            launch()
+        torch.cuda.synchronize()
     reduce_stats()
     # ---- timed region: exactly K launches, device resident inputs ----
     barrier()
@@ -321,6 +327,15 @@ def measure_extras(q, torch, env, rb, dev, stream, peak):
         rate = 65536 * k / (ms * 1e-3)
         out["envs_65536"] = {"env_steps_per_sec": rate, "ms_per_launch": ms, "steps_per_launch": k, "achieved_gbs": rate * BYTES_PER_ENV_STEP / 1e9,
                              "frac_of_peak": rate * BYTES_PER_ENV_STEP / 1e9 / peak}
+        for _ in range(3):
+            big.step_device(acts.data_ptr(), 1, None, None, stream)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(100):
+            big.step_device(acts.data_ptr(), 1, None, None, stream)
+        e1.record(); torch.cuda.synchronize()
+        ms1 = e0.elapsed_time(e1) / 100
+        out["envs_65536"]["single_step_launch"] = {"env_steps_per_sec": 65536 / (ms1 * 1e-3), "us_per_launch": ms1 * 1e3}
         big.close()
     except Exception as ex:  # e.g. not enough free HBM next to the main shard
         out["envs_65536"] = {"error": str(ex)}
@@ -336,6 +351,33 @@ def measure_extras(q, torch, env, rb, dev, stream, peak):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 500
     out["single_step_launch"] = {"env_steps_per_sec": env.n_envs / (ms * 1e-3), "us_per_launch": ms * 1e3}
+    # actor-loop shape of BASELINE configs[4] without the (out-of-scope) learner: per iteration a fresh action batch from a
+    # device-side policy stand-in (uniform random, like the learner's first 50k steps), ONE env-step launch, and on every
+    # 4th step (the learner's gate, self_driving_tf_q_learner.rs:181) a distinct-index sample + f32 [32,84,84,4] s/s' gather.
+    n = env.n_envs
+    idx = torch.empty((32,), dtype=torch.int32, device=dev)
+    st = torch.empty((32, per), dtype=torch.float32, device=dev); nx = torch.empty((32, per), dtype=torch.float32, device=dev)
+    r = torch.empty((32,), dtype=torch.float32, device=dev); a = torch.empty((32,), dtype=torch.uint8, device=dev); d = torch.empty((32,), dtype=torch.uint8, device=dev)
+    rew1 = torch.empty((1, n), dtype=torch.float32, device=dev); done1 = torch.empty((1, n), dtype=torch.uint8, device=dev)
+
+    def actor_iter(i):
+        acts = torch.randint(0, 3, (1, n), dtype=torch.uint8, device=dev)
+        env.step_device(acts.data_ptr(), 1, rew1.data_ptr(), done1.data_ptr(), stream)
+        if rb.should_sample(i, rb.len(), 32):
+            rb.sample_device(32, 1, i, idx.data_ptr(), stream)
+            rb.gather_device(idx.data_ptr(), 32, q.LAYOUT_F32_BXYH, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
+    for i in range(8):
+        actor_iter(i)
+    torch.cuda.synchronize()
+    iters = 400
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        actor_iter(i)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    out["actor_loop"] = {"env_steps_per_sec": n / (ms * 1e-3), "minibatches_per_sec": 0.25 / (ms * 1e-3), "us_per_iteration": ms * 1e3,
+                         "note": "1 step launch per iteration (actions from a device-side random policy), sample+gather B=32 f32 every 4th step; no learner"}
     return out
 
 

@@ -418,6 +418,11 @@ class ReplayBuffer:
         _check(self._L.qlc_replay_action_counts(self._env._h, _np_ptr(out)))
         return out
 
+    @staticmethod
+    def should_sample(step_count, length, batch, update_after_actions=4):
+        """The learner's sample gate (self_driving_tf_q_learner.rs:181): every n-th step once len > BATCH_SIZE."""
+        return step_count % update_after_actions == 0 and length > batch
+
     def generate_distinct_random_ids(self, batch, call_index=None):
         """BATCH distinct uniform indices in 0..len (self_driving_tf_q_learner.rs:276-296), host copy."""
         if call_index is None:

@@ -4,7 +4,7 @@ import shutil
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libqlcuda.so")
+SO_PATH = os.environ.get("QLC_LIB") or os.path.join(_HERE, "libqlcuda.so")   # QLC_LIB: A/B-test another build of the library
 SOURCES = [os.path.join(_HERE, "csrc", "qlc_api.cu")]
 HEADERS = [
     os.path.join(_HERE, "csrc", "kernels.cuh"),
@@ -26,6 +26,8 @@ def _nvcc():
 
 
 def needs_build():
+    if os.environ.get("QLC_LIB"):
+        return False
     if not os.path.exists(SO_PATH):
         return True
     t = os.path.getmtime(SO_PATH)

@@ -33,6 +33,7 @@ struct DeviceStats {                      // order-independent accumulators
 struct StepParams {
     uint32_t n_envs, env_id_base, time_slots, max_episode_steps, auto_reset, n_steps;
     uint32_t debug_skip;       // profiling aid (QLC_DEBUG_SKIP): 1 = no physics, 2 = no frame stores; 0 in production
+    unsigned int* work_counter; uint32_t work_base;   // dynamic batch hand-out: batch = atomicAdd(counter, 1) - base
     uint32_t epc;              // envs per CTA (<= R*NE), chosen by the host so that the grid fills all SMs evenly
     uint64_t t0, seed;
     uint8_t* frames; uint32_t* records; DeviceStats* stats;
@@ -149,18 +150,18 @@ template <int D, int EPC_MAX>
 struct AdvanceSmem {
     RasterTables tables;
     RenderRec queue[D][EPC_MAX];
+    uint32_t item_env0[D], item_n[D], item_step[D];   // which env batch / step a queue slot carries; item_n == 0 = no more work
     uint64_t full[D], empty[D];
 };
 
-template <int R, int NE, int D>
-__global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st, StepParams p) {
+template <int R, int NE, int D, int MINB>
+__global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArrays st, StepParams p) {
     static_assert(R * NE <= ENVS_PER_CTA, "one physics lane per env");
     const uint32_t EPC = p.epc;                       // envs per CTA (<= R*NE)
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     __shared__ AdvanceSmem<D, R * NE> S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t env0 = blockIdx.x * EPC;
-    const uint32_t n_here = min(EPC, p.n_envs - env0);
+    const uint32_t n_batches = (p.n_envs + EPC - 1) / EPC;   // env batches, handed out to the CTAs dynamically
 
     if (tid == 0) {
         for (int q = 0; q < D; ++q) { mbar_init(&S.full[q], 1); mbar_init(&S.empty[q], R); }
@@ -174,6 +175,20 @@ __global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st,
 
     if (warp == 0) {
         // ------------------------------- physics warp -------------------------------
+        uint32_t seq = 0;                                  // (batch, step) items published so far
+        for (;;) {
+        // env batches are handed out dynamically (SMs differ in their distance to L2/HBM; a static split would wait for the slowest)
+        uint32_t batch = 0;
+        if (lane == 0) batch = atomicAdd(p.work_counter, 1u) - p.work_base;
+        batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+        if (batch >= n_batches) {
+            const int q = seq % D;
+            if (seq >= (uint32_t)D) mbar_wait(&S.empty[q], ((seq / D) - 1) & 1);
+            if (lane == 0) { S.item_n[q] = 0u; mbar_arrive(&S.full[q]); }
+            break;
+        }
+        const uint32_t env0 = batch * EPC;
+        const uint32_t n_here = min(EPC, p.n_envs - env0);
         const uint32_t e = env0 + lane;
         const bool active = lane < n_here;
         Env env; uint32_t k = 0, episode = 0;
@@ -187,14 +202,14 @@ __global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st,
         }
         MoveCache mc; move_cache_update(mc, env);
         uint32_t action = active ? p.actions[e] : 0u;
-        for (uint32_t s = 0; s < p.n_steps; ++s) {
-            const int q = s % D;
+        for (uint32_t s = 0; s < p.n_steps; ++s, ++seq) {
+            const int q = seq % D;
             uint32_t next_action = 0u;
             if (active && s + 1 < p.n_steps) next_action = p.actions[(size_t)(s + 1) * p.n_envs + e];
             if (action >= 3u) { env.err |= ENVERR_ACTION; action = 0u; }
             const uint32_t score_before = env.score;
             if (active && p.debug_skip != 1u) time_step(env, action, mc);
-            if (s >= (uint32_t)D) mbar_wait(&S.empty[q], ((s / D) - 1) & 1);
+            if (seq >= (uint32_t)D) mbar_wait(&S.empty[q], ((seq / D) - 1) & 1);
             if (active) {
                 RenderRec rr;
                 rr.bx = scale84(env.cx); rr.by = scale84(env.cy); rr.x0 = scale84(env.pmin); rr.x1 = scale84(env.pmax); rr.bricks = env.bricks;
@@ -202,6 +217,7 @@ __global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st,
                 const int j0 = (int)floorf(fminf(fmaxf(rr.by, -100.0f), 200.0f) - 2.9f);
                 rr.box = (j0 << 16) | (i0 & 0xFFFF); rr.pad = 0u;
                 S.queue[q][lane] = rr;
+                if (lane == 0) { S.item_env0[q] = env0; S.item_n[q] = n_here; S.item_step[q] = s; }
                 const uint32_t reward = env.score - score_before;
                 const bool done = env.finished;
                 const uint32_t k_before = k;
@@ -233,6 +249,7 @@ __global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st,
             st.bricks[e] = env.bricks; st.score[e] = env.score; st.err[e] = env.err; st.finished[e] = env.finished ? 1 : 0;
             st.episode_step[e] = k; st.episode[e] = episode;
         }
+        }   // batches
     } else {
         // ------------------------------- render warps -------------------------------
         const int rw = warp - 1;
@@ -254,9 +271,12 @@ __global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st,
         constexpr int G = NE >= 2 ? 2 : 1;          // bulk groups per step: one half drains while the other is drawn
         constexpr int FPG = NE / G;                 // frames per group
         static_assert(NE % G == 0, "NE must be 1 or even");
-        for (uint32_t s = 0; s < p.n_steps; ++s) {
-            const int q = s % D;
-            mbar_wait(&S.full[q], (s / D) & 1);
+        for (uint32_t seq = 0;; ++seq) {
+        {
+            const int q = seq % D;
+            mbar_wait(&S.full[q], (seq / D) & 1);
+            const uint32_t env0 = S.item_env0[q], n_here = S.item_n[q], s = S.item_step[q];
+            if (n_here == 0u) break;                       // the physics warp found no more env batches
             RenderRec rr[NE];
             #pragma unroll
             for (int i = 0; i < NE; ++i) {
@@ -270,7 +290,7 @@ __global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st,
             #pragma unroll
             for (int g = 0; g < G; ++g) {
                 // this group's frames were last stored G groups ago: that store must have left shared memory
-                if (s > 0 && lane == 0) bulk_wait_read<G - 1>();
+                if (seq > 0 && lane == 0) bulk_wait_read<G - 1>();
                 __syncwarp();
                 // ---- phase 1: clear the old ball boxes, rewrite the paddle rows, rewrite the brick band where needed ----
                 #pragma unroll
@@ -362,6 +382,7 @@ __global__ void __launch_bounds__(32 * (R + 1)) env_advance_kernel(EnvArrays st,
                 }
             }
         }
+        }   // batches
         if (lane == 0) bulk_wait<0>();
     }
 }

@@ -29,6 +29,8 @@ struct qlc_env {
     uint32_t* records = nullptr;
     DeviceStats* stats = nullptr;
     unsigned long long* scratch = nullptr;     // 8 x u64 device scratch (histogram, err OR)
+    unsigned int* work_counter = nullptr;      // dynamic env-batch hand-out of the step kernel
+    uint32_t work_base = 0;
     uint32_t time_slots = 0;                   // frame/record ring length in time steps (= t_cap + 4)
     uint32_t t_cap = 0;                        // replay capacity in time steps
     uint64_t t = 0;                            // env-steps taken per env (global time)
@@ -42,6 +44,7 @@ struct qlc_env {
     int epc_override = 0;                      // QLC_EPC: force envs per CTA (0 = auto)
     int sm_count = 148;
     int debug_skip = 0;                        // QLC_DEBUG_SKIP (profiling aid)
+    int persistent = 1;                        // QLC_PERSISTENT=0: one CTA per env batch
     std::vector<void*> allocs;
 };
 
@@ -124,6 +127,7 @@ int32_t qlc_env_create(const qlc_config* cfg, qlc_env** out) {
     if (const char* c = getenv("QLC_ADVANCE_CFG")) env->advance_cfg = atoi(c);
     if (const char* c = getenv("QLC_EPC")) env->epc_override = atoi(c);
     if (const char* c = getenv("QLC_DEBUG_SKIP")) env->debug_skip = atoi(c);
+    if (const char* c = getenv("QLC_PERSISTENT")) env->persistent = atoi(c);
     env->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
 
 #define TRY_ALLOC(x) do { rc = (x); if (rc) { qlc_env_destroy(env); return rc; } } while (0)
@@ -144,6 +148,7 @@ int32_t qlc_env_create(const qlc_config* cfg, qlc_env** out) {
     TRY_ALLOC(dev_alloc(env, &env->records, (size_t)env->time_slots * n, true));
     TRY_ALLOC(dev_alloc(env, &env->stats, 1, false));
     TRY_ALLOC(dev_alloc(env, &env->scratch, 8, true));
+    TRY_ALLOC(dev_alloc(env, &env->work_counter, 1, true));
 #undef TRY_ALLOC
     cudaError_t ce = cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { qlc_env_destroy(env); return fail(QLC_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(ce)); }
@@ -202,20 +207,30 @@ static uint32_t pick_epc(uint32_t n_envs, uint32_t sms, uint32_t max_epc) {
     return epc < 1 ? 1 : epc;
 }
 
-template <int R, int NE, int D>
+template <int R, int NE, int D, int MINB>
 static int32_t launch_advance(qlc_env* env, StepParams& p, cudaStream_t s) {
     static bool configured[64] = {};
     const size_t dyn = (size_t)R * NE * FRAME_BYTES;
-    auto kern = env_advance_kernel<R, NE, D>;
+    auto kern = env_advance_kernel<R, NE, D, MINB>;
     if (!configured[env->cfg.device & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         configured[env->cfg.device & 63] = true;
     }
     p.epc = env->epc_override ? (uint32_t)env->epc_override : pick_epc(p.n_envs, (uint32_t)env->sm_count, R * NE);
     if (p.epc > (uint32_t)(R * NE)) p.epc = R * NE;
-    const uint32_t grid = (p.n_envs + p.epc - 1) / p.epc;
+    const uint32_t n_batches = (p.n_envs + p.epc - 1) / p.epc;
+    uint32_t grid = n_batches;
+    if (env->persistent) {       // CTAs walk the env batches; frames, raster tables and barriers are set up once per CTA
+        static int occ[64] = {};
+        int& o = occ[env->cfg.device & 63];
+        if (o == 0) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, 32 * (R + 1), dyn));
+        const uint32_t resident = (uint32_t)(o > 0 ? o : 1) * (uint32_t)env->sm_count;
+        if (grid > resident) grid = resident;
+    }
+    p.work_counter = env->work_counter; p.work_base = env->work_base;
     kern<<<grid, 32 * (R + 1), dyn, s>>>(env->st, p);
     CUDA_TRY(cudaGetLastError());
+    env->work_base += n_batches + grid;      // every CTA ends with one failed grab
     return QLC_OK;
 }
 
@@ -233,14 +248,14 @@ int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps,
     p.debug_skip = (uint32_t)env->debug_skip;
     cudaStream_t s = (cudaStream_t)stream;
     int cfg = env->advance_cfg;
-    if (cfg == 0) cfg = (p.n_envs <= (uint32_t)env->sm_count * 32u) ? 1 : 5;
+    if (cfg == 0) cfg = (p.n_envs <= (uint32_t)env->sm_count * 32u || n_steps < 4u) ? 1 : 5;   // measured: profiles/r01_notes.md
     switch (cfg) {
-        case 1: rc = launch_advance<8, 4, 4>(env, p, s); break;    // <= 32 envs / CTA, 1 CTA / SM
-        case 2: rc = launch_advance<8, 2, 2>(env, p, s); break;    // <= 16 envs / CTA, 2 CTAs / SM
-        case 3: rc = launch_advance<4, 4, 4>(env, p, s); break;    // <= 16 envs / CTA, fewer warps
-        case 4: rc = launch_advance<4, 2, 4>(env, p, s); break;    // <=  8 envs / CTA
-        case 5: rc = launch_advance<8, 1, 4>(env, p, s); break;    // <=  8 envs / CTA, 3 CTAs / SM
-        case 6: rc = launch_advance<16, 2, 4>(env, p, s); break;   // <= 32 envs / CTA, 16 render warps
+        case 1: rc = launch_advance<8, 4, 4, 1>(env, p, s); break;    // <= 32 envs / CTA, 1 CTA / SM
+        case 2: rc = launch_advance<8, 2, 2, 2>(env, p, s); break;    // <= 16 envs / CTA, 2 CTAs / SM
+        case 3: rc = launch_advance<4, 4, 4, 2>(env, p, s); break;    // <= 16 envs / CTA, fewer warps
+        case 4: rc = launch_advance<4, 2, 4, 3>(env, p, s); break;    // <=  8 envs / CTA
+        case 5: rc = launch_advance<8, 1, 4, 3>(env, p, s); break;    // <=  8 envs / CTA, 3 CTAs / SM
+        case 6: rc = launch_advance<16, 2, 4, 1>(env, p, s); break;   // <= 32 envs / CTA, 16 render warps
         default: return fail(QLC_ERR_INVALID_ARG, "unknown QLC_ADVANCE_CFG");
     }
     if (rc) return rc;

@@ -429,3 +429,51 @@ def test_rare_events_parity(qlb, O):
             assert so[k][0] == st[k][e] or (so[k][0] != so[k][0] and st[k][e] != st[k][e]), (k, int(e), so[k][0], st[k][e])
         o.close()
     env.close()
+
+
+def test_replay_config_1m_transitions(qlb, O):
+    """BASELINE configs[2] size: 4,096 envs, 1,048,576-transition replay (7.5 GB frame ring), filled past wrap-around;
+    uniform samples of 32 and 512 with frame-stack gather. Size-independent checks: host-recorded (action, reward, done)
+    history per sampled row, s'(t) == s(t+1) chaining across rows of the same env, and exact equality with the oracle's
+    FIFO replay for whole envs replayed on the CPU."""
+    n, cap, seed = 4096, 1 << 20, 77
+    t_cap = cap // n                       # 256 time steps
+    T = t_cap + 45                         # wrap the ring
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=seed, replay_capacity=cap)
+    rb = qlb.ReplayBuffer(env)
+    rng = np.random.default_rng(3)
+    acts = rng.integers(0, 3, size=(T, n), dtype=np.uint8)
+    reward = np.empty((T, n), dtype=np.float32); done = np.empty((T, n), dtype=np.uint8)
+    for t0 in range(0, T, 43):
+        k = min(43, T - t0)
+        r, d = env.step_many(acts[t0:t0 + k])
+        reward[t0:t0 + k] = r; done[t0:t0 + k] = d
+    assert rb.len() == cap == rb.capacity()
+    t_old = T - t_cap
+    for batch in (32, 512):
+        idx = rb.generate_distinct_random_ids(batch, 5)
+        assert len(set(idx.tolist())) == batch and idx.max() < cap
+        assert np.array_equal(idx, O.sample_distinct(seed, 5, cap, batch))
+        g = rb.get_many(idx, qlb.LAYOUT_U8_BHYX)
+        tt, ee = t_old + idx // n, idx % n
+        assert np.array_equal(g.action, acts[tt, ee]) and np.array_equal(g.reward, reward[tt, ee]) and np.array_equal(g.done, done[tt, ee])
+        # chaining: row (t, e) and row (t+1, e)
+        nxt = idx + n
+        ok = (nxt < cap) & (g.done == 0)
+        g2 = rb.get_many(nxt[ok], qlb.LAYOUT_U8_BHYX)
+        assert np.array_equal(g.state_next[ok], g2.state)
+        f = rb.get_many(idx[:16], qlb.LAYOUT_F32_BXYH)
+        assert np.array_equal(f.state, np.transpose(g.state[:16], (0, 3, 2, 1)).astype(np.float32))
+        assert np.array_equal(f.state_next, np.transpose(g.state_next[:16], (0, 3, 2, 1)).astype(np.float32))
+    # whole envs against the oracle FIFO (capacity t_cap for a single env == the same time window)
+    for e in (0, 1777, n - 1):
+        o = O.VecEnv(1, seed=seed, env_id_base=e, replay_capacity=t_cap)
+        for t in range(T):
+            o.step(acts[t, e:e + 1])
+        j = np.array([0, 1, 2, 3, 4, 5, t_cap // 2, t_cap - 2, t_cap - 1], dtype=np.uint32)
+        og = o.get_many(j, "u8")
+        gg = rb.get_many(j * n + e, qlb.LAYOUT_U8_BHYX)
+        assert np.array_equal(gg.state, og["state"]) and np.array_equal(gg.state_next, og["state_next"])
+        assert np.array_equal(gg.reward, og["reward"]) and np.array_equal(gg.action, og["action"]) and np.array_equal(gg.done, og["done"])
+        o.close()
+    env.close()

@@ -68,14 +68,7 @@ def time_gather(n_envs, batch, n_batches, layout, reps=20):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
-    for skip in (0, 2):
-        os.environ["QLC_DEBUG_SKIP"] = str(skip)
-        print("QLC_DEBUG_SKIP =", skip, "(1 = no physics, 2 = no frame stores)")
-        for cfg, epc in ((1, 32), (1, 28), (2, 16), (6, 32), (6, 28), (6, 30)):
-            os.environ["QLC_EPC"] = str(epc)
-            time_advance(4096, 64, 20, cfg)
-        os.environ["QLC_EPC"] = "0"
-        for cfg in (2, 5, 6):
-            time_advance(65536, 16, 10, cfg, cap_steps=32)
-        time_advance(4096, 1, 200, 1)
-        time_advance(4096, 1, 200, 6)
+    for rep in range(3):
+        time_advance(4096, 64, 30, 1)
+    time_advance(65536, 16, 10, 5, cap_steps=32)
+    time_advance(4096, 1, 200, 1)
