@@ -28,8 +28,12 @@ def build(force=False):
     """Compile liboracle.so + selftest with the Makefile in oracle/ (gcc, seconds)."""
     so = os.path.join(_HERE, "liboracle.so")
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h")) or f == "Makefile"]
-    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.run(["make", "-C", _HERE, "all"], check=True, stdout=subprocess.DEVNULL)
+    if force or not os.path.exists(so) or not os.path.exists(os.path.join(_HERE, "selftest")) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        try:
+            subprocess.run(["make", "-C", _HERE, "all"], check=True, stdout=subprocess.DEVNULL)
+        except (subprocess.CalledProcessError, OSError):
+            if force or not os.path.exists(so):
+                raise
     return so
 
 

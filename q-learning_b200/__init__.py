@@ -238,6 +238,8 @@ class BreakoutEnvironment:
                  replay_capacity=0, max_episode_steps=0, episode_window=100, auto_reset=True):
         self._L = load_library()
         self.n_envs = int(n_envs)
+        self.max_episode_steps = int(max_episode_steps)
+        self.auto_reset = bool(auto_reset)
         cfg = QlcConfig(C.sizeof(QlcConfig), device, n_envs, env_id_base, frame_size_x, frame_size_y, seed,
                         replay_capacity, max_episode_steps, episode_window, 1 if auto_reset else 0, 0)
         h = C.c_void_p()

@@ -38,12 +38,19 @@ def build(force=False, verbose=False):
     """Compile libqlcuda.so if missing or stale. Returns the path."""
     if not force and not needs_build():
         return SO_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH + ".tmp"] + SOURCES
-    env = dict(os.environ)
-    env.pop("CC", None)   # the image exports CC=/opt/gcc/bin/gcc; let nvcc use the system g++
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout)
+    try:
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH + ".tmp"] + SOURCES
+        env = dict(os.environ)
+        env.pop("CC", None)   # the image exports CC=/opt/gcc/bin/gcc; let nvcc use the system g++
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout)
+    except (RuntimeError, OSError):
+        # a prebuilt library that travelled with the tree (file times are not preserved by every copy) is still the
+        # CUDA product; only a missing library is fatal
+        if not force and os.path.exists(SO_PATH):
+            return SO_PATH
+        raise
     os.replace(SO_PATH + ".tmp", SO_PATH)
     if verbose:
         print(res.stdout)
