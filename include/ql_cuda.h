@@ -175,6 +175,10 @@ int32_t qlc_debug_collision_rect(float cx, float cy, float radius, float mvx, fl
                                  float min_x, float min_y, float max_x, float max_y,
                                  int32_t* some, float* way, float* approximation, float* nx, float* ny, uint32_t* err);
 
+/* batched rectangle sweep: in_host [n][9] = cx, cy, radius, mvx, mvy, min_x, min_y, max_x, max_y;
+ * out_host [n][6] = some (0/1), way, approximation, nx, ny, err (u32 bits in a float slot) */
+int32_t qlc_debug_collision_rect_batch(const float* in_host, float* out_host, uint32_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -397,3 +397,18 @@ float orc_reset_dir_x(uint64_t seed, uint32_t env_global_id, uint32_t episode) {
     orc_philox4x32_10(ctr, key, out);
     return orc_dir_x_from_bits(out[0]);
 }
+
+/* batched rectangle sweep for fuzzing the device routine: in [n][9] = cx, cy, r, mvx, mvy, minx, miny, maxx, maxy;
+ * out [n][6] = some, way, approximation, nx, ny, err (u32 bits in a float slot) */
+void orc_collision_rect_batch(const float* in, float* out, uint32_t n) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + (size_t)i * 9;
+        orc_circle ball = {{a[0], a[1]}, a[2]}; orc_v2 mv = {a[3], a[4]}; orc_aabb box = {{a[5], a[6]}, {a[7], a[8]}};
+        orc_contact_surface c; memset(&c, 0, sizeof c); uint32_t err = 0;
+        int some = orc_collision_check_with_rectangle(&ball, mv, &box, &c, &err);
+        float* o = out + (size_t)i * 6;
+        o[0] = some ? 1.0f : 0.0f;
+        o[1] = some ? c.way : 0.0f; o[2] = some ? c.approximation : 0.0f; o[3] = some ? c.surface_normal.x : 0.0f; o[4] = some ? c.surface_normal.y : 0.0f;
+        memcpy(&o[5], &err, 4);
+    }
+}

@@ -142,6 +142,15 @@ def collision_rect(center, radius, mv, rmin, rmax):
     return some, out.way, out.approximation, out.surface_normal.x, out.surface_normal.y, err.value
 
 
+def collision_rect_batch(cases):
+    a = np.ascontiguousarray(cases, dtype=np.float32)
+    out = np.empty((a.shape[0], 6), dtype=np.float32)
+    L = lib()
+    L.orc_collision_rect_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.orc_collision_rect_batch(_p(a), _p(out), a.shape[0])
+    return (out[:, 0] != 0).astype(np.uint8), out[:, 1:5].copy(), out[:, 5].copy().view(np.uint32)
+
+
 def sample_distinct(seed, call, length, batch):
     out = np.empty(batch, dtype=np.uint32)
     rc = lib().orc_sample_distinct(seed, call, length, batch, _p(out))

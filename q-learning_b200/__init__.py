@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "qlc_replay_len", "qlc_replay_capacity", "qlc_replay_sample", "qlc_replay_gather", "qlc_replay_sample_host",
     "qlc_replay_gather_host", "qlc_replay_action_counts",
     "qlc_stats_read", "qlc_stats_export", "qlc_stats_push", "qlc_stats_mean", "qlc_stats_min", "qlc_stats_window",
-    "qlc_debug_collision_wall", "qlc_debug_collision_rect",
+    "qlc_debug_collision_wall", "qlc_debug_collision_rect", "qlc_debug_collision_rect_batch",
 ]
 
 
@@ -135,6 +135,7 @@ def load_library(build_if_missing=True):
         "qlc_stats_window": (i32, [vp, vp, u32, C.POINTER(u32)]),
         "qlc_debug_collision_wall": (i32, [i32] + [C.c_float] * 5 + [vp] * 6),
         "qlc_debug_collision_rect": (i32, [C.c_float] * 9 + [vp] * 6),
+        "qlc_debug_collision_rect_batch": (i32, [vp, vp, u32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)   # AttributeError if the library lacks a declared symbol
@@ -479,3 +480,14 @@ def debug_collision_rect(center, radius, mv, rmin, rmax):
     _check(L.qlc_debug_collision_rect(center[0], center[1], radius, mv[0], mv[1], rmin[0], rmin[1], rmax[0], rmax[1],
                                       C.addressof(some), *[C.addressof(x) for x in f], C.addressof(err)))
     return some.value, f[0].value, f[1].value, f[2].value, f[3].value, err.value
+
+
+def debug_collision_rect_batch(cases):
+    """cases f32 [n][9] (cx, cy, radius, mvx, mvy, min_x, min_y, max_x, max_y) -> (some u8[n], surf f32[n][4], err u32[n])
+    from the DEVICE sweep routine."""
+    a = np.ascontiguousarray(cases, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] != 9:
+        raise QlError("cases must be [n][9]")
+    out = np.empty((a.shape[0], 6), dtype=np.float32)
+    _check(load_library().qlc_debug_collision_rect_batch(_np_ptr(a), _np_ptr(out), a.shape[0]))
+    return (out[:, 0] != 0).astype(np.uint8), out[:, 1:5].copy(), out[:, 5].copy().view(np.uint32)

@@ -637,4 +637,17 @@ __global__ void debug_collision_kernel(int which, float cx, float cy, float r, f
     out[0] = some ? 1.0f : 0.0f; out[1] = s.way; out[2] = s.approx; out[3] = s.nx; out[4] = s.ny; *err_out = err;
 }
 
+// batched form of the above for fuzzing the device collision code against the oracle: in [n][9] = cx, cy, r, mvx, mvy,
+// minx, miny, maxx, maxy; out [n][6] = some, way, approx, nx, ny, err (err as raw bits)
+__global__ void debug_collision_batch_kernel(const float* in, float* out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* a = in + (size_t)i * 9;
+    uint32_t err = 0; Surface s; s.way = s.approx = s.nx = s.ny = 0.0f;
+    const float len = length2(a[3], a[4]);
+    const bool some = sweep_ball_box(a[0], a[1], a[2], a[3], a[4], len, (a[5] + a[7]) / 2.0f, (a[6] + a[8]) / 2.0f, (a[7] - a[5]) / 2.0f, (a[8] - a[6]) / 2.0f, s, err);
+    float* o = out + (size_t)i * 6;
+    o[0] = some ? 1.0f : 0.0f; o[1] = s.way; o[2] = s.approx; o[3] = s.nx; o[4] = s.ny; o[5] = __uint_as_float(err);
+}
+
 }  // namespace qlc

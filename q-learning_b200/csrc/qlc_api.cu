@@ -561,6 +561,21 @@ static int32_t run_debug(int which, float cx, float cy, float r, float mvx, floa
     if (err) memcpy(err, &h[6], 4);
     return QLC_OK;
 }
+int32_t qlc_debug_collision_rect_batch(const float* in_host, float* out_host, uint32_t n) {
+    if (!in_host || !out_host) return fail(QLC_ERR_INVALID_ARG, "in/out is null");
+    if (n == 0) return QLC_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(QLC_ERR_NO_DEVICE, "no CUDA device: ql_cuda has no CPU fallback");
+    float *din = nullptr, *dout = nullptr;
+    CUDA_TRY(cudaMalloc(&din, (size_t)n * 9 * sizeof(float)));
+    cudaError_t e = cudaMalloc(&dout, (size_t)n * 6 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(din, in_host, (size_t)n * 9 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { debug_collision_batch_kernel<<<(n + 127) / 128, 128>>>(din, dout, n); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpy(out_host, dout, (size_t)n * 6 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(din); cudaFree(dout);
+    if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("debug batch: ") + cudaGetErrorString(e));
+    return QLC_OK;
+}
 int32_t qlc_debug_collision_wall(int32_t which, float cx, float cy, float radius, float mvx, float mvy, int32_t* some, float* way,
                                  float* approximation, float* nx, float* ny, uint32_t* err) {
     if (which < 0 || which > 2) return fail(QLC_ERR_INVALID_ARG, "which must be 0..2");

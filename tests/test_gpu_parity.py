@@ -477,3 +477,35 @@ def test_replay_config_1m_transitions(qlb, O):
         assert np.array_equal(gg.reward, og["reward"]) and np.array_equal(gg.action, og["action"]) and np.array_equal(gg.done, og["done"])
         o.close()
     env.close()
+
+
+def test_device_sweep_fuzz_vs_oracle(qlb, O):
+    """400k random and adversarial ball-vs-box sweeps through the DEVICE routine (sweep_ball_box: contact query, back-off
+    estimate, bisection, acos-free acceptance test) against the oracle's collision_check_with_rectangle: the Some/None
+    decision, way, approximation, normal and flags must agree bit for bit."""
+    rng = np.random.default_rng(2026)
+    n = 400_000
+    cases = np.empty((n, 9), dtype=np.float32)
+    # game-like: radius 10, |mv| about 4 (also after partial moves), bricks 25x25 / paddle 60x10 near the ball
+    c = rng.uniform(20, 580, size=(n, 2))
+    ang = rng.uniform(0, 2 * np.pi, size=n)
+    ln = np.where(rng.random(n) < 0.7, 4.0, rng.uniform(0.002, 4.0, size=n))
+    w = np.where(rng.random(n) < 0.8, 25.0, 60.0); h = np.where(w == 25.0, 25.0, 10.0)
+    off = rng.uniform(-18, 18, size=(n, 2))
+    cases[:, 0:2] = c; cases[:, 2] = 10.0
+    cases[:, 3] = ln * np.cos(ang); cases[:, 4] = ln * np.sin(ang)
+    # box placed around the ball so that touching / grazing / penetrating configurations are frequent
+    cases[:, 5] = c[:, 0] + off[:, 0] - np.where(off[:, 0] < 0, w, 0); cases[:, 6] = c[:, 1] + off[:, 1] - np.where(off[:, 1] < 0, h, 0)
+    cases[:, 7] = cases[:, 5] + w; cases[:, 8] = cases[:, 6] + h
+    # adversarial quarter: axis-aligned motion, exact touching distances, corners on the diagonal, integer coordinates
+    k = n // 4
+    cases[:k, 0:2] = np.round(cases[:k, 0:2]); cases[:k, 5:9] = np.round(cases[:k, 5:9])
+    cases[: k // 2, 3] = np.where(rng.random(k // 2) < 0.5, 0.0, cases[: k // 2, 3]); cases[k // 2: k, 3] = cases[k // 2: k, 4]
+    g_some, g_surf, g_err = qlb.debug_collision_rect_batch(cases)
+    o_some, o_surf, o_err = O.collision_rect_batch(cases)
+    assert np.array_equal(g_some, o_some), "Some/None differs in %d cases" % int((g_some != o_some).sum())
+    hit = g_some != 0
+    assert 0.02 < hit.mean() < 0.9, "fuzz distribution degenerate: %.3f hits" % hit.mean()
+    assert np.array_equal(g_surf[hit].view(np.uint32), o_surf[hit].view(np.uint32)), "surface bits differ"
+    assert np.array_equal(g_err, o_err)
+    print("fuzz: %d cases, %.1f%% contacts, %d with flags" % (n, 100 * hit.mean(), int((g_err != 0).sum())))
