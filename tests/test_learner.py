@@ -130,3 +130,29 @@ def test_parameter_defaults(qlb):
         (pytest.approx(0.99), 1.0, 0.1, 10_000, 50_000, 1_000_000.0, 1_000_000, 4, 100, 25_000)      # :50-67
     with pytest.raises(qlb.QlError):
         L.Parameter(nope=1)
+
+
+@pytest.mark.gpu
+def test_zero_copy_tensors_equal_the_host_path(qlb, O):
+    """§8f-2: the torch hand-off (gather kernels writing into CUDA tensors) gives the bytes of the host-buffer ABI."""
+    torch = pytest.importorskip("torch")
+    tio = importlib.import_module("q-learning_b200.torch_io")
+    n = 96
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=8, replay_capacity=n * 32)
+    rb = qlb.ReplayBuffer(env)
+    acts = torch.randint(0, 3, (50, n), dtype=torch.uint8, device="cuda")
+    reward, done = tio.step(env, acts)
+    torch.cuda.synchronize()
+    assert float(reward.sum()) >= 0 and rb.len() == n * 32
+    for layout in (qlb.LAYOUT_F32_BXYH, qlb.LAYOUT_U8_BHYX):
+        smp = tio.DeviceSampler(rb, 32, 4, layout).sample(11)
+        torch.cuda.synchronize()
+        idx = smp.indices.cpu().numpy().view(np.uint32)
+        for b in range(4):
+            assert np.array_equal(idx[b], O.sample_distinct(8, 11 + b, rb.len(), 32))
+            host = rb.get_many(idx[b], layout)
+            assert np.array_equal(smp.state[b].cpu().numpy(), host.state) and np.array_equal(smp.state_next[b].cpu().numpy(), host.state_next)
+            assert np.array_equal(smp.reward[b].cpu().numpy(), host.reward) and np.array_equal(smp.action[b].cpu().numpy(), host.action)
+            assert np.array_equal(smp.done[b].cpu().numpy(), host.done)
+        assert np.array_equal(tio.observe(env, layout).cpu().numpy(), env.obs(layout))
+    env.close()
