@@ -55,6 +55,7 @@ extern "C" {
 #define QLC_ENVERR_BISECTION     8u
 #define QLC_ENVERR_DEGENERATE   16u  /* informational: parry2d degenerate-contact branch taken */
 #define QLC_ENVERR_ACTION       32u  /* action byte >= 3 seen on the device path (treated as None) */
+#define QLC_ENVERR_HANDOVER     64u  /* (shard-wide) a time-chunk hand-over between CTAs timed out inside the step kernel */
 
 /* output layouts of the state gather (ToMultiDimArray) */
 #define QLC_LAYOUT_U8_BHYX   0  /* [b][slot h][y][x] u8  — fast path, frame-major                     */

@@ -34,7 +34,7 @@ LAYOUT_F32_BXYH = 1
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_OUT_OF_RANGE, ERR_NO_DEVICE, ERR_NOT_ENOUGH = 0, 1, 2, 3, 4, 5
 
-ENVERR_WALL_DISTANCE, ENVERR_APPROX_RANGE, ENVERR_RECURSION, ENVERR_BISECTION, ENVERR_DEGENERATE, ENVERR_ACTION = 1, 2, 4, 8, 16, 32
+ENVERR_WALL_DISTANCE, ENVERR_APPROX_RANGE, ENVERR_RECURSION, ENVERR_BISECTION, ENVERR_DEGENERATE, ENVERR_ACTION, ENVERR_HANDOVER = 1, 2, 4, 8, 16, 32, 64
 
 # every symbol include/ql_cuda.h declares (checked by tests/test_abi.py against the header and the built library)
 ABI_SYMBOLS = [

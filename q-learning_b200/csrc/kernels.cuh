@@ -33,7 +33,11 @@ struct DeviceStats {                      // order-independent accumulators
 struct StepParams {
     uint32_t n_envs, env_id_base, time_slots, max_episode_steps, auto_reset, n_steps;
     uint32_t debug_skip;       // profiling aid (QLC_DEBUG_SKIP): 1 = no physics, 2 = no frame stores; 0 in production
-    unsigned int* work_counter; uint32_t work_base;   // dynamic batch hand-out: batch = atomicAdd(counter, 1) - base
+    unsigned int* work_counter; uint32_t work_base;   // dynamic work hand-out: item = atomicAdd(counter, 1) - base
+    // time chunking (0 = off): an item is (chunk c, batch b) = steps [c*chunk_len, (c+1)*chunk_len) of batch b; chunk c of a
+    // batch may run on another CTA than chunk c-1 — the env state travels through HBM and `progress[b]` (launch serial << 32 |
+    // steps done) is the release/acquire flag. Lets fast SMs / GPCs take more of a single-wave launch.
+    uint32_t chunk_len; uint32_t launch_serial; unsigned long long* progress; unsigned int* spin_error;
     uint32_t epc;              // envs per CTA (<= R*NE), chosen by the host so that the grid fills all SMs evenly
     uint64_t t0, seed;
     uint8_t* frames; uint32_t* records; DeviceStats* stats;
@@ -76,6 +80,15 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)), "l"(gsrc),
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -178,31 +191,47 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
         uint32_t seq = 0;                                  // (batch, step) items published so far
         for (;;) {
         // env batches are handed out dynamically (SMs differ in their distance to L2/HBM; a static split would wait for the slowest)
-        uint32_t batch = 0;
-        if (lane == 0) batch = atomicAdd(p.work_counter, 1u) - p.work_base;
-        batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
-        if (batch >= n_batches) {
+        const uint32_t n_chunks = p.chunk_len ? (p.n_steps + p.chunk_len - 1) / p.chunk_len : 1u;
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(p.work_counter, 1u) - p.work_base;
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= n_batches * n_chunks) {
             const int q = seq % D;
             if (seq >= (uint32_t)D) mbar_wait(&S.empty[q], ((seq / D) - 1) & 1);
             if (lane == 0) { S.item_n[q] = 0u; mbar_arrive(&S.full[q]); }
             break;
+        }
+        const uint32_t chunk = item / n_batches, batch = item - chunk * n_batches;     // chunk-major: predecessors are handed out first
+        const uint32_t s_begin = p.chunk_len ? chunk * p.chunk_len : 0u;
+        const uint32_t s_end = p.chunk_len ? min(s_begin + p.chunk_len, p.n_steps) : p.n_steps;
+        if (chunk > 0) {
+            // wait until chunk-1 of this batch has been finished (by whichever CTA took it) and its state is visible
+            if (lane == 0) {
+                const unsigned long long want = ((unsigned long long)p.launch_serial << 32) | s_begin;
+                uint32_t polls = 0;
+                while (ld_acquire_u64(&p.progress[batch]) != want) {
+                    __nanosleep(100);
+                    if (++polls > (1u << 24)) { atomicExch(p.spin_error, 1u); break; }     // never hang the GPU
+                }
+            }
+            __syncwarp();
         }
         const uint32_t env0 = batch * EPC;
         const uint32_t n_here = min(EPC, p.n_envs - env0);
         const uint32_t e = env0 + lane;
         const bool active = lane < n_here;
         Env env; uint32_t k = 0, episode = 0;
-        if (active) {
-            env.cx = st.ball_cx[e]; env.cy = st.ball_cy[e]; env.dx = st.ball_dx[e]; env.dy = st.ball_dy[e];
-            env.pmin = st.pad_min_x[e]; env.pmax = st.pad_max_x[e]; env.pspeed = st.pad_speed[e];
-            env.bricks = st.bricks[e]; env.score = st.score[e]; env.err = st.err[e]; env.finished = st.finished[e] != 0;
-            k = st.episode_step[e]; episode = st.episode[e];
+        if (active) {   // __ldcg: read at L2 — with chunking another SM may have written this state during the launch
+            env.cx = __ldcg(&st.ball_cx[e]); env.cy = __ldcg(&st.ball_cy[e]); env.dx = __ldcg(&st.ball_dx[e]); env.dy = __ldcg(&st.ball_dy[e]);
+            env.pmin = __ldcg(&st.pad_min_x[e]); env.pmax = __ldcg(&st.pad_max_x[e]); env.pspeed = __ldcg(&st.pad_speed[e]);
+            env.bricks = __ldcg(&st.bricks[e]); env.score = __ldcg(&st.score[e]); env.err = __ldcg(&st.err[e]); env.finished = __ldcg(&st.finished[e]) != 0;
+            k = __ldcg(&st.episode_step[e]); episode = __ldcg(&st.episode[e]);
         } else {
             env_init(env, -0.25f); env.err = 0;
         }
         MoveCache mc; move_cache_update(mc, env);
-        uint32_t action = active ? p.actions[e] : 0u;
-        for (uint32_t s = 0; s < p.n_steps; ++s, ++seq) {
+        uint32_t action = active ? p.actions[(size_t)s_begin * p.n_envs + e] : 0u;
+        for (uint32_t s = s_begin; s < s_end; ++s, ++seq) {
             const int q = seq % D;
             uint32_t next_action = 0u;
             if (active && s + 1 < p.n_steps) next_action = p.actions[(size_t)(s + 1) * p.n_envs + e];
@@ -249,7 +278,12 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             st.bricks[e] = env.bricks; st.score[e] = env.score; st.err[e] = env.err; st.finished[e] = env.finished ? 1 : 0;
             st.episode_step[e] = k; st.episode[e] = episode;
         }
-        }   // batches
+        if (p.chunk_len) {   // publish: state stores of all lanes, then the flag (release)
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release_u64(&p.progress[batch], ((unsigned long long)p.launch_serial << 32) | s_end);
+        }
+        }   // items
     } else {
         // ------------------------------- render warps -------------------------------
         const int rw = warp - 1;

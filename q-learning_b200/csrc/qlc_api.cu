@@ -29,8 +29,12 @@ struct qlc_env {
     uint32_t* records = nullptr;
     DeviceStats* stats = nullptr;
     unsigned long long* scratch = nullptr;     // 8 x u64 device scratch (histogram, err OR)
-    unsigned int* work_counter = nullptr;      // dynamic env-batch hand-out of the step kernel
+    unsigned int* work_counter = nullptr;      // dynamic work hand-out of the step kernel
     uint32_t work_base = 0;
+    unsigned long long* progress = nullptr;    // per env batch: launch serial << 32 | steps done (time-chunk hand-over flag)
+    unsigned int* spin_error = nullptr;
+    uint32_t launch_serial = 0;
+    int chunk_override = -1;                   // QLC_CHUNK: force the chunk length (0 = off)
     uint32_t time_slots = 0;                   // frame/record ring length in time steps (= t_cap + 4)
     uint32_t t_cap = 0;                        // replay capacity in time steps
     uint64_t t = 0;                            // env-steps taken per env (global time)
@@ -128,6 +132,7 @@ int32_t qlc_env_create(const qlc_config* cfg, qlc_env** out) {
     if (const char* c = getenv("QLC_EPC")) env->epc_override = atoi(c);
     if (const char* c = getenv("QLC_DEBUG_SKIP")) env->debug_skip = atoi(c);
     if (const char* c = getenv("QLC_PERSISTENT")) env->persistent = atoi(c);
+    if (const char* c = getenv("QLC_CHUNK")) env->chunk_override = atoi(c);
     env->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
 
 #define TRY_ALLOC(x) do { rc = (x); if (rc) { qlc_env_destroy(env); return rc; } } while (0)
@@ -149,6 +154,8 @@ int32_t qlc_env_create(const qlc_config* cfg, qlc_env** out) {
     TRY_ALLOC(dev_alloc(env, &env->stats, 1, false));
     TRY_ALLOC(dev_alloc(env, &env->scratch, 8, true));
     TRY_ALLOC(dev_alloc(env, &env->work_counter, 1, true));
+    TRY_ALLOC(dev_alloc(env, &env->progress, n, true));
+    TRY_ALLOC(dev_alloc(env, &env->spin_error, 1, true));
 #undef TRY_ALLOC
     cudaError_t ce = cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { qlc_env_destroy(env); return fail(QLC_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(ce)); }
@@ -208,7 +215,7 @@ static uint32_t pick_epc(uint32_t n_envs, uint32_t sms, uint32_t max_epc) {
 }
 
 template <int R, int NE, int D, int MINB>
-static int32_t launch_advance(qlc_env* env, StepParams& p, cudaStream_t s) {
+static int32_t launch_advance(qlc_env* env, StepParams& p, cudaStream_t s, uint32_t chunk_request) {
     static bool configured[64] = {};
     const size_t dyn = (size_t)R * NE * FRAME_BYTES;
     auto kern = env_advance_kernel<R, NE, D, MINB>;
@@ -219,18 +226,30 @@ static int32_t launch_advance(qlc_env* env, StepParams& p, cudaStream_t s) {
     p.epc = env->epc_override ? (uint32_t)env->epc_override : pick_epc(p.n_envs, (uint32_t)env->sm_count, R * NE);
     if (p.epc > (uint32_t)(R * NE)) p.epc = R * NE;
     const uint32_t n_batches = (p.n_envs + p.epc - 1) / p.epc;
+    static int occ[64] = {};
+    int& o = occ[env->cfg.device & 63];
+    if (o == 0) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, 32 * (R + 1), dyn));
+    const uint32_t resident = (uint32_t)(o > 0 ? o : 1) * (uint32_t)env->sm_count;
+    uint32_t chunk = env->persistent ? chunk_request : 0u;
+    if (env->chunk_override >= 0) chunk = env->persistent ? (uint32_t)env->chunk_override : 0u;
+    if (chunk >= p.n_steps) chunk = 0;
+    const uint32_t n_chunks = chunk ? (p.n_steps + chunk - 1) / chunk : 1u;
     uint32_t grid = n_batches;
-    if (env->persistent) {       // CTAs walk the env batches; frames, raster tables and barriers are set up once per CTA
-        static int occ[64] = {};
-        int& o = occ[env->cfg.device & 63];
-        if (o == 0) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, 32 * (R + 1), dyn));
-        const uint32_t resident = (uint32_t)(o > 0 ? o : 1) * (uint32_t)env->sm_count;
+    if (env->persistent) {       // CTAs take (chunk, batch) items; frames, raster tables and barriers are set up once per CTA
+        grid = n_batches * n_chunks;
         if (grid > resident) grid = resident;
     }
     p.work_counter = env->work_counter; p.work_base = env->work_base;
-    kern<<<grid, 32 * (R + 1), dyn, s>>>(env->st, p);
+    p.chunk_len = chunk; p.launch_serial = ++env->launch_serial; p.progress = env->progress; p.spin_error = env->spin_error;
+    if (chunk) {
+        // CTAs wait on one another (chunk c of a batch on chunk c-1): a cooperative launch guarantees co-residency
+        void* args[] = {(void*)&env->st, (void*)&p};
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(32 * (R + 1)), args, dyn, s));
+    } else {
+        kern<<<grid, 32 * (R + 1), dyn, s>>>(env->st, p);
+    }
     CUDA_TRY(cudaGetLastError());
-    env->work_base += n_batches + grid;      // every CTA ends with one failed grab
+    env->work_base += n_batches * n_chunks + grid;      // every CTA ends with one failed grab
     return QLC_OK;
 }
 
@@ -247,15 +266,24 @@ int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps,
     p.actions = actions_dev; p.reward = reward_dev; p.done = done_dev;
     p.debug_skip = (uint32_t)env->debug_skip;
     cudaStream_t s = (cudaStream_t)stream;
+    // Shape selection (measured, profiles/r01_notes.md). Launches that are only a few waves of work are cut into
+    // (time chunk, 8-env batch) items handed out dynamically, so that every SM / GPC keeps pulling work at its own pace —
+    // this removes a 10-15 % GPU-to-GPU spread seen with one static 32-env batch per SM. Big shards are balanced by their
+    // many batches alone; short launches (< 8 steps) have nothing to chunk.
     int cfg = env->advance_cfg;
-    if (cfg == 0) cfg = (p.n_envs <= (uint32_t)env->sm_count * 32u || n_steps < 4u) ? 1 : 5;   // measured: profiles/r01_notes.md
+    uint32_t chunk = 0;
+    const uint32_t sms = (uint32_t)env->sm_count;
+    if (cfg == 0) {
+        if (n_steps >= 8u && p.n_envs >= sms * 16u && p.n_envs <= sms * 96u) { cfg = 5; chunk = n_steps / 4u; chunk = chunk < 4u ? 4u : (chunk > 16u ? 16u : chunk); }
+        else cfg = (p.n_envs <= sms * 32u || n_steps < 4u) ? 1 : 5;
+    }
     switch (cfg) {
-        case 1: rc = launch_advance<8, 4, 4, 1>(env, p, s); break;    // <= 32 envs / CTA, 1 CTA / SM
-        case 2: rc = launch_advance<8, 2, 2, 2>(env, p, s); break;    // <= 16 envs / CTA, 2 CTAs / SM
-        case 3: rc = launch_advance<4, 4, 4, 2>(env, p, s); break;    // <= 16 envs / CTA, fewer warps
-        case 4: rc = launch_advance<4, 2, 4, 3>(env, p, s); break;    // <=  8 envs / CTA
-        case 5: rc = launch_advance<8, 1, 4, 3>(env, p, s); break;    // <=  8 envs / CTA, 3 CTAs / SM
-        case 6: rc = launch_advance<16, 2, 4, 1>(env, p, s); break;   // <= 32 envs / CTA, 16 render warps
+        case 1: rc = launch_advance<8, 4, 4, 1>(env, p, s, chunk); break;    // <= 32 envs / batch, 1 CTA / SM
+        case 2: rc = launch_advance<8, 2, 2, 2>(env, p, s, chunk); break;    // <= 16 envs / batch, 2 CTAs / SM
+        case 3: rc = launch_advance<4, 4, 4, 2>(env, p, s, chunk); break;    // <= 16 envs / batch, fewer warps
+        case 4: rc = launch_advance<4, 2, 4, 3>(env, p, s, chunk); break;    // <=  8 envs / batch
+        case 5: rc = launch_advance<8, 1, 4, 3>(env, p, s, chunk); break;    // <=  8 envs / batch, 3 CTAs / SM
+        case 6: rc = launch_advance<16, 2, 4, 1>(env, p, s, chunk); break;   // <= 32 envs / batch, 16 render warps
         default: return fail(QLC_ERR_INVALID_ARG, "unknown QLC_ADVANCE_CFG");
     }
     if (rc) return rc;
@@ -393,6 +421,9 @@ int32_t qlc_env_error_flags(qlc_env* env, uint32_t* out) {
     err_or_kernel<<<64, 256>>>(env->st.err, env->cfg.n_envs, (uint32_t*)env->scratch);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(out, env->scratch, 4, cudaMemcpyDeviceToHost));
+    unsigned int spin = 0;
+    CUDA_TRY(cudaMemcpy(&spin, env->spin_error, 4, cudaMemcpyDeviceToHost));
+    if (spin) *out |= QLC_ENVERR_HANDOVER;
     return QLC_OK;
 }
 

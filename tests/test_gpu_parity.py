@@ -93,12 +93,15 @@ def test_trajectory_parity(qlb, O, n_envs, chunks, seed):
     env.close()
 
 
-@pytest.mark.parametrize("cfg,epc", [(1, 0), (2, 0), (3, 0), (4, 0), (5, 0), (6, 0), (1, 28), (1, 5), (2, 13), (6, 31), (5, 1)])
-def test_all_kernel_shapes_agree(qlb, O, cfg, epc, monkeypatch):
-    """Every instantiated CTA shape of the fused kernel (render warps x resident frames per warp) and any
-    envs-per-CTA split gives the same bits."""
+@pytest.mark.parametrize("cfg,epc,chunk", [(1, 0, -1), (2, 0, -1), (3, 0, -1), (4, 0, -1), (5, 0, -1), (6, 0, -1), (1, 28, 0), (1, 5, 4), (2, 13, 1),
+                                           (6, 31, 3), (5, 1, 7), (1, 3, 2), (2, 2, 5), (5, 4, 4)])
+def test_all_kernel_shapes_agree(qlb, O, cfg, epc, chunk, monkeypatch):
+    """Every instantiated CTA shape of the fused kernel (render warps x resident frames per warp), any envs-per-batch
+    split and any time-chunk length (env state handed from CTA to CTA through HBM) gives the same bits."""
     monkeypatch.setenv("QLC_ADVANCE_CFG", str(cfg))
     monkeypatch.setenv("QLC_EPC", str(epc))
+    if chunk >= 0:
+        monkeypatch.setenv("QLC_CHUNK", str(chunk))
     n, seed = 77, 31
     env = qlb.BreakoutEnvironment(n_envs=n, seed=seed, replay_capacity=n * 8)
     ora = O.VecEnv(n, seed=seed)
