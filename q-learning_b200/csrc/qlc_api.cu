@@ -35,6 +35,7 @@ struct qlc_env {
     unsigned int* spin_error = nullptr;
     uint32_t launch_serial = 0;
     int chunk_override = -1;                   // QLC_CHUNK: force the chunk length (0 = off)
+    int zero_copy = 1;                         // QLC_ZERO_COPY=0: always stage page-locked outputs through a D2H copy
     uint32_t time_slots = 0;                   // frame/record ring length in time steps (= t_cap + 4)
     uint32_t t_cap = 0;                        // replay capacity in time steps
     uint64_t t = 0;                            // env-steps taken per env (global time)
@@ -133,6 +134,7 @@ int32_t qlc_env_create(const qlc_config* cfg, qlc_env** out) {
     if (const char* c = getenv("QLC_DEBUG_SKIP")) env->debug_skip = atoi(c);
     if (const char* c = getenv("QLC_PERSISTENT")) env->persistent = atoi(c);
     if (const char* c = getenv("QLC_CHUNK")) env->chunk_override = atoi(c);
+    if (const char* c = getenv("QLC_ZERO_COPY")) env->zero_copy = atoi(c);
     env->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
 
 #define TRY_ALLOC(x) do { rc = (x); if (rc) { qlc_env_destroy(env); return rc; } } while (0)
@@ -314,15 +316,21 @@ int32_t qlc_env_step_host(qlc_env* env, const uint8_t* actions_host, uint32_t n_
     const bool pin_a = is_pinned(actions_host), pin_r = !reward_host || is_pinned(reward_host), pin_d = !done_host || is_pinned(done_host);
     uint8_t* pin = nullptr;
     if (!(pin_a && pin_r && pin_d)) { rc = ensure_pin(env, total); if (rc) return rc; pin = (uint8_t*)env->pin; }
-    if (pin_a) {
+    const uint8_t* actions_dev = dev;
+    if (pin_a && env->zero_copy >= 2) {
+        actions_dev = actions_host;             // the physics lanes read (and prefetch) the action bytes straight from host memory
+    } else if (pin_a) {
         CUDA_TRY(cudaMemcpyAsync(dev, actions_host, n, cudaMemcpyHostToDevice, s));
     } else {
         memcpy(pin, actions_host, n);
         CUDA_TRY(cudaMemcpyAsync(dev, pin, n, cudaMemcpyHostToDevice, s));
     }
-    rc = qlc_env_step(env, dev, n_steps, (float*)(dev + off_r), dev + off_d, s); if (rc) return rc;
-    if (reward_host) CUDA_TRY(cudaMemcpyAsync(pin_r ? (void*)reward_host : (void*)(pin + off_r), dev + off_r, n * 4, cudaMemcpyDeviceToHost, s));
-    if (done_host) CUDA_TRY(cudaMemcpyAsync(pin_d ? (void*)done_host : (void*)(pin + off_d), dev + off_d, n, cudaMemcpyDeviceToHost, s));
+    // page-locked outputs are written by the kernel itself (zero-copy stores over PCIe while it runs, UVA pointers);
+    // pageable ones go through device staging + a device->host copy
+    const bool zc_r = reward_host && pin_r && env->zero_copy, zc_d = done_host && pin_d && env->zero_copy;
+    rc = qlc_env_step(env, actions_dev, n_steps, zc_r ? reward_host : (float*)(dev + off_r), zc_d ? done_host : dev + off_d, s); if (rc) return rc;
+    if (reward_host && !zc_r) CUDA_TRY(cudaMemcpyAsync(pin_r ? (void*)reward_host : (void*)(pin + off_r), dev + off_r, n * 4, cudaMemcpyDeviceToHost, s));
+    if (done_host && !zc_d) CUDA_TRY(cudaMemcpyAsync(pin_d ? (void*)done_host : (void*)(pin + off_d), dev + off_d, n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (reward_host && !pin_r) memcpy(reward_host, pin + off_r, n * 4);
     if (done_host && !pin_d) memcpy(done_host, pin + off_d, n);
