@@ -86,10 +86,17 @@ extern "C" {
     pub fn qlc_replay_gather_host(env: *mut qlc_env, idx_host: *const u32, n: u32, layout: i32, state_host: *mut c_void, next_host: *mut c_void,
                                   reward_host: *mut f32, action_host: *mut u8, done_host: *mut u8) -> i32;
     pub fn qlc_replay_action_counts(env: *mut qlc_env, counts: *mut u64) -> i32;
+    pub fn qlc_env_save(env: *mut qlc_env, path: *const c_char) -> i32;
+    pub fn qlc_env_load(env: *mut qlc_env, path: *const c_char) -> i32;
     pub fn qlc_stats_read(env: *mut qlc_env, out: *mut qlc_episode_stats) -> i32;
     pub fn qlc_stats_export(env: *mut qlc_env, out_dev: *mut f64, stream: *mut c_void) -> i32;
     pub fn qlc_stats_push(env: *mut qlc_env, episode_reward: f32) -> i32;
     pub fn qlc_stats_mean(env: *mut qlc_env, out: *mut f32) -> i32;
     pub fn qlc_stats_min(env: *mut qlc_env, out: *mut f32) -> i32;
     pub fn qlc_stats_window(env: *mut qlc_env, out: *mut f32, cap: u32, n: *mut u32) -> i32;
+    pub fn qlc_debug_collision_wall(which: i32, cx: f32, cy: f32, radius: f32, mvx: f32, mvy: f32, some: *mut i32, way: *mut f32,
+                                    approximation: *mut f32, nx: *mut f32, ny: *mut f32, err: *mut u32) -> i32;
+    pub fn qlc_debug_collision_rect(cx: f32, cy: f32, radius: f32, mvx: f32, mvy: f32, min_x: f32, min_y: f32, max_x: f32, max_y: f32,
+                                    some: *mut i32, way: *mut f32, approximation: *mut f32, nx: *mut f32, ny: *mut f32, err: *mut u32) -> i32;
+    pub fn qlc_debug_collision_rect_batch(in_host: *const f32, out_host: *mut f32, n: u32) -> i32;
 }

@@ -168,6 +168,12 @@ int32_t qlc_stats_mean(qlc_env* env, float* out);                     /* avg_epi
 int32_t qlc_stats_min(qlc_env* env, float* out);                      /* min_episode_reward */
 int32_t qlc_stats_window(qlc_env* env, float* out, uint32_t cap, uint32_t* n);  /* episode_rewards() */
 
+/* ---- checkpoint / resume of the env shard + replay ring (the reference checkpoints only the model:
+ * q_learning_model.rs:191-202). qlc_env_load needs an env created with the same n_envs / env_id_base / seed /
+ * replay_capacity / episode limits; a resumed run continues bit-identically. Synchronous. ---- */
+int32_t qlc_env_save(qlc_env* env, const char* path);
+int32_t qlc_env_load(qlc_env* env, const char* path);
+
 /* ---- debug / known-answer entry points: run the DEVICE collision routines on the GPU for one input
  * (used to replay the reference's rstest vectors mechanics.rs:659-752 through the product code) ---- */
 int32_t qlc_debug_collision_wall(int32_t which /*0 left,1 right,2 top*/, float cx, float cy, float radius, float mvx, float mvy,

@@ -44,6 +44,7 @@ ABI_SYMBOLS = [
     "qlc_env_read_state", "qlc_env_goal_mean", "qlc_env_time", "qlc_env_error_flags",
     "qlc_replay_len", "qlc_replay_capacity", "qlc_replay_sample", "qlc_replay_gather", "qlc_replay_sample_host",
     "qlc_replay_gather_host", "qlc_replay_action_counts",
+    "qlc_env_save", "qlc_env_load",
     "qlc_stats_read", "qlc_stats_export", "qlc_stats_push", "qlc_stats_mean", "qlc_stats_min", "qlc_stats_window",
     "qlc_debug_collision_wall", "qlc_debug_collision_rect", "qlc_debug_collision_rect_batch",
 ]
@@ -127,6 +128,8 @@ def load_library(build_if_missing=True):
         "qlc_replay_sample_host": (i32, [vp, u32, u64, vp]),
         "qlc_replay_gather_host": (i32, [vp, vp, u32, i32, vp, vp, vp, vp, vp]),
         "qlc_replay_action_counts": (i32, [vp, vp]),
+        "qlc_env_save": (i32, [vp, C.c_char_p]),
+        "qlc_env_load": (i32, [vp, C.c_char_p]),
         "qlc_stats_read": (i32, [vp, C.POINTER(QlcEpisodeStats)]),
         "qlc_stats_export": (i32, [vp, vp, vp]),
         "qlc_stats_push": (i32, [vp, C.c_float]),
@@ -350,6 +353,14 @@ class BreakoutEnvironment:
 
     def sync(self, stream=None):
         _check(self._L.qlc_sync(self._h, stream))
+
+    def save(self, path):
+        """Checkpoint the env shard + replay ring (SoA state, records, frames, statistics, episode window)."""
+        _check(self._L.qlc_env_save(self._h, os.fsencode(path)))
+
+    def load(self, path):
+        """Resume from a checkpoint taken with the same configuration; the run continues bit-identically."""
+        _check(self._L.qlc_env_load(self._h, os.fsencode(path)))
 
     # -- shard statistics
     def stats(self):

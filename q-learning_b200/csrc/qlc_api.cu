@@ -579,6 +579,88 @@ int32_t qlc_stats_window(qlc_env* env, float* out, uint32_t cap, uint32_t* n) { 
     return QLC_OK;
 }
 
+// ---------------- checkpoint / resume (the reference checkpoints only the model) ----------------
+namespace {
+struct CkptHeader {
+    char magic[8];                 // "QLCCKPT1"
+    uint32_t version, header_bytes;
+    qlc_config cfg;
+    uint32_t time_slots, t_cap;
+    uint64_t t;
+    DeviceStats stats;
+    uint32_t window_len, reserved;
+};
+struct CkptArray { void* ptr; size_t bytes; };
+
+static std::vector<CkptArray> ckpt_arrays(qlc_env* env) {
+    const size_t n = env->cfg.n_envs;
+    return {
+        {env->st.ball_cx, n * 4}, {env->st.ball_cy, n * 4}, {env->st.ball_dx, n * 4}, {env->st.ball_dy, n * 4},
+        {env->st.pad_min_x, n * 4}, {env->st.pad_max_x, n * 4}, {env->st.pad_speed, n * 4}, {env->st.bricks, n * 8},
+        {env->st.score, n * 4}, {env->st.episode_step, n * 4}, {env->st.episode, n * 4}, {env->st.err, n * 4}, {env->st.finished, n},
+        {env->records, (size_t)env->time_slots * n * 4}, {env->frames, (size_t)env->time_slots * n * FRAME_BYTES},
+    };
+}
+}  // namespace
+
+int32_t qlc_env_save(qlc_env* env, const char* path) {
+    if (!env || !path) return fail(QLC_ERR_INVALID_ARG, "env/path is null");
+    int32_t rc = set_device(env); if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(QLC_ERR_INVALID_ARG, std::string("cannot open ") + path);
+    CkptHeader h{};
+    memcpy(h.magic, "QLCCKPT1", 8); h.version = 1; h.header_bytes = sizeof h; h.cfg = env->cfg;
+    h.time_slots = env->time_slots; h.t_cap = env->t_cap; h.t = env->t; h.window_len = (uint32_t)env->window.size();
+    cudaError_t e = cudaMemcpy(&h.stats, env->stats, sizeof h.stats, cudaMemcpyDeviceToHost);
+    bool ok = e == cudaSuccess && fwrite(&h, sizeof h, 1, f) == 1;
+    for (float v : env->window) ok = ok && fwrite(&v, 4, 1, f) == 1;
+    const size_t CH = (size_t)64 << 20;
+    if (ok && ensure_pin(env, CH) != QLC_OK) ok = false;
+    for (const CkptArray& a : ckpt_arrays(env)) {
+        for (size_t off = 0; ok && off < a.bytes; off += CH) {
+            const size_t m = a.bytes - off < CH ? a.bytes - off : CH;
+            ok = cudaMemcpy(env->pin, (const char*)a.ptr + off, m, cudaMemcpyDeviceToHost) == cudaSuccess && fwrite(env->pin, 1, m, f) == m;
+        }
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(QLC_ERR_CUDA, std::string("writing checkpoint failed: ") + path);
+    return QLC_OK;
+}
+
+int32_t qlc_env_load(qlc_env* env, const char* path) {
+    if (!env || !path) return fail(QLC_ERR_INVALID_ARG, "env/path is null");
+    int32_t rc = set_device(env); if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(QLC_ERR_INVALID_ARG, std::string("cannot open ") + path);
+    CkptHeader h{};
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "QLCCKPT1", 8) != 0 || h.version != 1 || h.header_bytes != sizeof h) {
+        fclose(f); return fail(QLC_ERR_INVALID_ARG, "not a ql_cuda checkpoint (or another version)");
+    }
+    const qlc_config& a = h.cfg; const qlc_config& b = env->cfg;
+    if (a.n_envs != b.n_envs || a.env_id_base != b.env_id_base || a.seed != b.seed || h.time_slots != env->time_slots || h.t_cap != env->t_cap ||
+        a.max_episode_steps != b.max_episode_steps || a.auto_reset != b.auto_reset) {
+        fclose(f); return fail(QLC_ERR_INVALID_ARG, "checkpoint was taken with a different configuration (n_envs / env_id_base / seed / replay_capacity / episode limits)");
+    }
+    bool ok = true;
+    std::deque<float> window;
+    for (uint32_t i = 0; ok && i < h.window_len; ++i) { float v; ok = fread(&v, 4, 1, f) == 1; window.push_back(v); }
+    const size_t CH = (size_t)64 << 20;
+    if (ok && ensure_pin(env, CH) != QLC_OK) ok = false;
+    for (const CkptArray& arr : ckpt_arrays(env)) {
+        for (size_t off = 0; ok && off < arr.bytes; off += CH) {
+            const size_t m = arr.bytes - off < CH ? arr.bytes - off : CH;
+            ok = fread(env->pin, 1, m, f) == m && cudaMemcpy((char*)arr.ptr + off, env->pin, m, cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+    }
+    fclose(f);
+    if (ok) ok = cudaMemcpy(env->stats, &h.stats, sizeof h.stats, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) return fail(QLC_ERR_CUDA, std::string("reading checkpoint failed (the env state is now undefined): ") + path);
+    env->t = h.t; env->window = window;
+    return QLC_OK;
+}
+
 // ---------------- debug / known-answer ----------------
 static int32_t run_debug(int which, float cx, float cy, float r, float mvx, float mvy, float minx, float miny, float maxx, float maxy,
                          int32_t* some, float* way, float* approx, float* nx, float* ny, uint32_t* err) {

@@ -512,3 +512,35 @@ def test_device_sweep_fuzz_vs_oracle(qlb, O):
     assert np.array_equal(g_surf[hit].view(np.uint32), o_surf[hit].view(np.uint32)), "surface bits differ"
     assert np.array_equal(g_err, o_err)
     print("fuzz: %d cases, %.1f%% contacts, %d with flags" % (n, 100 * hit.mean(), int((g_err != 0).sum())))
+
+
+def test_checkpoint_resume_is_bit_identical(qlb, O, tmp_path):
+    """save the env shard + replay ring, resume in a fresh env, continue — identical to never stopping."""
+    n, seed, cap = 160, 66, 160 * 24
+    acts = O.synthetic_actions(seed, 0, n, 0, 90)
+    a = qlb.BreakoutEnvironment(n_envs=n, seed=seed, replay_capacity=cap, max_episode_steps=200)
+    ra = qlb.ReplayBuffer(a)
+    a.step_many(acts[:60])
+    ra.add_episode_reward(3.0); ra.add_episode_reward(7.0)
+    path = str(tmp_path / "shard.qlc")
+    a.save(path)
+    a.step_many(acts[60:])
+    b = qlb.BreakoutEnvironment(n_envs=n, seed=seed, replay_capacity=cap, max_episode_steps=200)
+    rb = qlb.ReplayBuffer(b)
+    b.load(path)
+    assert b.time() == 60 and rb.len() == ra.len() and rb.episode_rewards().tolist() == [3.0, 7.0]
+    b.step_many(acts[60:])
+    sa, sb = a.read_state(), b.read_state()
+    for k in sa:
+        assert np.array_equal(sa[k].view(np.uint8), sb[k].view(np.uint8)), k
+    assert np.array_equal(a.obs(), b.obs()) and a.stats() == b.stats()
+    idx = ra.generate_distinct_random_ids(64, 3)
+    assert np.array_equal(idx, rb.generate_distinct_random_ids(64, 3))
+    ga, gb = ra.get_many(idx, qlb.LAYOUT_U8_BHYX), rb.get_many(idx, qlb.LAYOUT_U8_BHYX)
+    assert np.array_equal(ga.state, gb.state) and np.array_equal(ga.state_next, gb.state_next) and np.array_equal(ga.reward, gb.reward)
+    # a differently configured env refuses the file
+    c = qlb.BreakoutEnvironment(n_envs=n, seed=seed + 1, replay_capacity=cap, max_episode_steps=200)
+    with pytest.raises(qlb.QlError):
+        c.load(path)
+    for e in (a, b, c):
+        e.close()
