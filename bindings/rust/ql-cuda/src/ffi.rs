@@ -49,6 +49,29 @@ pub struct qlc_state_host {
     pub finished: *mut u8,
 }
 
+/// device pointers to the structure-of-arrays env state (valid until qlc_env_destroy)
+#[repr(C)]
+pub struct qlc_state_view {
+    pub ball_cx: *const f32,
+    pub ball_cy: *const f32,
+    pub ball_dx: *const f32,
+    pub ball_dy: *const f32,
+    pub pad_min_x: *const f32,
+    pub pad_max_x: *const f32,
+    pub pad_speed: *const f32,
+    pub bricks: *const u64,
+    pub score: *const u32,
+    pub episode_step: *const u32,
+    pub episode: *const u32,
+    pub err: *const u32,
+    pub finished: *const u8,
+    pub frames: *const u8,
+    pub records: *const u32,
+    pub n_envs: u32,
+    pub time_slots: u32,
+    pub time: u64,
+}
+
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
 pub struct qlc_episode_stats {
@@ -73,6 +96,7 @@ extern "C" {
     pub fn qlc_env_step_host(env: *mut qlc_env, actions_host: *const u8, n_steps: u32, reward_host: *mut f32, done_host: *mut u8) -> i32;
     pub fn qlc_env_obs(env: *mut qlc_env, layout: i32, out_dev: *mut c_void, stream: *mut c_void) -> i32;
     pub fn qlc_env_obs_host(env: *mut qlc_env, layout: i32, out_host: *mut c_void) -> i32;
+    pub fn qlc_env_state_view(env: *mut qlc_env, out: *mut qlc_state_view) -> i32;
     pub fn qlc_env_read_state(env: *mut qlc_env, out: *const qlc_state_host) -> i32;
     pub fn qlc_env_goal_mean() -> f32;
     pub fn qlc_env_time(env: *mut qlc_env, steps_taken: *mut u64) -> i32;

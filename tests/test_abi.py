@@ -83,3 +83,17 @@ def test_action_enum(qlb):
     assert A.try_from_numeric(2) is A.RIGHT
     with pytest.raises(qlb.QlError):
         A.try_from_numeric(3)
+
+
+def test_rust_ffi_mirrors_the_header():
+    """bindings/rust/ql-cuda/src/ffi.rs (source only, no cargo here) declares every entry point of include/ql_cuda.h and
+    its #[repr(C)] qlc_config has the header's fields in order."""
+    ffi = open(os.path.join(ROOT, "bindings", "rust", "ql-cuda", "src", "ffi.rs")).read()
+    rust_syms = sorted(set(re.findall(r"pub fn (qlc_[a-z0-9_]+)\s*\(", ffi)))
+    assert rust_syms == _header_symbols()
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ql_cuda.h")).read(), flags=re.S)
+    cfg_c = re.search(r"typedef struct qlc_config \{(.*?)\} qlc_config;", hdr, flags=re.S).group(1)
+    c_fields = [n for decl in cfg_c.split(";") for n in re.findall(r"([a-z_0-9]+)\s*(?:,|$)", decl.split(None, 1)[1] if decl.strip() else "")]
+    cfg_r = re.search(r"pub struct qlc_config \{(.*?)\}", ffi, flags=re.S).group(1)
+    r_fields = re.findall(r"pub ([a-z_0-9]+):", cfg_r)
+    assert r_fields == c_fields, (r_fields, c_fields)
