@@ -156,3 +156,18 @@ def test_zero_copy_tensors_equal_the_host_path(qlb, O):
             assert np.array_equal(smp.done[b].cpu().numpy(), host.done)
         assert np.array_equal(tio.observe(env, layout).cpu().numpy(), env.obs(layout))
     env.close()
+
+
+@pytest.mark.gpu
+def test_torch_dqn_example_runs_on_device(qlb):
+    """examples/dqn_breakout_torch.py: env + replay (this repo) feeding a torch Q-network with no host round trip."""
+    pytest.importorskip("torch")
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("dqn_example", os.path.join(root, "examples", "dqn_breakout_torch.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.run(n_envs=256, iterations=60, batch=32, quiet=True)
+    assert out["env_steps"] == 256 * 60 and out["train_calls"] >= 50 and np.isfinite(out["last_loss"])
+    assert out["epsilon"] < 1.0 and out["error_flags"] & ~qlb.ENVERR_DEGENERATE == 0
