@@ -544,3 +544,41 @@ def test_checkpoint_resume_is_bit_identical(qlb, O, tmp_path):
         c.load(path)
     for e in (a, b, c):
         e.close()
+
+
+def test_shard_of_65536_envs(qlb, O):
+    """BASELINE configs[3] shard size: 65,536 envs on one GPU (multi-wave, unchunked 8-env batches) — spot-checked envs
+    against the oracle, frame values, statistics identities, replay chaining."""
+    n, seed, k = 65536, 909, 48
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=seed, env_id_base=1_000_000, replay_capacity=n * 16)
+    rb = qlb.ReplayBuffer(env)
+    rng = np.random.default_rng(12)
+    acts = rng.integers(0, 3, size=(k, n), dtype=np.uint8)
+    reward, done = env.step_many(acts[:16])
+    r2, d2 = env.step_many(acts[16:17])          # a single-step launch in between (32-env batches)
+    r3, d3 = env.step_many(acts[17:])
+    reward = np.concatenate([reward, r2, r3]); done = np.concatenate([done, d2, d3])
+    st = env.read_state()
+    for e in (0, 7, 4095, 32768, 65535):
+        o = O.VecEnv(1, seed=seed, env_id_base=1_000_000 + e)
+        for t in range(k):
+            r, d = o.step(acts[t, e:e + 1])
+            assert r[0] == reward[t, e] and d[0] == done[t, e], (e, t)
+        so = o.state()
+        for key in STATE_F32 + STATE_INT:
+            assert so[key][0] == st[key][e], (key, e)
+        o.close()
+    s = env.stats()
+    assert s["steps"] == n * k and s["episodes"] == int(done.sum())
+    assert s["sum_return"] + int(st["score"].sum()) == int(reward.sum())
+    assert rb.len() == n * 16
+    idx = rb.generate_distinct_random_ids(512, 1)
+    g = rb.get_many(idx, qlb.LAYOUT_U8_BHYX)
+    assert set(np.unique(g.state).tolist()) <= {0, 96, 236, 255}
+    tt, ee = (k - 16) + idx // n, idx % n
+    assert np.array_equal(g.action, acts[tt, ee]) and np.array_equal(g.reward, reward[tt, ee]) and np.array_equal(g.done, done[tt, ee])
+    nxt = idx + n
+    ok = (nxt < rb.len()) & (g.done == 0)
+    assert np.array_equal(g.state_next[ok], rb.get_many(nxt[ok], qlb.LAYOUT_U8_BHYX).state)
+    assert env.error_flags() & ~qlb.ENVERR_DEGENERATE == 0
+    env.close()
