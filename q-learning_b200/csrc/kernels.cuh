@@ -30,10 +30,13 @@ struct DeviceStats {                      // order-independent accumulators
     unsigned int min_return, max_return;
 };
 
+struct RasterTables;
+
 struct StepParams {
     uint32_t n_envs, env_id_base, time_slots, max_episode_steps, auto_reset, n_steps;
     uint32_t debug_skip;       // profiling aid (QLC_DEBUG_SKIP): 1 = no physics, 2 = no frame stores; 0 in production
-    unsigned int* work_counter; uint32_t work_base;   // dynamic work hand-out: item = atomicAdd(counter, 1) - base
+    const RasterTables* tables;   // built once per env handle by raster_tables_kernel
+    unsigned int* work_counter; uint32_t work_base;   // work hand-out: first item = blockIdx.x, then gridDim.x + atomicAdd(counter, 1) - base
     // time chunking (0 = off): an item is (chunk c, batch b) = steps [c*chunk_len, (c+1)*chunk_len) of batch b; chunk c of a
     // batch may run on another CTA than chunk c-1 — the env state travels through HBM and `progress[b]` (launch serial << 32 |
     // steps done) is the release/acquire flag. Lets fast SMs / GPCs take more of a single-wave launch.
@@ -138,6 +141,14 @@ __device__ __forceinline__ void build_raster_tables(RasterTables& T, int tid, in
     __syncthreads();
 }
 
+// one-time table build (env creation): the per-launch prologue only copies the ~1 KB result into shared memory
+__global__ void raster_tables_kernel(RasterTables* out) {
+    __shared__ RasterTables T;
+    build_raster_tables(T, threadIdx.x, blockDim.x);
+    uint32_t* src = reinterpret_cast<uint32_t*>(&T); uint32_t* dst = reinterpret_cast<uint32_t*>(out);
+    for (int i = threadIdx.x; i < (int)(sizeof(RasterTables) / 4); i += blockDim.x) dst[i] = src[i];
+}
+
 // What a render warp needs to draw one frame; the scaled coordinates are computed once per env by the physics lane
 // (pos * 84 / 600, app_game_drawer.rs:21-36) instead of redundantly by all 32 lanes of a render warp.
 struct __align__(16) RenderRec {
@@ -184,18 +195,30 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
         uint4* z = reinterpret_cast<uint4*>(dyn_smem + (size_t)(warp - 1) * NE * FRAME_BYTES);
         for (int i = lane; i < NE * FRAME_VEC16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
     }
-    build_raster_tables(S.tables, tid, blockDim.x);   // contains __syncthreads()
+    {   // raster tables: ~1 KB copy from the per-handle global copy
+        static_assert(sizeof(RasterTables) % 4 == 0, "word copy");
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.tables); uint32_t* dst = reinterpret_cast<uint32_t*>(&S.tables);
+        for (int i = tid; i < (int)(sizeof(RasterTables) / 4); i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
 
     if (warp == 0) {
         // ------------------------------- physics warp -------------------------------
         uint32_t seq = 0;                                  // (batch, step) items published so far
+        bool first_done = false;
         for (;;) {
         // env batches are handed out dynamically (SMs differ in their distance to L2/HBM; a static split would wait for the slowest)
         const uint32_t n_chunks = p.chunk_len ? (p.n_steps + p.chunk_len - 1) / p.chunk_len : 1u;
-        uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(p.work_counter, 1u) - p.work_base;
-        item = __shfl_sync(0xFFFFFFFFu, item, 0);
-        if (item >= n_batches * n_chunks) {
+        const uint32_t n_items = n_batches * n_chunks;
+        uint32_t item;
+        if (seq == 0 && !first_done) { item = blockIdx.x; first_done = true; }       // first item is static: no atomic on the critical path
+        else if (n_items <= gridDim.x) item = n_items;                               // one item per CTA: nothing left to hand out
+        else {
+            item = 0;
+            if (lane == 0) item = gridDim.x + (atomicAdd(p.work_counter, 1u) - p.work_base);
+            item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        }
+        if (item >= n_items) {
             const int q = seq % D;
             if (seq >= (uint32_t)D) mbar_wait(&S.empty[q], ((seq / D) - 1) & 1);
             if (lane == 0) { S.item_n[q] = 0u; mbar_arrive(&S.full[q]); }

@@ -29,6 +29,7 @@ struct qlc_env {
     uint32_t* records = nullptr;
     DeviceStats* stats = nullptr;
     unsigned long long* scratch = nullptr;     // 8 x u64 device scratch (histogram, err OR)
+    RasterTables* tables = nullptr;            // raster tables, built once on the device
     unsigned int* work_counter = nullptr;      // dynamic work hand-out of the step kernel
     uint32_t work_base = 0;
     unsigned long long* progress = nullptr;    // per env batch: launch serial << 32 | steps done (time-chunk hand-over flag)
@@ -156,6 +157,7 @@ int32_t qlc_env_create(const qlc_config* cfg, qlc_env** out) {
     TRY_ALLOC(dev_alloc(env, &env->stats, 1, false));
     TRY_ALLOC(dev_alloc(env, &env->scratch, 8, true));
     TRY_ALLOC(dev_alloc(env, &env->work_counter, 1, true));
+    TRY_ALLOC(dev_alloc(env, &env->tables, 1, false));
     TRY_ALLOC(dev_alloc(env, &env->progress, n, true));
     TRY_ALLOC(dev_alloc(env, &env->spin_error, 1, true));
 #undef TRY_ALLOC
@@ -164,6 +166,7 @@ int32_t qlc_env_create(const qlc_config* cfg, qlc_env** out) {
     DeviceStats init{0ull, 0ull, 0xFFFFFFFFu, 0u};
     ce = cudaMemcpy(env->stats, &init, sizeof init, cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { qlc_env_destroy(env); return fail(QLC_ERR_CUDA, std::string("stats init: ") + cudaGetErrorString(ce)); }
+    raster_tables_kernel<<<1, 128>>>(env->tables);
     rc = launch_reset(env, nullptr, nullptr, 1, nullptr);
     if (rc) { qlc_env_destroy(env); return rc; }
     ce = cudaDeviceSynchronize();
@@ -241,7 +244,7 @@ static int32_t launch_advance(qlc_env* env, StepParams& p, cudaStream_t s, uint3
         grid = n_batches * n_chunks;
         if (grid > resident) grid = resident;
     }
-    p.work_counter = env->work_counter; p.work_base = env->work_base;
+    p.tables = env->tables; p.work_counter = env->work_counter; p.work_base = env->work_base;
     p.chunk_len = chunk; p.launch_serial = ++env->launch_serial; p.progress = env->progress; p.spin_error = env->spin_error;
     if (chunk) {
         // CTAs wait on one another (chunk c of a batch on chunk c-1): a cooperative launch guarantees co-residency
@@ -251,7 +254,7 @@ static int32_t launch_advance(qlc_env* env, StepParams& p, cudaStream_t s, uint3
         kern<<<grid, 32 * (R + 1), dyn, s>>>(env->st, p);
     }
     CUDA_TRY(cudaGetLastError());
-    env->work_base += n_batches * n_chunks + grid;      // every CTA ends with one failed grab
+    if (n_batches * n_chunks > grid) env->work_base += n_batches * n_chunks;      // (n_items - grid) hand-outs + one failed grab per CTA
     return QLC_OK;
 }
 

@@ -68,5 +68,5 @@ def time_gather(n_envs, batch, n_batches, layout, reps=20):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
-    for n, k in ((4096, 64), (4096, 16), (4096, 8), (4096, 1), (1024, 64), (8192, 64), (16384, 64), (65536, 16), (65536, 1)):
+    for n, k in ((4096, 64), (4096, 1), (4096, 2), (1024, 1), (65536, 1), (65536, 16), (8192, 64)):
         time_advance(n, k, max(5, 640 // k), 0, cap_steps=64)
