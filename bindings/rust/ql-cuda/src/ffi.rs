@@ -73,6 +73,26 @@ pub struct qlc_state_view {
 }
 
 #[repr(C)]
+pub struct qlc_qnet {
+    _private: [u8; 0],
+}
+
+/// host f32 arrays in the Keras layouts
+#[repr(C)]
+pub struct qlc_qnet_weights {
+    pub conv1_kernel: *const f32,
+    pub conv1_bias: *const f32,
+    pub conv2_kernel: *const f32,
+    pub conv2_bias: *const f32,
+    pub conv3_kernel: *const f32,
+    pub conv3_bias: *const f32,
+    pub dense1_kernel: *const f32,
+    pub dense1_bias: *const f32,
+    pub dense2_kernel: *const f32,
+    pub dense2_bias: *const f32,
+}
+
+#[repr(C)]
 #[derive(Clone, Copy, Default)]
 pub struct qlc_episode_stats {
     pub sum_return: u64,
@@ -123,4 +143,10 @@ extern "C" {
     pub fn qlc_debug_collision_rect(cx: f32, cy: f32, radius: f32, mvx: f32, mvy: f32, min_x: f32, min_y: f32, max_x: f32, max_y: f32,
                                     some: *mut i32, way: *mut f32, approximation: *mut f32, nx: *mut f32, ny: *mut f32, err: *mut u32) -> i32;
     pub fn qlc_debug_collision_rect_batch(in_host: *const f32, out_host: *mut f32, n: u32) -> i32;
+    pub fn qlc_qnet_create(env: *mut qlc_env, weights_host: *const qlc_qnet_weights, out: *mut *mut qlc_qnet) -> i32;
+    pub fn qlc_qnet_set_weights(qnet: *mut qlc_qnet, weights_host: *const qlc_qnet_weights) -> i32;
+    pub fn qlc_qnet_destroy(qnet: *mut qlc_qnet) -> i32;
+    pub fn qlc_qnet_forward(qnet: *mut qlc_qnet, idx_dev: *const u32, n: u32, which: i32, q_dev: *mut f32, action_dev: *mut u8, max_q_dev: *mut f32, stream: *mut c_void) -> i32;
+    pub fn qlc_qnet_forward_host(qnet: *mut qlc_qnet, idx_host: *const u32, n: u32, which: i32, q_host: *mut f32, action_host: *mut u8, max_q_host: *mut f32) -> i32;
+    pub fn qlc_debug_gemm_bf16(a_host: *const f32, w_host: *const f32, bias_host: *const f32, relu: i32, out_host: *mut f32, m: u32, n: u32, k: u32) -> i32;
 }

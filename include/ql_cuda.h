@@ -168,6 +168,27 @@ int32_t qlc_stats_mean(qlc_env* env, float* out);                     /* avg_epi
 int32_t qlc_stats_min(qlc_env* env, float* out);                      /* min_episode_reward */
 int32_t qlc_stats_window(qlc_env* env, float* out, uint32_t cap, uint32_t* n);  /* episode_rewards() */
 
+/* ---- Q-network forward on the tensor cores (tcgen05, bf16 operands, f32 accumulation) — SURVEY.md 8f-3. Architecture of
+ * python_model/create_ql_model_breakout_84x84x4_3_32.py:17-33; the first convolution reads the u8 frames straight from
+ * the frame ring. Replaces QLearningTensorflowModel::predict_action / batch_predict_max_future_reward
+ * (ql-with-tensorflow/src/ml_model/tensorflow_python/q_learning_model.rs:107-152) for inference. ---- */
+typedef struct qlc_qnet qlc_qnet;
+typedef struct qlc_qnet_weights {          /* host f32 arrays in the Keras layouts */
+    const float* conv1_kernel; const float* conv1_bias;    /* [8][8][4][32], [32]  (axes: x offset, y offset, ring slot, out) */
+    const float* conv2_kernel; const float* conv2_bias;    /* [4][4][32][64], [64] */
+    const float* conv3_kernel; const float* conv3_bias;    /* [3][3][64][64], [64] */
+    const float* dense1_kernel; const float* dense1_bias;  /* [3136][512], [512]   (input order of Flatten([7][7][64])) */
+    const float* dense2_kernel; const float* dense2_bias;  /* [512][3], [3] */
+} qlc_qnet_weights;
+int32_t qlc_qnet_create(qlc_env* env, const qlc_qnet_weights* weights_host, qlc_qnet** out);
+int32_t qlc_qnet_set_weights(qlc_qnet* qnet, const qlc_qnet_weights* weights_host);
+int32_t qlc_qnet_destroy(qlc_qnet* qnet);
+/* idx_dev NULL: the current observation of all n_envs envs (predict_action for every env); else n replay transitions by
+ * logical index, which = 0 their state / 1 their state_next. Outputs (device, any may be NULL): q [n][3] f32, action [n] u8
+ * (first maximum, tf.argmax), max_q [n] f32 (tf.reduce_max). Asynchronous on `stream`. */
+int32_t qlc_qnet_forward(qlc_qnet* qnet, const uint32_t* idx_dev, uint32_t n, int32_t which, float* q_dev, uint8_t* action_dev, float* max_q_dev, void* stream);
+int32_t qlc_qnet_forward_host(qlc_qnet* qnet, const uint32_t* idx_host, uint32_t n, int32_t which, float* q_host, uint8_t* action_host, float* max_q_host);
+
 /* ---- checkpoint / resume of the env shard + replay ring (the reference checkpoints only the model:
  * q_learning_model.rs:191-202). qlc_env_load needs an env created with the same n_envs / env_id_base / seed /
  * replay_capacity / episode limits; a resumed run continues bit-identically. Synchronous. ---- */
@@ -185,6 +206,11 @@ int32_t qlc_debug_collision_rect(float cx, float cy, float radius, float mvx, fl
 /* batched rectangle sweep: in_host [n][9] = cx, cy, radius, mvx, mvy, min_x, min_y, max_x, max_y;
  * out_host [n][6] = some (0/1), way, approximation, nx, ny, err (u32 bits in a float slot) */
 int32_t qlc_debug_collision_rect_batch(const float* in_host, float* out_host, uint32_t n);
+
+/* test hook of the tcgen05 GEMM the Q-network layers are built from: out[m][n] = act(bf16(a)[m][k] * bf16(w)[n][k]^T + bias),
+ * host f32 buffers in and out; k % 64 == 0, n in {32, 64, 128, 256, 512} */
+int32_t qlc_debug_gemm_bf16(const float* a_host, const float* w_host, const float* bias_host, int32_t relu, float* out_host,
+                            uint32_t m, uint32_t n, uint32_t k);
 
 #ifdef __cplusplus
 }

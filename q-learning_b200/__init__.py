@@ -46,7 +46,8 @@ ABI_SYMBOLS = [
     "qlc_replay_gather_host", "qlc_replay_action_counts",
     "qlc_env_save", "qlc_env_load",
     "qlc_stats_read", "qlc_stats_export", "qlc_stats_push", "qlc_stats_mean", "qlc_stats_min", "qlc_stats_window",
-    "qlc_debug_collision_wall", "qlc_debug_collision_rect", "qlc_debug_collision_rect_batch",
+    "qlc_debug_collision_wall", "qlc_debug_collision_rect", "qlc_debug_collision_rect_batch", "qlc_debug_gemm_bf16",
+    "qlc_qnet_create", "qlc_qnet_set_weights", "qlc_qnet_destroy", "qlc_qnet_forward", "qlc_qnet_forward_host",
 ]
 
 
@@ -77,6 +78,16 @@ class QlcStateView(C.Structure):
         "ball_cx", "ball_cy", "ball_dx", "ball_dy", "pad_min_x", "pad_max_x", "pad_speed",
         "bricks", "score", "episode_step", "episode", "err", "finished", "frames", "records")] + [
         ("n_envs", C.c_uint32), ("time_slots", C.c_uint32), ("time", C.c_uint64)]
+
+
+class QlcQnetWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("conv1_kernel", "conv1_bias", "conv2_kernel", "conv2_bias", "conv3_kernel", "conv3_bias",
+                                           "dense1_kernel", "dense1_bias", "dense2_kernel", "dense2_bias")]
+
+
+QNET_SHAPES = {"conv1_kernel": (8, 8, 4, 32), "conv1_bias": (32,), "conv2_kernel": (4, 4, 32, 64), "conv2_bias": (64,),
+               "conv3_kernel": (3, 3, 64, 64), "conv3_bias": (64,), "dense1_kernel": (3136, 512), "dense1_bias": (512,),
+               "dense2_kernel": (512, 3), "dense2_bias": (3,)}
 
 
 class QlcEpisodeStats(C.Structure):
@@ -139,6 +150,12 @@ def load_library(build_if_missing=True):
         "qlc_debug_collision_wall": (i32, [i32] + [C.c_float] * 5 + [vp] * 6),
         "qlc_debug_collision_rect": (i32, [C.c_float] * 9 + [vp] * 6),
         "qlc_debug_collision_rect_batch": (i32, [vp, vp, u32]),
+        "qlc_debug_gemm_bf16": (i32, [vp, vp, vp, i32, vp, u32, u32, u32]),
+        "qlc_qnet_create": (i32, [vp, C.POINTER(QlcQnetWeights), C.POINTER(vp)]),
+        "qlc_qnet_set_weights": (i32, [vp, C.POINTER(QlcQnetWeights)]),
+        "qlc_qnet_destroy": (i32, [vp]),
+        "qlc_qnet_forward": (i32, [vp, vp, u32, i32, vp, vp, vp, vp]),
+        "qlc_qnet_forward_host": (i32, [vp, vp, u32, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)   # AttributeError if the library lacks a declared symbol
@@ -502,3 +519,72 @@ def debug_collision_rect_batch(cases):
     out = np.empty((a.shape[0], 6), dtype=np.float32)
     _check(load_library().qlc_debug_collision_rect_batch(_np_ptr(a), _np_ptr(out), a.shape[0]))
     return (out[:, 0] != 0).astype(np.uint8), out[:, 1:5].copy(), out[:, 5].copy().view(np.uint32)
+
+
+def debug_gemm_bf16(a, w, bias, relu=False):
+    """out[m][n] = act(bf16(a)[m][k] @ bf16(w)[n][k].T + bias) on the tcgen05 tensor-core kernel (f32 host arrays)."""
+    a = np.ascontiguousarray(a, dtype=np.float32); w = np.ascontiguousarray(w, dtype=np.float32); bias = np.ascontiguousarray(bias, dtype=np.float32)
+    m, k = a.shape
+    n = w.shape[0]
+    out = np.empty((m, n), dtype=np.float32)
+    _check(load_library().qlc_debug_gemm_bf16(_np_ptr(a), _np_ptr(w), _np_ptr(bias), 1 if relu else 0, _np_ptr(out), m, n, k))
+    return out
+
+
+class QNetwork:
+    """Q-network forward on the tensor cores (tcgen05) for a BreakoutEnvironment: the inference half of the reference's
+    DeepQLearningModel (ml_model/model.rs:29-77) — predict_action for every env, batch_predict_max_future_reward for replay
+    samples — reading the u8 frames straight from the frame ring. `weights`: dict of f32 arrays in the Keras layouts
+    (QNET_SHAPES); bf16 operands, f32 accumulation."""
+
+    def __init__(self, env, weights):
+        self._env = env
+        self._L = env._L
+        h = C.c_void_p()
+        w, self._keep = self._pack(weights)
+        _check(self._L.qlc_qnet_create(env._h, C.byref(w), C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def _pack(weights):
+        keep = []
+        vals = []
+        for name, _ in QlcQnetWeights._fields_:
+            a = np.ascontiguousarray(weights[name], dtype=np.float32)
+            if a.shape != QNET_SHAPES[name]:
+                raise QlError("%s must have shape %s" % (name, QNET_SHAPES[name]))
+            keep.append(a)
+            vals.append(a.ctypes.data)
+        return QlcQnetWeights(*vals), keep
+
+    def set_weights(self, weights):
+        w, keep = self._pack(weights)
+        _check(self._L.qlc_qnet_set_weights(self._h, C.byref(w)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.qlc_qnet_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def forward(self, indices=None, which=0):
+        """indices None: current observation of every env; else replay transitions (which = 0 state / 1 state_next).
+        Returns (q f32 [n][3], action u8 [n], max_q f32 [n]) on the host."""
+        if indices is None:
+            n, idx = self._env.n_envs, None
+        else:
+            idx = np.ascontiguousarray(indices, dtype=np.uint32)
+            n = idx.size
+        q = np.empty((n, 3), dtype=np.float32)
+        a = np.empty(n, dtype=np.uint8)
+        m = np.empty(n, dtype=np.float32)
+        _check(self._L.qlc_qnet_forward_host(self._h, None if idx is None else _np_ptr(idx), n, which, _np_ptr(q), _np_ptr(a), _np_ptr(m)))
+        return q, a, m
+
+    def forward_device(self, idx_ptr, n, which, q_ptr=None, action_ptr=None, max_q_ptr=None, stream=None):
+        _check(self._L.qlc_qnet_forward(self._h, idx_ptr, n, which, q_ptr, action_ptr, max_q_ptr, stream))

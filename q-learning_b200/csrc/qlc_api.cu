@@ -2,6 +2,7 @@
 // computes needs a CUDA device and fails with QLC_ERR_NO_DEVICE / QLC_ERR_CUDA otherwise.
 #include "../../include/ql_cuda.h"
 #include "kernels.cuh"
+#include "qnet.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -700,6 +701,183 @@ int32_t qlc_debug_collision_rect_batch(const float* in_host, float* out_host, ui
     if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("debug batch: ") + cudaGetErrorString(e));
     return QLC_OK;
 }
+}  // extern "C"
+
+template <int N, class Loader>
+static cudaError_t launch_gemm_tc(const Loader& ld, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, uint32_t m, uint32_t k, int relu,
+                                  unsigned int* err, cudaStream_t s) {
+    const size_t dyn = (size_t)qnet::TILE_M * qnet::KC * 2 + (size_t)N * qnet::KC * 2;
+    auto kern = qnet::gemm_tc_kernel<N, Loader>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    kern<<<(m + qnet::TILE_M - 1) / qnet::TILE_M, 128, dyn, s>>>(ld, w, bias, out, m, k, relu, err);
+    return cudaGetLastError();
+}
+
+extern "C" {
+
+// ---------------- Q-network forward on the tensor cores ----------------
+struct qlc_qnet {
+    qlc_env* env = nullptr;
+    __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr; float* w5 = nullptr;
+    float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *b4 = nullptr, *b5 = nullptr;
+    __nv_bfloat16 *a1 = nullptr, *a2 = nullptr, *a3 = nullptr, *a4 = nullptr; uint32_t* slot_frame = nullptr; unsigned int* err = nullptr;
+    float* stage = nullptr; size_t stage_bytes = 0;
+    uint32_t cap_items = 0;
+};
+
+static void qnet_free_acts(qlc_qnet* q) {
+    cudaFree(q->a1); cudaFree(q->a2); cudaFree(q->a3); cudaFree(q->a4); cudaFree(q->slot_frame);
+    q->a1 = q->a2 = q->a3 = q->a4 = nullptr; q->slot_frame = nullptr; q->cap_items = 0;
+}
+
+int32_t qlc_qnet_destroy(qlc_qnet* q) {
+    if (!q) return QLC_OK;
+    cudaSetDevice(q->env->cfg.device);
+    cudaDeviceSynchronize();
+    qnet_free_acts(q);
+    cudaFree(q->w1); cudaFree(q->w2); cudaFree(q->w3); cudaFree(q->w4); cudaFree(q->w5);
+    cudaFree(q->b1); cudaFree(q->b2); cudaFree(q->b3); cudaFree(q->b4); cudaFree(q->b5); cudaFree(q->err); cudaFree(q->stage);
+    delete q;
+    return QLC_OK;
+}
+
+int32_t qlc_qnet_set_weights(qlc_qnet* q, const qlc_qnet_weights* w) {
+    if (!q || !w) return fail(QLC_ERR_INVALID_ARG, "qnet/weights is null");
+    const float* srcs[10] = {w->conv1_kernel, w->conv1_bias, w->conv2_kernel, w->conv2_bias, w->conv3_kernel, w->conv3_bias, w->dense1_kernel, w->dense1_bias, w->dense2_kernel, w->dense2_bias};
+    const size_t counts[10] = {8 * 8 * 4 * 32, 32, 4 * 4 * 32 * 64, 64, 3 * 3 * 64 * 64, 64, 3136 * 512, 512, 512 * 3, 3};
+    for (int i = 0; i < 10; ++i) if (!srcs[i]) return fail(QLC_ERR_INVALID_ARG, "a weight pointer is null");
+    int32_t rc = set_device(q->env); if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    const size_t need = (size_t)3136 * 512 * 4;
+    if (q->stage_bytes < need) { cudaFree(q->stage); q->stage = nullptr; CUDA_TRY(cudaMalloc(&q->stage, need)); q->stage_bytes = need; }
+    float* biases[5] = {q->b1, q->b2, q->b3, q->b4, q->b5};
+    for (int l = 0; l < 5; ++l) {
+        CUDA_TRY(cudaMemcpy(q->stage, srcs[2 * l], counts[2 * l] * 4, cudaMemcpyHostToDevice));
+        switch (l) {
+            case 0: qnet::prep_conv1_kernel<<<(32 * 256 + 255) / 256, 256>>>(q->stage, q->w1); break;
+            case 1: qnet::prep_transpose_kernel<<<(512 * 64 + 255) / 256, 256>>>(q->stage, q->w2, 512, 64); break;       // [kh][kw][c][cout] = [K][N]
+            case 2: qnet::prep_transpose_kernel<<<(576 * 64 + 255) / 256, 256>>>(q->stage, q->w3, 576, 64); break;
+            case 3: qnet::prep_transpose_kernel<<<(3136 * 512 + 255) / 256, 256>>>(q->stage, q->w4, 3136, 512); break;
+            default: qnet::prep_head_kernel<<<(3 * 512 + 255) / 256, 256>>>(q->stage, q->w5); break;
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpy(biases[l], srcs[2 * l + 1], counts[2 * l + 1] * 4, cudaMemcpyHostToDevice));
+    }
+    return QLC_OK;
+}
+
+int32_t qlc_qnet_create(qlc_env* env, const qlc_qnet_weights* w, qlc_qnet** out) {
+    if (!env || !w || !out) return fail(QLC_ERR_INVALID_ARG, "env/weights/out is null");
+    *out = nullptr;
+    int32_t rc = set_device(env); if (rc) return rc;
+    qlc_qnet* q = new qlc_qnet();
+    q->env = env;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void**)&q->w1, 32 * 256 * 2); A((void**)&q->w2, 64 * 512 * 2); A((void**)&q->w3, 64 * 576 * 2); A((void**)&q->w4, (size_t)512 * 3136 * 2); A((void**)&q->w5, 3 * 512 * 4);
+    A((void**)&q->b1, 32 * 4); A((void**)&q->b2, 64 * 4); A((void**)&q->b3, 64 * 4); A((void**)&q->b4, 512 * 4); A((void**)&q->b5, 3 * 4); A((void**)&q->err, 4);
+    if (e == cudaSuccess) e = cudaMemset(q->err, 0, 4);
+    if (e != cudaSuccess) { qlc_qnet_destroy(q); return fail(QLC_ERR_CUDA, std::string("qnet alloc: ") + cudaGetErrorString(e)); }
+    rc = qlc_qnet_set_weights(q, w);
+    if (rc) { qlc_qnet_destroy(q); return rc; }
+    *out = q;
+    return QLC_OK;
+}
+
+int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32_t which, float* q_dev, uint8_t* action_dev, float* max_q_dev, void* stream) {
+    if (!q) return fail(QLC_ERR_INVALID_ARG, "qnet is null");
+    qlc_env* env = q->env;
+    int32_t rc = set_device(env); if (rc) return rc;
+    if (!idx_dev) { n = env->cfg.n_envs; which = 0; }
+    if (n == 0) return QLC_OK;
+    if ((uint64_t)n * 400ull >= 0xFFFFFFFFull) return fail(QLC_ERR_INVALID_ARG, "too many items for one forward pass");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n > q->cap_items) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        qnet_free_acts(q);
+        CUDA_TRY(cudaMalloc(&q->a1, (size_t)n * 400 * 32 * 2)); CUDA_TRY(cudaMalloc(&q->a2, (size_t)n * 81 * 64 * 2));
+        CUDA_TRY(cudaMalloc(&q->a3, (size_t)n * 49 * 64 * 2)); CUDA_TRY(cudaMalloc(&q->a4, (size_t)n * 512 * 2)); CUDA_TRY(cudaMalloc(&q->slot_frame, (size_t)n * 16));
+        q->cap_items = n;
+    }
+    GatherParams g{}; fill_gather(env, g);
+    g.indices = idx_dev; g.n_items = n;
+    qnet::qnet_locate_kernel<<<(n + 127) / 128, 128, 0, s>>>(g, which ? 1u : 0u, q->slot_frame);
+    CUDA_TRY(cudaGetLastError());
+    cudaError_t e;
+    qnet::LoadConv1FromRing l1{env->frames, q->slot_frame};
+    e = launch_gemm_tc<32>(l1, q->w1, q->b1, q->a1, n * 400u, 256u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv1: ") + cudaGetErrorString(e));
+    qnet::LoadConvNHWC l2{q->a1, 20, 20, 32, 9, 9, 4, 4, 2};
+    e = launch_gemm_tc<64>(l2, q->w2, q->b2, q->a2, n * 81u, 512u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv2: ") + cudaGetErrorString(e));
+    qnet::LoadConvNHWC l3{q->a2, 9, 9, 64, 7, 7, 3, 3, 1};
+    e = launch_gemm_tc<64>(l3, q->w3, q->b3, q->a3, n * 49u, 576u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv3: ") + cudaGetErrorString(e));
+    qnet::LoadRowMajorBf16 l4{q->a3, 3136u};
+    e = launch_gemm_tc<512>(l4, q->w4, q->b4, q->a4, n, 3136u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("dense1: ") + cudaGetErrorString(e));
+    qnet::head_kernel<<<(n + 7) / 8, 256, 0, s>>>(q->a4, q->w5, q->b5, q_dev, action_dev, max_q_dev, n);
+    CUDA_TRY(cudaGetLastError());
+    return QLC_OK;
+}
+
+int32_t qlc_qnet_forward_host(qlc_qnet* q, const uint32_t* idx_host, uint32_t n, int32_t which, float* q_host, uint8_t* action_host, float* max_q_host) {
+    if (!q) return fail(QLC_ERR_INVALID_ARG, "qnet is null");
+    qlc_env* env = q->env;
+    int32_t rc = set_device(env); if (rc) return rc;
+    if (!idx_host) n = env->cfg.n_envs;
+    if (n == 0) return QLC_OK;
+    if (idx_host) { const uint64_t len = replay_len(env); for (uint32_t i = 0; i < n; ++i) if (idx_host[i] >= len) return fail(QLC_ERR_OUT_OF_RANGE, "replay index out of range"); }
+    const size_t o_idx = 0, o_q = ((size_t)n * 4 + 255) & ~(size_t)255, o_m = o_q + (size_t)n * 12, o_a = o_m + (size_t)n * 4, total = o_a + n;
+    rc = ensure_dev_stage(env, total); if (rc) return rc;
+    uint8_t* dev = (uint8_t*)env->dev_stage;
+    cudaStream_t s = env->own_stream;
+    if (idx_host) CUDA_TRY(cudaMemcpyAsync(dev + o_idx, idx_host, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    rc = qlc_qnet_forward(q, idx_host ? (const uint32_t*)(dev + o_idx) : nullptr, n, which, (float*)(dev + o_q), dev + o_a, (float*)(dev + o_m), s); if (rc) return rc;
+    if (q_host) CUDA_TRY(cudaMemcpyAsync(q_host, dev + o_q, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
+    if (max_q_host) CUDA_TRY(cudaMemcpyAsync(max_q_host, dev + o_m, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (action_host) CUDA_TRY(cudaMemcpyAsync(action_host, dev + o_a, n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    unsigned int herr = 0;
+    CUDA_TRY(cudaMemcpy(&herr, q->err, 4, cudaMemcpyDeviceToHost));
+    if (herr) return fail(QLC_ERR_CUDA, "qnet: an MMA completion barrier timed out");
+    return QLC_OK;
+}
+
+// test hook: out[M][N] = act(bf16(a)[M][K] * bf16(w)[N][K]^T + bias) through the tcgen05 GEMM kernel (host f32 in / out)
+int32_t qlc_debug_gemm_bf16(const float* a_host, const float* w_host, const float* bias_host, int32_t relu, float* out_host, uint32_t m, uint32_t n, uint32_t k) {
+    if (!a_host || !w_host || !bias_host || !out_host) return fail(QLC_ERR_INVALID_ARG, "null pointer");
+    if (k % qnet::KC != 0 || !(n == 32 || n == 64 || n == 128 || n == 256 || n == 512) || m == 0) return fail(QLC_ERR_INVALID_ARG, "need K % 64 == 0 and N in {32, 64, 128, 256, 512}");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(QLC_ERR_NO_DEVICE, "no CUDA device: ql_cuda has no CPU fallback");
+    float *da = nullptr, *dw = nullptr, *db = nullptr, *dof = nullptr; __nv_bfloat16 *ba = nullptr, *bw = nullptr, *bo = nullptr; unsigned int* derr = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void**)&da, (size_t)m * k * 4); A((void**)&dw, (size_t)n * k * 4); A((void**)&db, (size_t)n * 4); A((void**)&dof, (size_t)m * n * 4);
+    A((void**)&ba, (size_t)m * k * 2); A((void**)&bw, (size_t)n * k * 2); A((void**)&bo, (size_t)m * n * 2); A((void**)&derr, 4);
+    if (e == cudaSuccess) e = cudaMemset(derr, 0, 4);
+    if (e == cudaSuccess) e = cudaMemcpy(da, a_host, (size_t)m * k * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dw, w_host, (size_t)n * k * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, bias_host, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        qnet::f32_to_bf16_kernel<<<256, 256>>>(da, ba, (size_t)m * k);
+        qnet::f32_to_bf16_kernel<<<256, 256>>>(dw, bw, (size_t)n * k);
+        qnet::LoadRowMajorBf16 ld{ba, k};
+        switch (n) {
+            case 32: e = launch_gemm_tc<32>(ld, bw, db, bo, m, k, relu, derr, nullptr); break;
+            case 64: e = launch_gemm_tc<64>(ld, bw, db, bo, m, k, relu, derr, nullptr); break;
+            case 128: e = launch_gemm_tc<128>(ld, bw, db, bo, m, k, relu, derr, nullptr); break;
+            case 256: e = launch_gemm_tc<256>(ld, bw, db, bo, m, k, relu, derr, nullptr); break;
+            default: e = launch_gemm_tc<512>(ld, bw, db, bo, m, k, relu, derr, nullptr); break;
+        }
+    }
+    unsigned int herr = 0;
+    if (e == cudaSuccess) { qnet::bf16_to_f32_kernel<<<256, 256>>>(bo, dof, (size_t)m * n); e = cudaMemcpy(out_host, dof, (size_t)m * n * 4, cudaMemcpyDeviceToHost); }
+    if (e == cudaSuccess) e = cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(dw); cudaFree(db); cudaFree(dof); cudaFree(ba); cudaFree(bw); cudaFree(bo); cudaFree(derr);
+    if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("tensor-core GEMM: ") + cudaGetErrorString(e));
+    if (herr) return fail(QLC_ERR_CUDA, "tensor-core GEMM: the MMA completion barrier timed out");
+    return QLC_OK;
+}
+
 int32_t qlc_debug_collision_wall(int32_t which, float cx, float cy, float radius, float mvx, float mvy, int32_t* some, float* way,
                                  float* approximation, float* nx, float* ny, uint32_t* err) {
     if (which < 0 || which > 2) return fail(QLC_ERR_INVALID_ARG, "which must be 0..2");
