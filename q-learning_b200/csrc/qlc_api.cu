@@ -703,14 +703,29 @@ int32_t qlc_debug_collision_rect_batch(const float* in_host, float* out_host, ui
 }
 }  // extern "C"
 
-template <int N, class Loader>
-static cudaError_t launch_gemm_tc(const Loader& ld, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, uint32_t m, uint32_t k, int relu,
-                                  unsigned int* err, cudaStream_t s) {
-    const size_t dyn = (size_t)qnet::TILE_M * qnet::KC * 2 + (size_t)N * qnet::KC * 2;
-    auto kern = qnet::gemm_tc_kernel<N, Loader>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    if (e != cudaSuccess) return e;
-    kern<<<(m + qnet::TILE_M - 1) / qnet::TILE_M, 128, dyn, s>>>(ld, w, bias, out, m, k, relu, err);
+template <int NT, class Loader>
+static cudaError_t launch_gemm_tc(const Loader& ld, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, uint32_t m, uint32_t k, uint32_t n_total,
+                                  int relu, unsigned int* err, cudaStream_t s) {
+    const size_t dyn = 2 * ((size_t)qnet::TILE_M * qnet::KC * 2 + (size_t)NT * qnet::KC * 2);
+    auto kern = qnet::gemm_tc_kernel<NT, Loader>;
+    static int occ = 0, sms = 0;
+    cudaError_t e = cudaSuccess;
+    if (occ == 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, dyn);
+        if (e != cudaSuccess) return e;
+        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int tmem_limit = 512 / (NT <= 32 ? 32 : (NT <= 64 ? 64 : (NT <= 128 ? 128 : 256)));   // TMEM columns per SM
+        if (getenv("QLC_DEBUG_OCC")) fprintf(stderr, "gemm_tc NT=%d dyn=%zu occ(api)=%d tmem_limit=%d sms=%d\n", NT, dyn, occ, tmem_limit, sms);
+        if (occ > tmem_limit) occ = tmem_limit;
+        if (occ < 1) occ = 1;
+    }
+    const uint32_t n_mtiles = (m + qnet::TILE_M - 1) / qnet::TILE_M, n_ntiles = n_total / NT;
+    uint32_t gx = (uint32_t)(occ * sms) / n_ntiles;
+    if (gx < 1) gx = 1;
+    if (gx > n_mtiles) gx = n_mtiles;
+    kern<<<dim3(gx, n_ntiles), 128, dyn, s>>>(ld, w, bias, out, m, k, n_total, relu, err);
     return cudaGetLastError();
 }
 
@@ -807,13 +822,13 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
     CUDA_TRY(cudaGetLastError());
     cudaError_t e;
     qnet::LoadConv1FromRing l1{env->frames, q->slot_frame};
-    e = launch_gemm_tc<32>(l1, q->w1, q->b1, q->a1, n * 400u, 256u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv1: ") + cudaGetErrorString(e));
+    e = launch_gemm_tc<32>(l1, q->w1, q->b1, q->a1, n * 400u, 256u, 32u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv1: ") + cudaGetErrorString(e));
     qnet::LoadConvNHWC l2{q->a1, 20, 20, 32, 9, 9, 4, 4, 2};
-    e = launch_gemm_tc<64>(l2, q->w2, q->b2, q->a2, n * 81u, 512u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv2: ") + cudaGetErrorString(e));
+    e = launch_gemm_tc<64>(l2, q->w2, q->b2, q->a2, n * 81u, 512u, 64u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv2: ") + cudaGetErrorString(e));
     qnet::LoadConvNHWC l3{q->a2, 9, 9, 64, 7, 7, 3, 3, 1};
-    e = launch_gemm_tc<64>(l3, q->w3, q->b3, q->a3, n * 49u, 576u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv3: ") + cudaGetErrorString(e));
+    e = launch_gemm_tc<64>(l3, q->w3, q->b3, q->a3, n * 49u, 576u, 64u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv3: ") + cudaGetErrorString(e));
     qnet::LoadRowMajorBf16 l4{q->a3, 3136u};
-    e = launch_gemm_tc<512>(l4, q->w4, q->b4, q->a4, n, 3136u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("dense1: ") + cudaGetErrorString(e));
+    e = launch_gemm_tc<128>(l4, q->w4, q->b4, q->a4, n, 3136u, 512u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("dense1: ") + cudaGetErrorString(e));
     qnet::head_kernel<<<(n + 7) / 8, 256, 0, s>>>(q->a4, q->w5, q->b5, q_dev, action_dev, max_q_dev, n);
     CUDA_TRY(cudaGetLastError());
     return QLC_OK;
@@ -862,11 +877,11 @@ int32_t qlc_debug_gemm_bf16(const float* a_host, const float* w_host, const floa
         qnet::f32_to_bf16_kernel<<<256, 256>>>(dw, bw, (size_t)n * k);
         qnet::LoadRowMajorBf16 ld{ba, k};
         switch (n) {
-            case 32: e = launch_gemm_tc<32>(ld, bw, db, bo, m, k, relu, derr, nullptr); break;
-            case 64: e = launch_gemm_tc<64>(ld, bw, db, bo, m, k, relu, derr, nullptr); break;
-            case 128: e = launch_gemm_tc<128>(ld, bw, db, bo, m, k, relu, derr, nullptr); break;
-            case 256: e = launch_gemm_tc<256>(ld, bw, db, bo, m, k, relu, derr, nullptr); break;
-            default: e = launch_gemm_tc<512>(ld, bw, db, bo, m, k, relu, derr, nullptr); break;
+            case 32: e = launch_gemm_tc<32>(ld, bw, db, bo, m, k, n, relu, derr, nullptr); break;
+            case 64: e = launch_gemm_tc<64>(ld, bw, db, bo, m, k, n, relu, derr, nullptr); break;
+            case 128: e = launch_gemm_tc<128>(ld, bw, db, bo, m, k, n, relu, derr, nullptr); break;
+            case 256: e = launch_gemm_tc<256>(ld, bw, db, bo, m, k, n, relu, derr, nullptr); break;
+            default: e = launch_gemm_tc<128>(ld, bw, db, bo, m, k, n, relu, derr, nullptr); break;      // 512 = 4 N tiles of 128
         }
     }
     unsigned int herr = 0;

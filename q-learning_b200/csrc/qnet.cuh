@@ -78,40 +78,47 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// ---- A-operand loaders: 8 consecutive K elements (16 bytes of bf16) of one row ----
+// ---- A-operand loaders: prepare(row) hoists the per-row index math, load8() returns 8 consecutive K elements (16 B) ----
 struct LoadRowMajorBf16 {            // plain GEMM: A bf16 [M][K] row-major (Dense layers, and conv outputs flattened)
     const __nv_bfloat16* a; uint32_t k_total;
-    __device__ __forceinline__ uint4 load8(uint32_t row, uint32_t kchunk) const {
-        return __ldg(reinterpret_cast<const uint4*>(a + (size_t)row * k_total + (size_t)kchunk * 8));
-    }
+    struct Row { const __nv_bfloat16* p; };
+    __device__ __forceinline__ Row prepare(uint32_t row) const { return Row{a + (size_t)row * k_total}; }
+    __device__ __forceinline__ uint4 load8(const Row& r, uint32_t kchunk) const { return __ldg(reinterpret_cast<const uint4*>(r.p + (size_t)kchunk * 8)); }
 };
 struct LoadConvNHWC {                // conv over bf16 activations [B][H][W][C] (C % 8 == 0), K order (kh, kw, c)
     const __nv_bfloat16* act; int H, W, C, OH, OW, KH, KW, stride;
-    __device__ __forceinline__ uint4 load8(uint32_t row, uint32_t kchunk) const {
+    struct Row { const __nv_bfloat16* p; };
+    __device__ __forceinline__ Row prepare(uint32_t row) const {
         const int per = OH * OW;
         const int b = row / per, pos = row - b * per;
         const int oh = pos / OW, ow = pos - oh * OW;
+        return Row{act + (((size_t)b * H + oh * stride) * W + ow * stride) * C};
+    }
+    __device__ __forceinline__ uint4 load8(const Row& r, uint32_t kchunk) const {
         const int k = kchunk * 8;
-        const int c = k % C, kk = k / C;
+        const int kk = k / C, c = k - kk * C;
         const int kh = kk / KW, kw = kk - kh * KW;
-        const size_t off = (((size_t)b * H + (oh * stride + kh)) * W + (ow * stride + kw)) * C + c;
-        return __ldg(reinterpret_cast<const uint4*>(act + off));
+        return __ldg(reinterpret_cast<const uint4*>(r.p + ((size_t)kh * W + kw) * C + c));
     }
 };
 struct LoadConv1FromRing {           // conv1 straight from the u8 frame ring: K order (slot, kw, kh), kh fastest = 8 bytes of a frame row
     const uint8_t* frames; const uint32_t* slot_frame;   // slot_frame[item][4]: frame number in the ring of ring-slot h, ~0u = all zero
-    __device__ __forceinline__ uint4 load8(uint32_t row, uint32_t kchunk) const {
+    struct Row { uint32_t b, off; };
+    __device__ __forceinline__ Row prepare(uint32_t row) const {
         const uint32_t b = row / 400u, pos = row - b * 400u;
         const uint32_t ox = pos / 20u, oy = pos - ox * 20u;            // output pixel (x, y): reference tensor layout is [x][y][slot]
+        return Row{b, 4u * oy * FRAME_W + 4u * ox};
+    }
+    __device__ __forceinline__ uint4 load8(const Row& r, uint32_t kchunk) const {
         const uint32_t h = kchunk >> 3, kw = kchunk & 7u;              // ring slot, y offset
-        const uint32_t fi = __ldg(slot_frame + b * 4u + h);
+        const uint32_t fi = __ldg(slot_frame + r.b * 4u + h);
         if (fi == 0xFFFFFFFFu) return make_uint4(0u, 0u, 0u, 0u);      // slot not written yet in this episode
-        const uint8_t* f = frames + (size_t)fi * FRAME_BYTES + (4u * oy + kw) * FRAME_W + 4u * ox;
+        const uint8_t* f = frames + (size_t)fi * FRAME_BYTES + r.off + kw * FRAME_W;
         const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(f)), hi = __ldg(reinterpret_cast<const uint32_t*>(f + 4));
-        uint4 r;
-        r.x = pack_bf16((float)(lo & 0xFFu), (float)((lo >> 8) & 0xFFu));  r.y = pack_bf16((float)((lo >> 16) & 0xFFu), (float)(lo >> 24));
-        r.z = pack_bf16((float)(hi & 0xFFu), (float)((hi >> 8) & 0xFFu));  r.w = pack_bf16((float)((hi >> 16) & 0xFFu), (float)(hi >> 24));
-        return r;
+        uint4 o;
+        o.x = pack_bf16((float)(lo & 0xFFu), (float)((lo >> 8) & 0xFFu));  o.y = pack_bf16((float)((lo >> 16) & 0xFFu), (float)(lo >> 24));
+        o.z = pack_bf16((float)(hi & 0xFFu), (float)((hi >> 8) & 0xFFu));  o.w = pack_bf16((float)((hi >> 16) & 0xFFu), (float)(hi >> 24));
+        return o;
     }
 };
 
@@ -150,86 +157,119 @@ __global__ void prep_head_kernel(const float* __restrict__ kernel /*[512][3]*/, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// C[M x N] = act(A * W^T + bias): one CTA = 128 rows x N columns. N in {32, 64, 128, 256, 512}; K % 64 == 0.
-// W: bf16 [N][K] row-major (K-major). out: bf16 [M][N]. Rows >= m_total are computed on zeros and not stored.
+// C[M x N_TOTAL] = act(A * W^T + bias). Persistent CTAs (128 threads): blockIdx.y picks an N tile of NT columns, the CTA
+// walks the 128-row M tiles blockIdx.x, +gridDim.x, ... K is consumed in 64-element chunks through a 2-stage shared-memory
+// ring that runs on across tile boundaries: while the tensor core works on chunk g the threads already gather chunk g+1
+// (global loads in flight) and chunk g-1's stage is being refilled; completion per stage via tcgen05.commit -> mbarrier.
+// W: bf16 [N_TOTAL][K] (K-major). out: bf16 [M][N_TOTAL]. NT in {32, 64, 128, 256}; K % 64 == 0.
 // ---------------------------------------------------------------------------------------------------------
-template <int N, class Loader>
+template <int NT, class Loader>
 __global__ void __launch_bounds__(128) gemm_tc_kernel(Loader ld, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
-                                                     __nv_bfloat16* __restrict__ out, uint32_t m_total, uint32_t k_total, int relu,
+                                                     __nv_bfloat16* __restrict__ out, uint32_t m_total, uint32_t k_total, uint32_t n_total, int relu,
                                                      unsigned int* err_flag) {
-    static_assert(N % 16 == 0 && N >= 32 && N <= 512, "N");
-    constexpr uint32_t A_BYTES = TILE_M * KC * 2;              // 16 KB
-    constexpr uint32_t B_BYTES = (uint32_t)N * KC * 2;
+    static_assert(NT % 16 == 0 && NT >= 32 && NT <= 256, "NT");
+    constexpr uint32_t A_BYTES = TILE_M * KC * 2;              // 16 KB per stage
+    constexpr uint32_t B_BYTES = (uint32_t)NT * KC * 2;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t LBO = CORE_BYTES;                       // K-adjacent core matrices are contiguous
     constexpr uint32_t SBO = (KC / 8) * CORE_BYTES;            // 8-row groups are 1 KB apart
-    constexpr uint32_t TMEM_COLS = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : (N <= 256 ? 256 : 512)));
+    constexpr uint32_t TMEM_COLS = NT <= 32 ? 32 : (NT <= 64 ? 64 : (NT <= 128 ? 128 : 256));
+    constexpr int BV = (NT * (KC / 8) + 127) / 128;            // W chunks (16 B) per thread and stage
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sa = smem;
-    uint8_t* sb = smem + A_BYTES;
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar[2];
     __shared__ uint32_t tmem_slot;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    const uint32_t row0 = blockIdx.x * TILE_M;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t n0 = blockIdx.y * NT;
 
-    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    const uint32_t my_row = row0 + tid;
-    const bool row_ok = my_row < m_total;
     const uint32_t n_chunks = k_total / KC;
-    for (uint32_t c = 0; c < n_chunks; ++c) {
-        // gather this thread's row of A (8 x 16 bytes) and its share of W while the previous MMAs still run
-        uint4 av[KC / 8];
+    const uint32_t n_mtiles = (m_total + TILE_M - 1) / TILE_M;
+    const __nv_bfloat16* wrow = w + (size_t)n0 * k_total;
+
+    uint4 av[KC / 8], bv[BV];
+    auto gather = [&](const typename Loader::Row& r, bool row_ok, uint32_t c) {
         #pragma unroll
-        for (int j = 0; j < KC / 8; ++j) av[j] = row_ok ? ld.load8(my_row, c * (KC / 8) + j) : make_uint4(0u, 0u, 0u, 0u);
-        if (c > 0 && !mbar_wait_bounded(&bar, (c - 1) & 1u)) { if (tid == 0 && err_flag) atomicExch(err_flag, 1u); break; }   // tensor core done with the staged tiles
+        for (int j = 0; j < KC / 8; ++j) av[j] = row_ok ? ld.load8(r, c * (KC / 8) + j) : make_uint4(0u, 0u, 0u, 0u);
         #pragma unroll
-        for (int j = 0; j < KC / 8; ++j)
-            *reinterpret_cast<uint4*>(sa + (tid >> 3) * SBO + j * LBO + (tid & 7u) * 16u) = av[j];
-        for (uint32_t i = tid; i < (uint32_t)N * (KC / 8); i += 128u) {
-            const uint32_t n = i / (KC / 8), j = i % (KC / 8);
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + (size_t)n * k_total + (size_t)c * KC + j * 8));
-            *reinterpret_cast<uint4*>(sb + (n >> 3) * SBO + j * LBO + (n & 7u) * 16u) = v;
+        for (int i = 0; i < BV; ++i) {
+            const uint32_t idx = tid + i * 128u, n = idx / (KC / 8), j = idx % (KC / 8);
+            bv[i] = (n < (uint32_t)NT) ? __ldg(reinterpret_cast<const uint4*>(wrow + (size_t)n * k_total + (size_t)c * KC + j * 8)) : make_uint4(0u, 0u, 0u, 0u);
         }
-        fence_proxy_async_smem();                              // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
+    };
+
+    uint32_t g = 0;                                            // chunks issued so far by this CTA (stage = g & 1)
+    uint32_t tile = blockIdx.x;
+    if (tile >= n_mtiles) { tc_fence_before(); __syncthreads(); if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS); return; }
+    uint32_t my_row = tile * TILE_M + tid;
+    bool row_ok = my_row < m_total;
+    typename Loader::Row rprep = ld.prepare(row_ok ? my_row : 0u);
+    gather(rprep, row_ok, 0);
+    bool alive = true;
+    while (alive) {
+        for (uint32_t c = 0; c < n_chunks; ++c, ++g) {
+            const uint32_t st = g & 1u;
+            uint8_t* sa = smem + st * STAGE_BYTES;
+            uint8_t* sb = sa + A_BYTES;
+            // stage `st` was last read by the MMAs of chunk g-2
+            if (g >= 2u && !mbar_wait_bounded(&bar[st], ((g - 2u) >> 1) & 1u)) { if (tid == 0 && err_flag) atomicExch(err_flag, 1u); }
             #pragma unroll
-            for (int kk = 0; kk < KC / 16; ++kk) {
-                const uint64_t da = smem_desc(smem_u32(sa) + kk * 2 * LBO, LBO, SBO);
-                #pragma unroll
-                for (int nb = 0; nb < N; nb += 256) {
-                    constexpr int NI = N < 256 ? N : 256;
-                    const uint64_t db = smem_desc(smem_u32(sb) + (nb >> 3) * SBO + kk * 2 * LBO, LBO, SBO);
-                    tc_mma_bf16(tmem_base + nb, da, db, instr_desc_bf16(TILE_M, NI), (c > 0 || kk > 0) ? 1u : 0u);
-                }
+            for (int j = 0; j < KC / 8; ++j) *reinterpret_cast<uint4*>(sa + (tid >> 3) * SBO + j * LBO + (tid & 7u) * 16u) = av[j];
+            #pragma unroll
+            for (int i = 0; i < BV; ++i) {
+                const uint32_t idx = tid + i * 128u, n = idx / (KC / 8), j = idx % (KC / 8);
+                if (n < (uint32_t)NT) *reinterpret_cast<uint4*>(sb + (n >> 3) * SBO + j * LBO + (n & 7u) * 16u) = bv[i];
             }
-            tc_commit(&bar);
+            // next chunk's operands go in flight now (next K chunk of this tile, or chunk 0 of the CTA's next tile)
+            uint32_t next_tile = tile, next_c = c + 1;
+            if (next_c == n_chunks) { next_tile = tile + gridDim.x; next_c = 0; }
+            typename Loader::Row nprep = rprep; bool nrow_ok = row_ok; uint32_t nrow = my_row;
+            if (next_tile != tile) {
+                nrow = next_tile * TILE_M + tid; nrow_ok = next_tile < n_mtiles && nrow < m_total;
+                nprep = ld.prepare(nrow_ok ? nrow : 0u);
+            }
+            if (next_tile < n_mtiles) gather(nprep, nrow_ok, next_c);
+            fence_proxy_async_smem();                          // generic-proxy writes -> visible to the tensor core (async proxy)
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                #pragma unroll
+                for (int kk = 0; kk < KC / 16; ++kk) {
+                    const uint64_t da = smem_desc(smem_u32(sa) + kk * 2 * LBO, LBO, SBO);
+                    const uint64_t db = smem_desc(smem_u32(sb) + kk * 2 * LBO, LBO, SBO);
+                    tc_mma_bf16(tmem_base, da, db, instr_desc_bf16(TILE_M, NT), (c > 0 || kk > 0) ? 1u : 0u);
+                }
+                tc_commit(&bar[st]);
+            }
+            if (c + 1 == n_chunks) {
+                // epilogue of this tile: wait for its last MMAs, thread = row (TMEM lane), 8 columns per tcgen05.ld
+                if (!mbar_wait_bounded(&bar[st], (g >> 1) & 1u)) { if (tid == 0 && err_flag) atomicExch(err_flag, 1u); }
+                tc_fence_after();
+                #pragma unroll 1
+                for (int col = 0; col < NT; col += 8) {
+                    uint32_t v[8];
+                    tmem_ld8(tmem_base + ((warp * 32u) << 16) + (uint32_t)col, v);
+                    if (row_ok) {
+                        float f[8];
+                        #pragma unroll
+                        for (int i = 0; i < 8; ++i) { f[i] = __uint_as_float(v[i]) + bias[n0 + col + i]; if (relu) f[i] = fmaxf(f[i], 0.0f); }
+                        *reinterpret_cast<uint4*>(out + (size_t)my_row * n_total + n0 + col) =
+                            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                    }
+                }
+                tc_fence_before();                             // the next tile's first MMA overwrites the accumulator
+                __syncthreads();
+                tile = next_tile; my_row = nrow; row_ok = nrow_ok; rprep = nprep;
+                alive = tile < n_mtiles;
+            }
         }
     }
-    if (!mbar_wait_bounded(&bar, (n_chunks - 1) & 1u) && tid == 0 && err_flag) atomicExch(err_flag, 1u);
-    tc_fence_after();
-    // epilogue: thread = row (TMEM lane), 8 columns per tcgen05.ld
-    for (int col = 0; col < N; col += 8) {
-        uint32_t v[8];
-        tmem_ld8(tmem_base + ((warp * 32u) << 16) + (uint32_t)col, v);
-        if (row_ok) {
-            float f[8];
-            #pragma unroll
-            for (int i = 0; i < 8; ++i) { f[i] = __uint_as_float(v[i]) + bias[col + i]; if (relu) f[i] = fmaxf(f[i], 0.0f); }
-            const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-            *reinterpret_cast<uint4*>(out + (size_t)my_row * N + col) = o;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
-    (void)lane;
 }
 
 // Dense 512 -> 3 + argmax (tiny: CUDA cores). act bf16 [M][512], w f32 [3][512]; q f32 [M][3]; action u8 [M]
