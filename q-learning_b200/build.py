@@ -10,6 +10,7 @@ HEADERS = [
     os.path.join(_HERE, "csrc", "kernels.cuh"),
     os.path.join(_HERE, "csrc", "physics.cuh"),
     os.path.join(_HERE, "csrc", "qnet.cuh"),
+    os.path.join(_HERE, "csrc", "qnet_conv.cuh"),
     os.path.join(os.path.dirname(_HERE), "include", "ql_cuda.h"),
 ]
 # -fmad=false: the reference's Rust never contracts a*b+c; results must be bit-identical to that arithmetic.

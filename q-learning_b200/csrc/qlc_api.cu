@@ -3,6 +3,7 @@
 #include "../../include/ql_cuda.h"
 #include "kernels.cuh"
 #include "qnet.cuh"
+#include "qnet_conv.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -729,6 +730,20 @@ static cudaError_t launch_gemm_tc(const Loader& ld, const __nv_bfloat16* w, cons
     return cudaGetLastError();
 }
 
+template <class G, class Out>
+static cudaError_t launch_conv_sw(const qnet::ConvArgs& a, const Out& o, cudaStream_t s) {
+    auto kern = qnet::conv_sw_kernel<G, Out>;
+    static int sms = 0;
+    if (sms == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const uint32_t n_batches = (a.n_items + G::B - 1) / G::B;
+    kern<<<n_batches < (uint32_t)sms ? n_batches : (uint32_t)sms, G::THREADS, G::SMEM_BYTES, s>>>(a, o);      // persistent: one CTA per SM
+    return cudaGetLastError();
+}
+
 extern "C" {
 
 // ---------------- Q-network forward on the tensor cores ----------------
@@ -736,14 +751,17 @@ struct qlc_qnet {
     qlc_env* env = nullptr;
     __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr; float* w5 = nullptr;
     float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *b4 = nullptr, *b5 = nullptr;
+    __nv_bfloat16 *w1p = nullptr, *w2p = nullptr, *w3p = nullptr;        // shifted-window conv weights: planes [K/8][N][8]
     __nv_bfloat16 *a1 = nullptr, *a2 = nullptr, *a3 = nullptr, *a4 = nullptr; uint32_t* slot_frame = nullptr; unsigned int* err = nullptr;
+    __nv_bfloat16 *a1p = nullptr, *a2p = nullptr;                         // conv1 / conv2 outputs in the next layer's plane layout
+    int impl = 3;                                                          // how many convs run as shifted-window kernels (QLC_QNET_IMPL, A/B testing)
     float* stage = nullptr; size_t stage_bytes = 0;
     uint32_t cap_items = 0;
 };
 
 static void qnet_free_acts(qlc_qnet* q) {
-    cudaFree(q->a1); cudaFree(q->a2); cudaFree(q->a3); cudaFree(q->a4); cudaFree(q->slot_frame);
-    q->a1 = q->a2 = q->a3 = q->a4 = nullptr; q->slot_frame = nullptr; q->cap_items = 0;
+    cudaFree(q->a1); cudaFree(q->a2); cudaFree(q->a3); cudaFree(q->a4); cudaFree(q->slot_frame); cudaFree(q->a1p); cudaFree(q->a2p);
+    q->a1 = q->a2 = q->a3 = q->a4 = q->a1p = q->a2p = nullptr; q->slot_frame = nullptr; q->cap_items = 0;
 }
 
 int32_t qlc_qnet_destroy(qlc_qnet* q) {
@@ -751,7 +769,7 @@ int32_t qlc_qnet_destroy(qlc_qnet* q) {
     cudaSetDevice(q->env->cfg.device);
     cudaDeviceSynchronize();
     qnet_free_acts(q);
-    cudaFree(q->w1); cudaFree(q->w2); cudaFree(q->w3); cudaFree(q->w4); cudaFree(q->w5);
+    cudaFree(q->w1); cudaFree(q->w2); cudaFree(q->w3); cudaFree(q->w4); cudaFree(q->w5); cudaFree(q->w1p); cudaFree(q->w2p); cudaFree(q->w3p);
     cudaFree(q->b1); cudaFree(q->b2); cudaFree(q->b3); cudaFree(q->b4); cudaFree(q->b5); cudaFree(q->err); cudaFree(q->stage);
     delete q;
     return QLC_OK;
@@ -770,9 +788,12 @@ int32_t qlc_qnet_set_weights(qlc_qnet* q, const qlc_qnet_weights* w) {
     for (int l = 0; l < 5; ++l) {
         CUDA_TRY(cudaMemcpy(q->stage, srcs[2 * l], counts[2 * l] * 4, cudaMemcpyHostToDevice));
         switch (l) {
-            case 0: qnet::prep_conv1_kernel<<<(32 * 256 + 255) / 256, 256>>>(q->stage, q->w1); break;
-            case 1: qnet::prep_transpose_kernel<<<(512 * 64 + 255) / 256, 256>>>(q->stage, q->w2, 512, 64); break;       // [kh][kw][c][cout] = [K][N]
-            case 2: qnet::prep_transpose_kernel<<<(576 * 64 + 255) / 256, 256>>>(q->stage, q->w3, 576, 64); break;
+            case 0: qnet::prep_conv1_kernel<<<(32 * 256 + 255) / 256, 256>>>(q->stage, q->w1);
+                    qnet::prep_conv1_planes_kernel<<<(32 * 256 + 255) / 256, 256>>>(q->stage, q->w1p); break;
+            case 1: qnet::prep_transpose_kernel<<<(512 * 64 + 255) / 256, 256>>>(q->stage, q->w2, 512, 64);             // [kh][kw][c][cout] = [K][N]
+                    qnet::prep_conv2_planes_kernel<<<(512 * 64 + 255) / 256, 256>>>(q->stage, q->w2p); break;
+            case 2: qnet::prep_transpose_kernel<<<(576 * 64 + 255) / 256, 256>>>(q->stage, q->w3, 576, 64);
+                    qnet::prep_conv3_planes_kernel<<<(576 * 64 + 255) / 256, 256>>>(q->stage, q->w3p); break;
             case 3: qnet::prep_transpose_kernel<<<(3136 * 512 + 255) / 256, 256>>>(q->stage, q->w4, 3136, 512); break;
             default: qnet::prep_head_kernel<<<(3 * 512 + 255) / 256, 256>>>(q->stage, q->w5); break;
         }
@@ -792,6 +813,8 @@ int32_t qlc_qnet_create(qlc_env* env, const qlc_qnet_weights* w, qlc_qnet** out)
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     A((void**)&q->w1, 32 * 256 * 2); A((void**)&q->w2, 64 * 512 * 2); A((void**)&q->w3, 64 * 576 * 2); A((void**)&q->w4, (size_t)512 * 3136 * 2); A((void**)&q->w5, 3 * 512 * 4);
+    A((void**)&q->w1p, 32 * 256 * 2); A((void**)&q->w2p, 64 * 512 * 2); A((void**)&q->w3p, 64 * 576 * 2);
+    if (const char* v = getenv("QLC_QNET_IMPL")) q->impl = atoi(v);
     A((void**)&q->b1, 32 * 4); A((void**)&q->b2, 64 * 4); A((void**)&q->b3, 64 * 4); A((void**)&q->b4, 512 * 4); A((void**)&q->b5, 3 * 4); A((void**)&q->err, 4);
     if (e == cudaSuccess) e = cudaMemset(q->err, 0, 4);
     if (e != cudaSuccess) { qlc_qnet_destroy(q); return fail(QLC_ERR_CUDA, std::string("qnet alloc: ") + cudaGetErrorString(e)); }
@@ -814,6 +837,10 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
         qnet_free_acts(q);
         CUDA_TRY(cudaMalloc(&q->a1, (size_t)n * 400 * 32 * 2)); CUDA_TRY(cudaMalloc(&q->a2, (size_t)n * 81 * 64 * 2));
         CUDA_TRY(cudaMalloc(&q->a3, (size_t)n * 49 * 64 * 2)); CUDA_TRY(cudaMalloc(&q->a4, (size_t)n * 512 * 2)); CUDA_TRY(cudaMalloc(&q->slot_frame, (size_t)n * 16));
+        const size_t a1p_bytes = (size_t)((n + qnet::Conv2Geom::B - 1) / qnet::Conv2Geom::B) * qnet::Conv2Geom::STAGE_BYTES;
+        const size_t a2p_bytes = (size_t)((n + qnet::Conv3Geom::B - 1) / qnet::Conv3Geom::B) * qnet::Conv3Geom::STAGE_BYTES;
+        CUDA_TRY(cudaMalloc(&q->a1p, a1p_bytes)); CUDA_TRY(cudaMalloc(&q->a2p, a2p_bytes));
+        CUDA_TRY(cudaMemset(q->a1p, 0, a1p_bytes)); CUDA_TRY(cudaMemset(q->a2p, 0, a2p_bytes));     // rows of a partial last batch are read (never used)
         q->cap_items = n;
     }
     GatherParams g{}; fill_gather(env, g);
@@ -821,12 +848,31 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
     qnet::qnet_locate_kernel<<<(n + 127) / 128, 128, 0, s>>>(g, which ? 1u : 0u, q->slot_frame);
     CUDA_TRY(cudaGetLastError());
     cudaError_t e;
-    qnet::LoadConv1FromRing l1{env->frames, q->slot_frame};
-    e = launch_gemm_tc<32>(l1, q->w1, q->b1, q->a1, n * 400u, 256u, 32u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv1: ") + cudaGetErrorString(e));
-    qnet::LoadConvNHWC l2{q->a1, 20, 20, 32, 9, 9, 4, 4, 2};
-    e = launch_gemm_tc<64>(l2, q->w2, q->b2, q->a2, n * 81u, 512u, 64u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv2: ") + cudaGetErrorString(e));
-    qnet::LoadConvNHWC l3{q->a2, 9, 9, 64, 7, 7, 3, 3, 1};
-    e = launch_gemm_tc<64>(l3, q->w3, q->b3, q->a3, n * 49u, 576u, 64u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv3: ") + cudaGetErrorString(e));
+    const int impl = q->impl;
+    if (impl >= 1) {
+        qnet::ConvArgs a{(const uint8_t*)q->w1p, q->b1, env->frames, q->slot_frame, n, q->err};
+        e = impl >= 2 ? launch_conv_sw<qnet::Conv1Geom>(a, qnet::OutConv2Planes{q->a1p}, s) : launch_conv_sw<qnet::Conv1Geom>(a, qnet::OutXYC{q->a1, 20, 20, 32}, s);
+    } else {
+        qnet::LoadConv1FromRing l1{env->frames, q->slot_frame};
+        e = launch_gemm_tc<32>(l1, q->w1, q->b1, q->a1, n * 400u, 256u, 32u, 1, q->err, s);
+    }
+    if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv1: ") + cudaGetErrorString(e));
+    if (impl >= 2) {
+        qnet::ConvArgs a{(const uint8_t*)q->w2p, q->b2, (const uint8_t*)q->a1p, nullptr, n, q->err};
+        e = impl >= 3 ? launch_conv_sw<qnet::Conv2Geom>(a, qnet::OutConv3Planes{q->a2p}, s) : launch_conv_sw<qnet::Conv2Geom>(a, qnet::OutXYC{q->a2, 9, 9, 64}, s);
+    } else {
+        qnet::LoadConvNHWC l2{q->a1, 20, 20, 32, 9, 9, 4, 4, 2};
+        e = launch_gemm_tc<64>(l2, q->w2, q->b2, q->a2, n * 81u, 512u, 64u, 1, q->err, s);
+    }
+    if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv2: ") + cudaGetErrorString(e));
+    if (impl >= 3) {
+        qnet::ConvArgs a{(const uint8_t*)q->w3p, q->b3, (const uint8_t*)q->a2p, nullptr, n, q->err};
+        e = launch_conv_sw<qnet::Conv3Geom>(a, qnet::OutXYC{q->a3, 7, 7, 64}, s);
+    } else {
+        qnet::LoadConvNHWC l3{q->a2, 9, 9, 64, 7, 7, 3, 3, 1};
+        e = launch_gemm_tc<64>(l3, q->w3, q->b3, q->a3, n * 49u, 576u, 64u, 1, q->err, s);
+    }
+    if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv3: ") + cudaGetErrorString(e));
     qnet::LoadRowMajorBf16 l4{q->a3, 3136u};
     e = launch_gemm_tc<128>(l4, q->w4, q->b4, q->a4, n, 3136u, 512u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("dense1: ") + cudaGetErrorString(e));
     qnet::head_kernel<<<(n + 7) / 8, 256, 0, s>>>(q->a4, q->w5, q->b5, q_dev, action_dev, max_q_dev, n);

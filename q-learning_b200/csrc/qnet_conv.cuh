@@ -1,0 +1,316 @@
+// qnet_conv.cuh — the three convolutions of the Q-network as "shifted-window" implicit GEMMs on tcgen05, without im2col.
+//
+// Idea: a stride-s convolution becomes a stride-1 convolution with few taps after a space-to-depth by s
+// (conv1: 8x8/4 over 84x84x4 -> 2x2 over 21x21x64; conv2: 4x4/2 over 20x20x32 -> 2x2 over 10x10x128; conv3 is 3x3/1 over
+// 9x9x64 already). With the activation stored as a matrix [row = pixel (y*W + x)][channel], tap (dy, dx) of a stride-1
+// convolution is THE SAME matrix shifted by dy*W + dx rows. The tensor core reads its A operand through a shared-memory
+// descriptor, so a shift is just another start address — if the layout allows arbitrary row offsets. The K-major
+// no-swizzle canonical layout does when its 8-row groups are packed back to back (stride-byte-offset = 128): then row r of
+// the 16-byte K chunk j lives at  j * PLANE + r * 16  ("planes" of 8 channels, rows linear), and a window shifted by S rows
+// starts S * 16 bytes further. Each activation byte is staged ONCE (vs 3.6x / 4x / 9x for im2col) and no thread touches
+// the operands of conv2 / conv3 at all: their planes arrive by cp.async.bulk exactly as the previous layer's epilogue
+// wrote them. Output rows whose window crosses the right / bottom edge (or an item boundary) are junk and never stored.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warps 0-3  epilogue: tcgen05.ld of their TMEM lane quadrant, bias + ReLU, bf16, store in the NEXT layer's plane layout
+//   warp  4    one thread issues every tcgen05.mma of a batch (tiles x taps x K steps) and commits to mbarriers
+//   warp  5    one thread issues the bulk copies (conv1: the four u8 ring frames of an item, raw; conv2/3: a whole stage)
+//   warps 6..  conv1 only: convert the raw u8 frames to bf16 planes (space-to-depth by 4) in shared memory
+// Input stages and TMEM accumulator sets are double-buffered, so copies, conversion, MMAs and epilogue of neighbouring
+// batches overlap. Architecture: /root/reference/src/ql-with-tensorflow/python_model/create_ql_model_breakout_84x84x4_3_32.py:17-33.
+#pragma once
+#include "qnet.cuh"
+
+namespace qlc {
+namespace qnet {
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, "
+        "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- layer geometry ---------------------------------------------------------------------------------------
+// ROWS = pixels of one item's (space-to-depth) input, WIN its width; PL = 16-byte channel planes per tap (channels / 8);
+// TY x TX taps; OH x OW valid outputs; N output channels; B items per batch (their rows are concatenated in a plane).
+template <int ROWS_, int WIN_, int PL_, int TY_, int TX_, int OH_, int OW_, int N_, int B_, int NSTAGE_, bool FROM_RING_, int NCONV_>
+struct ConvGeom {
+    static constexpr int ROWS = ROWS_, WIN = WIN_, PL = PL_, TY = TY_, TX = TX_, OH = OH_, OW = OW_, N = N_, B = B_, NSTAGE = NSTAGE_;
+    static constexpr bool FROM_RING = FROM_RING_;
+    static constexpr int NCONV = FROM_RING_ ? NCONV_ : 0;                  // converter warps
+    static constexpr int NRAW = 3;                                         // raw u8 item stages (conv1)
+    static constexpr int TAPS = TY * TX, KSTEPS = PL / 2;                  // K = 16 per MMA = two planes
+    static constexpr int M_NEEDED = (B - 1) * ROWS + (OH - 1) * WIN + OW;  // last valid output row + 1
+    static constexpr int NTILES = (M_NEEDED + TILE_M - 1) / TILE_M;
+    static constexpr int PLANE_BYTES = B * ROWS * 16;
+    static constexpr int STAGE_BYTES = PL * PLANE_BYTES;
+    static constexpr int W_BYTES = TAPS * PL * N * 16;
+    static constexpr int RAW_BYTES = 4 * FRAME_BYTES;
+    static constexpr int TMEM_COLS = 2 * NTILES * N <= 32 ? 32 : (2 * NTILES * N <= 64 ? 64 : (2 * NTILES * N <= 128 ? 128 : (2 * NTILES * N <= 256 ? 256 : 512)));
+    static constexpr int THREADS = 32 * (6 + NCONV);
+    static constexpr int NBAR = 1 + 2 * NSTAGE + 2 * NTILES + 2 + 2 * NRAW;
+    static constexpr size_t SMEM_BYTES = (size_t)W_BYTES + (size_t)NSTAGE * STAGE_BYTES + (FROM_RING ? (size_t)NRAW * RAW_BYTES : 0) + 64 * 4 + NBAR * 8 + 16;
+    static_assert(M_NEEDED >= TILE_M, "a batch must fill at least one M tile");
+    static_assert(2 * NTILES * N <= 512, "accumulators exceed TMEM");
+    static_assert(N == 32 || N == 64, "N");
+    __host__ __device__ static constexpr int row0(int t) { return t < NTILES - 1 ? t * TILE_M : M_NEEDED - TILE_M; }   // the last tile overlaps its predecessor
+    __host__ __device__ static constexpr int first_new_row(int t) { return t * TILE_M; }                                  // rows below were stored by the previous tile
+};
+//                         ROWS WIN PL TY TX OH  OW  N  B  NSTAGE ring  NCONV
+using Conv1Geom = ConvGeom<441, 21, 8, 2, 2, 20, 20, 32, 1, 2, true, 4>;
+using Conv2Geom = ConvGeom<100, 10, 16, 2, 2, 9, 9, 64, 2, 2, false, 0>;
+using Conv3Geom = ConvGeom<81, 9, 8, 3, 3, 7, 7, 64, 3, 2, false, 0>;
+
+// element offset of (item, plane, row) in a global plane buffer grouped in batches of B items: [batch][plane][item in batch][row][8]
+template <class G>
+__host__ __device__ __forceinline__ size_t plane_elem_offset(uint32_t item, uint32_t plane, uint32_t row) {
+    return ((((size_t)(item / G::B) * G::PL + plane) * G::B + item % G::B) * G::ROWS + row) * 8;
+}
+
+// ---- epilogue targets: where the bf16 outputs of pixel (ox, oy) of an item go ---------------------------------
+struct OutXYC {                      // [item][ox][oy][c]: the Keras tensor order (H = x), used for Flatten -> Dense and by the plain GEMM loaders
+    __nv_bfloat16* out; int ow, oh, n;
+    __device__ __forceinline__ void store8(uint32_t item, uint32_t ox, uint32_t oy, uint32_t c0, uint4 v) const {
+        *reinterpret_cast<uint4*>(out + (((size_t)item * ow + ox) * oh + oy) * n + c0) = v;
+    }
+};
+struct OutConv2Planes {              // conv1 -> conv2 input: space-to-depth by 2, channel = (oy&1, ox&1, c), row = (oy/2)*10 + ox/2
+    __nv_bfloat16* out;
+    __device__ __forceinline__ void store8(uint32_t item, uint32_t ox, uint32_t oy, uint32_t c0, uint4 v) const {
+        const uint32_t plane = (((oy & 1u) * 2u + (ox & 1u)) * 32u + c0) >> 3, row = (oy >> 1) * 10u + (ox >> 1);
+        *reinterpret_cast<uint4*>(out + plane_elem_offset<Conv2Geom>(item, plane, row)) = v;
+    }
+};
+struct OutConv3Planes {              // conv2 -> conv3 input: row = oy*9 + ox
+    __nv_bfloat16* out;
+    __device__ __forceinline__ void store8(uint32_t item, uint32_t ox, uint32_t oy, uint32_t c0, uint4 v) const {
+        *reinterpret_cast<uint4*>(out + plane_elem_offset<Conv3Geom>(item, c0 >> 3, oy * 9u + ox)) = v;
+    }
+};
+
+struct ConvArgs {
+    const uint8_t* w;                // prepared weights: bf16 [K/8 planes][N][8], K = tap * (8 PL) + channel
+    const float* bias;               // [N]
+    const uint8_t* in;               // FROM_RING: the u8 frame ring; else the plane buffer written by the previous layer
+    const uint32_t* slot_frame;      // FROM_RING: [item][4] frame number of ring slot h, ~0u = all zero
+    uint32_t n_items;
+    unsigned int* err;
+};
+
+// four u8 pixels -> four bf16 (exact): byte k goes into the mantissa of 2^23, minus 2^23
+__device__ __forceinline__ uint2 u8x4_to_bf16x4(uint32_t w) {
+    const float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - 8388608.0f;
+    const float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - 8388608.0f;
+    const float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388608.0f;
+    const float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388608.0f;
+    return make_uint2(pack_bf16(f0, f1), pack_bf16(f2, f3));
+}
+
+template <class G, class Out>
+__global__ void __launch_bounds__(G::THREADS, 1) conv_sw_kernel(ConvArgs args, Out out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* const s_w = smem;
+    uint8_t* const s_in = s_w + G::W_BYTES;
+    uint8_t* const s_raw = s_in + (size_t)G::NSTAGE * G::STAGE_BYTES;
+    float* const s_bias = reinterpret_cast<float*>(s_raw + (G::FROM_RING ? (size_t)G::NRAW * G::RAW_BYTES : 0));
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(s_bias + 64);
+    uint64_t* const w_full = bars;                       // [1]
+    uint64_t* const in_full = w_full + 1;                // [NSTAGE]
+    uint64_t* const in_empty = in_full + G::NSTAGE;      // [NSTAGE]
+    uint64_t* const acc_full = in_empty + G::NSTAGE;     // [2 * NTILES]
+    uint64_t* const acc_empty = acc_full + 2 * G::NTILES; // [2]
+    uint64_t* const raw_full = acc_empty + 2;            // [NRAW]
+    uint64_t* const raw_empty = raw_full + G::NRAW;      // [NRAW]
+    uint32_t* const s_misc = reinterpret_cast<uint32_t*>(bars + G::NBAR);   // [0] TMEM base, [1] abort flag
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t n_batches = (args.n_items + G::B - 1) / G::B;
+
+    if (tid == 0) {
+        mbar_init(w_full, 1);
+        for (int i = 0; i < G::NSTAGE; ++i) { mbar_init(&in_full[i], G::FROM_RING ? G::NCONV : 1); mbar_init(&in_empty[i], 1); }
+        for (int i = 0; i < 2 * G::NTILES; ++i) mbar_init(&acc_full[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&acc_empty[i], 4);
+        for (int i = 0; i < G::NRAW; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], G::FROM_RING ? G::NCONV : 1); }
+        s_misc[1] = 0u;
+        fence_mbar_init();
+    }
+    if (tid < (uint32_t)G::N) s_bias[tid] = args.bias[tid];
+    if (warp == 4) tmem_alloc(&s_misc[0], G::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_misc[0];
+    volatile uint32_t* const abort_flag = &s_misc[1];
+    // a wait that never hangs the GPU: on time-out raise the error flag and make every role leave its loop
+    auto wait = [&](uint64_t* bar, uint32_t parity) -> bool {
+        if (mbar_wait_bounded(bar, parity)) return true;
+        *abort_flag = 1u;
+        if (args.err) atomicExch(args.err, 2u);
+        return false;
+    };
+
+    if (warp < 4) {
+        // ================= epilogue =================
+        for (uint32_t it = 0, bi = blockIdx.x; bi < n_batches && !*abort_flag; ++it, bi += gridDim.x) {
+            const uint32_t a = it & 1u, ph = (it >> 1) & 1u;
+            #pragma unroll 1
+            for (int t = 0; t < G::NTILES; ++t) {
+                if (!wait(&acc_full[a * G::NTILES + t], ph)) break;
+                tc_fence_after();
+                const uint32_t m = (uint32_t)G::row0(t) + warp * 32u + lane;
+                const uint32_t ib = m / (uint32_t)G::ROWS, r = m - ib * (uint32_t)G::ROWS;
+                const uint32_t oy = r / (uint32_t)G::WIN, ox = r - oy * (uint32_t)G::WIN;
+                const uint32_t item = bi * G::B + ib;
+                const bool ok = m >= (uint32_t)G::first_new_row(t) && ib < (uint32_t)G::B && ox < (uint32_t)G::OW && oy < (uint32_t)G::OH && item < args.n_items;
+                #pragma unroll
+                for (int half = 0; half < G::N / 32; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((warp * 32u) << 16) + (uint32_t)((a * G::NTILES + t) * G::N + half * 32), v);
+                    if (ok) {
+                        #pragma unroll
+                        for (int c = 0; c < 32; c += 8) {
+                            float f[8];
+                            #pragma unroll
+                            for (int i = 0; i < 8; ++i) f[i] = fmaxf(__uint_as_float(v[c + i]) + s_bias[half * 32 + c + i], 0.0f);
+                            out.store8(item, ox, oy, (uint32_t)(half * 32 + c),
+                                       make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+        }
+    } else if (warp == 4) {
+        // ================= MMA issue =================
+        if (lane == 0) {
+            constexpr uint32_t IDESC = instr_desc_bf16(TILE_M, G::N);
+            bool live = wait(w_full, 0);
+            for (uint32_t it = 0, bi = blockIdx.x; live && bi < n_batches && !*abort_flag; ++it, bi += gridDim.x) {
+                const uint32_t s = it % G::NSTAGE, ph_in = (it / G::NSTAGE) & 1u, a = it & 1u, ph_acc = (it >> 1) & 1u;
+                if (!wait(&in_full[s], ph_in) || !wait(&acc_empty[a], ph_acc ^ 1u)) break;
+                tc_fence_after();
+                const uint32_t in_addr = smem_u32(s_in + (size_t)s * G::STAGE_BYTES), w_addr = smem_u32(s_w);
+                #pragma unroll 1
+                for (int t = 0; t < G::NTILES; ++t) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((a * G::NTILES + t) * G::N);
+                    #pragma unroll
+                    for (int tap = 0; tap < G::TAPS; ++tap) {
+                        const uint32_t shift = (uint32_t)((tap / G::TX) * G::WIN + (tap % G::TX));
+                        #pragma unroll
+                        for (int kk = 0; kk < G::KSTEPS; ++kk) {
+                            const uint64_t da = smem_desc(in_addr + (uint32_t)(2 * kk) * G::PLANE_BYTES + ((uint32_t)G::row0(t) + shift) * 16u, G::PLANE_BYTES, 128u);
+                            const uint64_t db = smem_desc(w_addr + (uint32_t)((tap * G::PL + 2 * kk) * G::N * 16), G::N * 16, 128u);
+                            tc_mma_bf16(d_tmem, da, db, IDESC, (tap > 0 || kk > 0) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(&acc_full[a * G::NTILES + t]);
+                }
+                tc_commit(&in_empty[s]);
+            }
+        }
+    } else if (warp == 5) {
+        // ================= bulk-copy issue =================
+        if (lane == 0) {
+            mbar_expect_tx(w_full, G::W_BYTES);
+            for (int off = 0; off < G::W_BYTES; off += 16384) bulk_load(s_w + off, args.w + off, (uint32_t)(G::W_BYTES - off < 16384 ? G::W_BYTES - off : 16384), w_full);
+            for (uint32_t it = 0, bi = blockIdx.x; bi < n_batches && !*abort_flag; ++it, bi += gridDim.x) {
+                if constexpr (G::FROM_RING) {
+                    const uint32_t r = it % G::NRAW, ph = (it / G::NRAW) & 1u;
+                    if (!wait(&raw_empty[r], ph ^ 1u)) break;
+                    uint32_t fi[4], nv = 0;
+                    #pragma unroll
+                    for (int h = 0; h < 4; ++h) { fi[h] = __ldg(args.slot_frame + (size_t)bi * 4 + h); nv += fi[h] != 0xFFFFFFFFu; }
+                    if (nv) {
+                        mbar_expect_tx(&raw_full[r], nv * FRAME_BYTES);
+                        #pragma unroll
+                        for (int h = 0; h < 4; ++h)
+                            if (fi[h] != 0xFFFFFFFFu) bulk_load(s_raw + (size_t)r * G::RAW_BYTES + h * FRAME_BYTES, args.in + (size_t)fi[h] * FRAME_BYTES, FRAME_BYTES, &raw_full[r]);
+                    } else {
+                        mbar_arrive(&raw_full[r]);
+                    }
+                } else {
+                    const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1u;
+                    if (!wait(&in_empty[s], ph ^ 1u)) break;
+                    mbar_expect_tx(&in_full[s], G::STAGE_BYTES);
+                    const uint8_t* src = args.in + (size_t)bi * G::STAGE_BYTES;
+                    uint8_t* dst = s_in + (size_t)s * G::STAGE_BYTES;
+                    constexpr int CH = (G::STAGE_BYTES / 4 + 15) & ~15;
+                    for (int off = 0; off < G::STAGE_BYTES; off += CH) bulk_load(dst + off, src + off, (uint32_t)(G::STAGE_BYTES - off < CH ? G::STAGE_BYTES - off : CH), &in_full[s]);
+                }
+            }
+        }
+    } else {
+        // ================= conv1: u8 ring frames -> bf16 planes, space-to-depth by 4 =================
+        if constexpr (G::FROM_RING) {
+            const uint32_t ct = (warp - 6u) * 32u + lane;
+            constexpr uint32_t CT = G::NCONV * 32;
+            for (uint32_t it = 0, bi = blockIdx.x; bi < n_batches && !*abort_flag; ++it, bi += gridDim.x) {
+                const uint32_t r = it % G::NRAW, ph_r = (it / G::NRAW) & 1u, s = it % G::NSTAGE, ph_s = (it / G::NSTAGE) & 1u;
+                if (!wait(&raw_full[r], ph_r) || !wait(&in_empty[s], ph_s ^ 1u)) break;
+                const uint8_t* raw = s_raw + (size_t)r * G::RAW_BYTES;
+                uint8_t* dst = s_in + (size_t)s * G::STAGE_BYTES;
+                #pragma unroll 1
+                for (uint32_t h = 0; h < 4; ++h) {
+                    const bool present = __ldg(args.slot_frame + (size_t)bi * 4 + h) != 0xFFFFFFFFu;
+                    // work item = (row pair q = y/2, X = x/4): 8 pixels = channels (y&1, x&3) of plane 2h + (q&1), row (q/2)*21 + X
+                    #pragma unroll 7
+                    for (uint32_t idx = ct; idx < 42u * 21u; idx += CT) {
+                        const uint32_t q = idx / 21u, X = idx - q * 21u;
+                        uint32_t lo = 0u, hi = 0u;
+                        if (present) {
+                            const uint8_t* p = raw + h * FRAME_BYTES + q * (2u * FRAME_W) + X * 4u;
+                            lo = *reinterpret_cast<const uint32_t*>(p);
+                            hi = *reinterpret_cast<const uint32_t*>(p + FRAME_W);
+                        }
+                        const uint2 a = u8x4_to_bf16x4(lo), b = u8x4_to_bf16x4(hi);
+                        *reinterpret_cast<uint4*>(dst + (size_t)(2u * h + (q & 1u)) * G::PLANE_BYTES + ((q >> 1) * 21u + X) * 16u) = make_uint4(a.x, a.y, b.x, b.y);
+                    }
+                }
+                fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&in_full[s]); mbar_arrive(&raw_empty[r]); }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, G::TMEM_COLS);
+}
+
+// ---- weight preparation: Keras [kx][ky][cin][cout] f32 -> bf16 planes [K/8][N][8] in each layer's K order ---------------
+// conv1: k = tap*64 + h*16 + iy*4 + ix, tap = dy*2 + dx, kernel index (kx = 4dx + ix, ky = 4dy + iy, h)
+__global__ void prep_conv1_planes_kernel(const float* __restrict__ kernel /*[8][8][4][32]*/, __nv_bfloat16* __restrict__ w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 256 * 32) return;
+    const int e = i & 7, n = (i >> 3) % 32, k = (i / 256) * 8 + e;
+    const int tap = k / 64, c = k % 64, dy = tap / 2, dx = tap % 2, h = c / 16, iy = (c / 4) % 4, ix = c % 4;
+    w[i] = __float2bfloat16_rn(kernel[(((4 * dx + ix) * 8 + (4 * dy + iy)) * 4 + h) * 32 + n]);
+}
+// conv2: k = tap*128 + (iy*2 + ix)*32 + ci, tap = dy*2 + dx, kernel index (kx = 2dx + ix, ky = 2dy + iy, ci)
+__global__ void prep_conv2_planes_kernel(const float* __restrict__ kernel /*[4][4][32][64]*/, __nv_bfloat16* __restrict__ w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 512 * 64) return;
+    const int e = i & 7, n = (i >> 3) % 64, k = (i / 512) * 8 + e;
+    const int tap = k / 128, c = k % 128, dy = tap / 2, dx = tap % 2, iy = c / 64, ix = (c / 32) % 2, ci = c % 32;
+    w[i] = __float2bfloat16_rn(kernel[(((2 * dx + ix) * 4 + (2 * dy + iy)) * 32 + ci) * 64 + n]);
+}
+// conv3: k = tap*64 + ci, tap = dy*3 + dx, kernel index (kx = dx, ky = dy, ci)
+__global__ void prep_conv3_planes_kernel(const float* __restrict__ kernel /*[3][3][64][64]*/, __nv_bfloat16* __restrict__ w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 576 * 64) return;
+    const int e = i & 7, n = (i >> 3) % 64, k = (i / 512) * 8 + e;
+    const int tap = k / 64, ci = k % 64, dy = tap / 3, dx = tap % 3;
+    w[i] = __float2bfloat16_rn(kernel[((dx * 3 + dy) * 64 + ci) * 64 + n]);
+}
+
+}  // namespace qnet
+}  // namespace qlc
