@@ -751,17 +751,18 @@ struct qlc_qnet {
     qlc_env* env = nullptr;
     __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr; float* w5 = nullptr;
     float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *b4 = nullptr, *b5 = nullptr;
-    __nv_bfloat16 *w1p = nullptr, *w2p = nullptr, *w3p = nullptr;        // shifted-window conv weights: planes [K/8][N][8]
+    __nv_bfloat16 *w1p = nullptr, *w2p = nullptr, *w3p = nullptr, *w4p = nullptr;   // operand-layout weights: planes [K/8][N][8]
     __nv_bfloat16 *a1 = nullptr, *a2 = nullptr, *a3 = nullptr, *a4 = nullptr; uint32_t* slot_frame = nullptr; unsigned int* err = nullptr;
-    __nv_bfloat16 *a1p = nullptr, *a2p = nullptr;                         // conv1 / conv2 outputs in the next layer's plane layout
-    int impl = 3;                                                          // how many convs run as shifted-window kernels (QLC_QNET_IMPL, A/B testing)
+    __nv_bfloat16 *a1p = nullptr, *a2p = nullptr, *a3p = nullptr;         // conv outputs in the next layer's operand (plane) layout
+    unsigned long long* prof = nullptr;                                    // QLC_QNET_PROF: per-role cycle counters of CTA 0, printed after each forward
+    int impl = 4;                                                          // how many convs run as shifted-window kernels (QLC_QNET_IMPL, A/B testing)
     float* stage = nullptr; size_t stage_bytes = 0;
     uint32_t cap_items = 0;
 };
 
 static void qnet_free_acts(qlc_qnet* q) {
-    cudaFree(q->a1); cudaFree(q->a2); cudaFree(q->a3); cudaFree(q->a4); cudaFree(q->slot_frame); cudaFree(q->a1p); cudaFree(q->a2p);
-    q->a1 = q->a2 = q->a3 = q->a4 = q->a1p = q->a2p = nullptr; q->slot_frame = nullptr; q->cap_items = 0;
+    cudaFree(q->a1); cudaFree(q->a2); cudaFree(q->a3); cudaFree(q->a4); cudaFree(q->slot_frame); cudaFree(q->a1p); cudaFree(q->a2p); cudaFree(q->a3p);
+    q->a1 = q->a2 = q->a3 = q->a4 = q->a1p = q->a2p = q->a3p = nullptr; q->slot_frame = nullptr; q->cap_items = 0;
 }
 
 int32_t qlc_qnet_destroy(qlc_qnet* q) {
@@ -769,8 +770,8 @@ int32_t qlc_qnet_destroy(qlc_qnet* q) {
     cudaSetDevice(q->env->cfg.device);
     cudaDeviceSynchronize();
     qnet_free_acts(q);
-    cudaFree(q->w1); cudaFree(q->w2); cudaFree(q->w3); cudaFree(q->w4); cudaFree(q->w5); cudaFree(q->w1p); cudaFree(q->w2p); cudaFree(q->w3p);
-    cudaFree(q->b1); cudaFree(q->b2); cudaFree(q->b3); cudaFree(q->b4); cudaFree(q->b5); cudaFree(q->err); cudaFree(q->stage);
+    cudaFree(q->w1); cudaFree(q->w2); cudaFree(q->w3); cudaFree(q->w4); cudaFree(q->w5); cudaFree(q->w1p); cudaFree(q->w2p); cudaFree(q->w3p); cudaFree(q->w4p);
+    cudaFree(q->b1); cudaFree(q->b2); cudaFree(q->b3); cudaFree(q->b4); cudaFree(q->b5); cudaFree(q->err); cudaFree(q->stage); cudaFree(q->prof);
     delete q;
     return QLC_OK;
 }
@@ -794,7 +795,8 @@ int32_t qlc_qnet_set_weights(qlc_qnet* q, const qlc_qnet_weights* w) {
                     qnet::prep_conv2_planes_kernel<<<(512 * 64 + 255) / 256, 256>>>(q->stage, q->w2p); break;
             case 2: qnet::prep_transpose_kernel<<<(576 * 64 + 255) / 256, 256>>>(q->stage, q->w3, 576, 64);
                     qnet::prep_conv3_planes_kernel<<<(576 * 64 + 255) / 256, 256>>>(q->stage, q->w3p); break;
-            case 3: qnet::prep_transpose_kernel<<<(3136 * 512 + 255) / 256, 256>>>(q->stage, q->w4, 3136, 512); break;
+            case 3: qnet::prep_transpose_kernel<<<(3136 * 512 + 255) / 256, 256>>>(q->stage, q->w4, 3136, 512);
+                    qnet::prep_dense_planes_kernel<<<(3136 * 512 + 255) / 256, 256>>>(q->stage, q->w4p); break;
             default: qnet::prep_head_kernel<<<(3 * 512 + 255) / 256, 256>>>(q->stage, q->w5); break;
         }
         CUDA_TRY(cudaGetLastError());
@@ -813,8 +815,9 @@ int32_t qlc_qnet_create(qlc_env* env, const qlc_qnet_weights* w, qlc_qnet** out)
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     A((void**)&q->w1, 32 * 256 * 2); A((void**)&q->w2, 64 * 512 * 2); A((void**)&q->w3, 64 * 576 * 2); A((void**)&q->w4, (size_t)512 * 3136 * 2); A((void**)&q->w5, 3 * 512 * 4);
-    A((void**)&q->w1p, 32 * 256 * 2); A((void**)&q->w2p, 64 * 512 * 2); A((void**)&q->w3p, 64 * 576 * 2);
+    A((void**)&q->w1p, 32 * 256 * 2); A((void**)&q->w2p, 64 * 512 * 2); A((void**)&q->w3p, 64 * 576 * 2); A((void**)&q->w4p, (size_t)512 * 3136 * 2);
     if (const char* v = getenv("QLC_QNET_IMPL")) q->impl = atoi(v);
+    if (getenv("QLC_QNET_PROF")) A((void**)&q->prof, 3 * 32 * 8);
     A((void**)&q->b1, 32 * 4); A((void**)&q->b2, 64 * 4); A((void**)&q->b3, 64 * 4); A((void**)&q->b4, 512 * 4); A((void**)&q->b5, 3 * 4); A((void**)&q->err, 4);
     if (e == cudaSuccess) e = cudaMemset(q->err, 0, 4);
     if (e != cudaSuccess) { qlc_qnet_destroy(q); return fail(QLC_ERR_CUDA, std::string("qnet alloc: ") + cudaGetErrorString(e)); }
@@ -840,6 +843,8 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
         const size_t a1p_bytes = (size_t)((n + qnet::Conv2Geom::B - 1) / qnet::Conv2Geom::B) * qnet::Conv2Geom::STAGE_BYTES;
         const size_t a2p_bytes = (size_t)((n + qnet::Conv3Geom::B - 1) / qnet::Conv3Geom::B) * qnet::Conv3Geom::STAGE_BYTES;
         CUDA_TRY(cudaMalloc(&q->a1p, a1p_bytes)); CUDA_TRY(cudaMalloc(&q->a2p, a2p_bytes));
+        const size_t a3p_bytes = (size_t)((n + 127) / 128) * qnet::DenseGeom::A_TILE_BYTES;
+        CUDA_TRY(cudaMalloc(&q->a3p, a3p_bytes)); CUDA_TRY(cudaMemset(q->a3p, 0, a3p_bytes));
         CUDA_TRY(cudaMemset(q->a1p, 0, a1p_bytes)); CUDA_TRY(cudaMemset(q->a2p, 0, a2p_bytes));     // rows of a partial last batch are read (never used)
         q->cap_items = n;
     }
@@ -850,7 +855,7 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
     cudaError_t e;
     const int impl = q->impl;
     if (impl >= 1) {
-        qnet::ConvArgs a{(const uint8_t*)q->w1p, q->b1, env->frames, q->slot_frame, n, q->err};
+        qnet::ConvArgs a{(const uint8_t*)q->w1p, q->b1, env->frames, q->slot_frame, n, q->err, q->prof};
         e = impl >= 2 ? launch_conv_sw<qnet::Conv1Geom>(a, qnet::OutConv2Planes{q->a1p}, s) : launch_conv_sw<qnet::Conv1Geom>(a, qnet::OutXYC{q->a1, 20, 20, 32}, s);
     } else {
         qnet::LoadConv1FromRing l1{env->frames, q->slot_frame};
@@ -858,7 +863,7 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
     }
     if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv1: ") + cudaGetErrorString(e));
     if (impl >= 2) {
-        qnet::ConvArgs a{(const uint8_t*)q->w2p, q->b2, (const uint8_t*)q->a1p, nullptr, n, q->err};
+        qnet::ConvArgs a{(const uint8_t*)q->w2p, q->b2, (const uint8_t*)q->a1p, nullptr, n, q->err, q->prof ? q->prof + 32 : nullptr};
         e = impl >= 3 ? launch_conv_sw<qnet::Conv2Geom>(a, qnet::OutConv3Planes{q->a2p}, s) : launch_conv_sw<qnet::Conv2Geom>(a, qnet::OutXYC{q->a2, 9, 9, 64}, s);
     } else {
         qnet::LoadConvNHWC l2{q->a1, 20, 20, 32, 9, 9, 4, 4, 2};
@@ -866,17 +871,34 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
     }
     if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv2: ") + cudaGetErrorString(e));
     if (impl >= 3) {
-        qnet::ConvArgs a{(const uint8_t*)q->w3p, q->b3, (const uint8_t*)q->a2p, nullptr, n, q->err};
-        e = launch_conv_sw<qnet::Conv3Geom>(a, qnet::OutXYC{q->a3, 7, 7, 64}, s);
+        qnet::ConvArgs a{(const uint8_t*)q->w3p, q->b3, (const uint8_t*)q->a2p, nullptr, n, q->err, q->prof ? q->prof + 64 : nullptr};
+        e = impl >= 4 ? launch_conv_sw<qnet::Conv3Geom>(a, qnet::OutDensePlanes{q->a3p}, s) : launch_conv_sw<qnet::Conv3Geom>(a, qnet::OutXYC{q->a3, 7, 7, 64}, s);
     } else {
         qnet::LoadConvNHWC l3{q->a2, 9, 9, 64, 7, 7, 3, 3, 1};
         e = launch_gemm_tc<64>(l3, q->w3, q->b3, q->a3, n * 49u, 576u, 64u, 1, q->err, s);
     }
     if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv3: ") + cudaGetErrorString(e));
-    qnet::LoadRowMajorBf16 l4{q->a3, 3136u};
-    e = launch_gemm_tc<128>(l4, q->w4, q->b4, q->a4, n, 3136u, 512u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("dense1: ") + cudaGetErrorString(e));
-    qnet::head_kernel<<<(n + 7) / 8, 256, 0, s>>>(q->a4, q->w5, q->b5, q_dev, action_dev, max_q_dev, n);
+    if (impl >= 4) {
+        static bool attr_set = false;
+        if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(qnet::dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qnet::DenseGeom::SMEM_BYTES)); attr_set = true; }
+        qnet::dense_tc_kernel<<<dim3((n + 127) / 128, 2), qnet::DenseGeom::THREADS, qnet::DenseGeom::SMEM_BYTES, s>>>((const uint8_t*)q->a3p, (const uint8_t*)q->w4p, q->b4, q->a4, n, q->err);
+        CUDA_TRY(cudaGetLastError());
+        const uint32_t hb = (n + 7) / 8;
+        qnet::head_vec_kernel<<<hb < 592u ? hb : 592u, 256, 0, s>>>(q->a4, q->w5, q->b5, q_dev, action_dev, max_q_dev, n);
+    } else {
+        qnet::LoadRowMajorBf16 l4{q->a3, 3136u};
+        e = launch_gemm_tc<128>(l4, q->w4, q->b4, q->a4, n, 3136u, 512u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("dense1: ") + cudaGetErrorString(e));
+        qnet::head_kernel<<<(n + 7) / 8, 256, 0, s>>>(q->a4, q->w5, q->b5, q_dev, action_dev, max_q_dev, n);
+    }
     CUDA_TRY(cudaGetLastError());
+    if (q->prof) {
+        unsigned long long h[96];
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaMemcpy(h, q->prof, sizeof(h), cudaMemcpyDeviceToHost));
+        static const char* roles[4] = {"epilogue", "mma", "loader", "converter"};
+        for (int l = 0; l < 3; ++l) for (int r = 0; r < 4; ++r)
+            fprintf(stderr, "qnet prof conv%d %-9s total %8llu wait1 %8llu wait2 %8llu other-wait %8llu\n", l + 1, roles[r], h[l * 32 + r * 8], h[l * 32 + r * 8 + 1], h[l * 32 + r * 8 + 2], h[l * 32 + r * 8 + 7]);
+    }
     return QLC_OK;
 }
 

@@ -36,6 +36,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// warp-wide variants: all 32 lanes execute them with identical operands, one elected lane issues
+__device__ __forceinline__ void tc_mma_bf16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// same with the descriptors given as their low words (start address >> 4 | leading-dimension offset << 16); the high word
+// is the constant stride-byte-offset 128 + descriptor version 1
+__device__ __forceinline__ void tc_mma_bf16_elect_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, 0x4008};\n\t"
+        "mov.b64 db, {%2, 0x4008};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---- layer geometry ---------------------------------------------------------------------------------------
 // ROWS = pixels of one item's (space-to-depth) input, WIN its width; PL = 16-byte channel planes per tap (channels / 8);
 // TY x TX taps; OH x OW valid outputs; N output channels; B items per batch (their rows are concatenated in a plane).
@@ -55,7 +83,7 @@ struct ConvGeom {
     static constexpr int TMEM_COLS = 2 * NTILES * N <= 32 ? 32 : (2 * NTILES * N <= 64 ? 64 : (2 * NTILES * N <= 128 ? 128 : (2 * NTILES * N <= 256 ? 256 : 512)));
     static constexpr int THREADS = 32 * (6 + NCONV);
     static constexpr int NBAR = 1 + 2 * NSTAGE + 2 * NTILES + 2 + 2 * NRAW;
-    static constexpr size_t SMEM_BYTES = (size_t)W_BYTES + (size_t)NSTAGE * STAGE_BYTES + (FROM_RING ? (size_t)NRAW * RAW_BYTES : 0) + 64 * 4 + NBAR * 8 + 16;
+    static constexpr size_t SMEM_BYTES = (size_t)W_BYTES + (size_t)NSTAGE * STAGE_BYTES + (FROM_RING ? (size_t)NRAW * RAW_BYTES : 0) + 64 * 4 + NBAR * 8 + 16 + NRAW * 16;
     static_assert(M_NEEDED >= TILE_M, "a batch must fill at least one M tile");
     static_assert(2 * NTILES * N <= 512, "accumulators exceed TMEM");
     static_assert(N == 32 || N == 64, "N");
@@ -63,7 +91,7 @@ struct ConvGeom {
     __host__ __device__ static constexpr int first_new_row(int t) { return t * TILE_M; }                                  // rows below were stored by the previous tile
 };
 //                         ROWS WIN PL TY TX OH  OW  N  B  NSTAGE ring  NCONV
-using Conv1Geom = ConvGeom<441, 21, 8, 2, 2, 20, 20, 32, 1, 2, true, 4>;
+using Conv1Geom = ConvGeom<441, 21, 8, 2, 2, 20, 20, 32, 1, 2, true, 8>;
 using Conv2Geom = ConvGeom<100, 10, 16, 2, 2, 9, 9, 64, 2, 2, false, 0>;
 using Conv3Geom = ConvGeom<81, 9, 8, 3, 3, 7, 7, 64, 3, 2, false, 0>;
 
@@ -101,6 +129,7 @@ struct ConvArgs {
     const uint32_t* slot_frame;      // FROM_RING: [item][4] frame number of ring slot h, ~0u = all zero
     uint32_t n_items;
     unsigned int* err;
+    unsigned long long* prof;        // optional (QLC_QNET_PROF): CTA 0 writes per-role cycle counters [4 roles][8]
 };
 
 // four u8 pixels -> four bf16 (exact): byte k goes into the mantissa of 2^23, minus 2^23
@@ -119,7 +148,8 @@ __global__ void __launch_bounds__(G::THREADS, 1) conv_sw_kernel(ConvArgs args, O
     uint8_t* const s_in = s_w + G::W_BYTES;
     uint8_t* const s_raw = s_in + (size_t)G::NSTAGE * G::STAGE_BYTES;
     float* const s_bias = reinterpret_cast<float*>(s_raw + (G::FROM_RING ? (size_t)G::NRAW * G::RAW_BYTES : 0));
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(s_bias + 64);
+    uint32_t* const s_slot = reinterpret_cast<uint32_t*>(s_bias + 64);      // [NRAW][4] ring frame of each slot of the item in raw stage r (16-byte aligned)
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(s_slot + G::NRAW * 4);
     uint64_t* const w_full = bars;                       // [1]
     uint64_t* const in_full = w_full + 1;                // [NSTAGE]
     uint64_t* const in_empty = in_full + G::NSTAGE;      // [NSTAGE]
@@ -149,8 +179,14 @@ __global__ void __launch_bounds__(G::THREADS, 1) conv_sw_kernel(ConvArgs args, O
     const uint32_t tmem_base = s_misc[0];
     volatile uint32_t* const abort_flag = &s_misc[1];
     // a wait that never hangs the GPU: on time-out raise the error flag and make every role leave its loop
-    auto wait = [&](uint64_t* bar, uint32_t parity) -> bool {
-        if (mbar_wait_bounded(bar, parity)) return true;
+    const bool prof_on = args.prof != nullptr && blockIdx.x == 0 && lane == 0;
+    unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
+    auto wait = [&](uint64_t* bar, uint32_t parity, int slot = 7) -> bool {
+        const long long t0 = prof_on ? clock64() : 0;
+        const bool done = mbar_wait_bounded(bar, parity);
+        if (prof_on) pc[slot] += (unsigned long long)(clock64() - t0);
+        if (done) return true;
         *abort_flag = 1u;
         if (args.err) atomicExch(args.err, 2u);
         return false;
@@ -162,7 +198,7 @@ __global__ void __launch_bounds__(G::THREADS, 1) conv_sw_kernel(ConvArgs args, O
             const uint32_t a = it & 1u, ph = (it >> 1) & 1u;
             #pragma unroll 1
             for (int t = 0; t < G::NTILES; ++t) {
-                if (!wait(&acc_full[a * G::NTILES + t], ph)) break;
+                if (!wait(&acc_full[a * G::NTILES + t], ph, 1)) break;
                 tc_fence_after();
                 const uint32_t m = (uint32_t)G::row0(t) + warp * 32u + lane;
                 const uint32_t ib = m / (uint32_t)G::ROWS, r = m - ib * (uint32_t)G::ROWS;
@@ -191,44 +227,56 @@ __global__ void __launch_bounds__(G::THREADS, 1) conv_sw_kernel(ConvArgs args, O
         }
     } else if (warp == 4) {
         // ================= MMA issue =================
-        if (lane == 0) {
-            constexpr uint32_t IDESC = instr_desc_bf16(TILE_M, G::N);
-            bool live = wait(w_full, 0);
-            for (uint32_t it = 0, bi = blockIdx.x; live && bi < n_batches && !*abort_flag; ++it, bi += gridDim.x) {
-                const uint32_t s = it % G::NSTAGE, ph_in = (it / G::NSTAGE) & 1u, a = it & 1u, ph_acc = (it >> 1) & 1u;
-                if (!wait(&in_full[s], ph_in) || !wait(&acc_empty[a], ph_acc ^ 1u)) break;
-                tc_fence_after();
-                const uint32_t in_addr = smem_u32(s_in + (size_t)s * G::STAGE_BYTES), w_addr = smem_u32(s_w);
-                #pragma unroll 1
-                for (int t = 0; t < G::NTILES; ++t) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)((a * G::NTILES + t) * G::N);
+        // The whole warp runs the loop so that every operand of tcgen05.mma stays warp-uniform (uniform registers, no
+        // per-instruction broadcast loop in SASS); one elected lane issues.
+        // Loop control is kept provably warp-uniform too (votes on the wait results; the TMEM base through a warp reduction,
+        // which lands in a uniform register).
+        constexpr uint32_t IDESC = instr_desc_bf16(TILE_M, G::N);
+        const uint32_t tmem_u = __reduce_max_sync(0xFFFFFFFFu, tmem_base);
+        const bool live = __all_sync(0xFFFFFFFFu, wait(w_full, 0));
+        for (uint32_t it = 0, bi = blockIdx.x; live && bi < n_batches; ++it, bi += gridDim.x) {
+            const uint32_t s = it % G::NSTAGE, ph_in = (it / G::NSTAGE) & 1u, a = it & 1u, ph_acc = (it >> 1) & 1u;
+            const bool ok = wait(&in_full[s], ph_in, 1) && wait(&acc_empty[a], ph_acc ^ 1u, 2);
+            if (!__all_sync(0xFFFFFFFFu, ok)) break;
+            tc_fence_after();
+            // descriptor low words: start address >> 4 (shared-memory addresses are < 2^18, all offsets multiples of 16) | LBO << 16
+            const uint32_t b_lo0 = (smem_u32(s_w) >> 4) | ((uint32_t)(G::N * 16 >> 4) << 16);
+            const uint32_t a_lo0 = ((smem_u32(s_in) + s * (uint32_t)G::STAGE_BYTES) >> 4) | ((uint32_t)(G::PLANE_BYTES >> 4) << 16);
+            #pragma unroll 1
+            for (int t = 0; t < G::NTILES; ++t) {
+                const uint32_t d_tmem = tmem_u + (uint32_t)((a * G::NTILES + t) * G::N);
+                const uint32_t a_lo = a_lo0 + (uint32_t)G::row0(t);                       // one row = 16 bytes = 1 address unit
+                #pragma unroll
+                for (int tap = 0; tap < G::TAPS; ++tap) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const uint32_t shift = (uint32_t)((tap / G::TX) * G::WIN + (tap % G::TX));
                     #pragma unroll
-                    for (int tap = 0; tap < G::TAPS; ++tap) {
-                        const uint32_t shift = (uint32_t)((tap / G::TX) * G::WIN + (tap % G::TX));
-                        #pragma unroll
-                        for (int kk = 0; kk < G::KSTEPS; ++kk) {
-                            const uint64_t da = smem_desc(in_addr + (uint32_t)(2 * kk) * G::PLANE_BYTES + ((uint32_t)G::row0(t) + shift) * 16u, G::PLANE_BYTES, 128u);
-                            const uint64_t db = smem_desc(w_addr + (uint32_t)((tap * G::PL + 2 * kk) * G::N * 16), G::N * 16, 128u);
-                            tc_mma_bf16(d_tmem, da, db, IDESC, (tap > 0 || kk > 0) ? 1u : 0u);
-                        }
-                    }
-                    tc_commit(&acc_full[a * G::NTILES + t]);
+                    for (int kk = 0; kk < G::KSTEPS; ++kk)
+                        tc_mma_bf16_elect_lo(d_tmem, a_lo + shift + (uint32_t)(2 * kk) * (G::PLANE_BYTES >> 4), b_lo0 + (uint32_t)((tap * G::PL + 2 * kk) * G::N),
+                                             IDESC, (tap > 0 || kk > 0) ? 1u : 0u);
                 }
-                tc_commit(&in_empty[s]);
+                tc_commit_elect(&acc_full[a * G::NTILES + t]);
             }
+            tc_commit_elect(&in_empty[s]);
         }
     } else if (warp == 5) {
         // ================= bulk-copy issue =================
         if (lane == 0) {
             mbar_expect_tx(w_full, G::W_BYTES);
             for (int off = 0; off < G::W_BYTES; off += 16384) bulk_load(s_w + off, args.w + off, (uint32_t)(G::W_BYTES - off < 16384 ? G::W_BYTES - off : 16384), w_full);
+            uint4 cur = make_uint4(0u, 0u, 0u, 0u);
+            if constexpr (G::FROM_RING) { if (blockIdx.x < n_batches) cur = __ldg(reinterpret_cast<const uint4*>(args.slot_frame) + blockIdx.x); }
             for (uint32_t it = 0, bi = blockIdx.x; bi < n_batches && !*abort_flag; ++it, bi += gridDim.x) {
                 if constexpr (G::FROM_RING) {
                     const uint32_t r = it % G::NRAW, ph = (it / G::NRAW) & 1u;
-                    if (!wait(&raw_empty[r], ph ^ 1u)) break;
-                    uint32_t fi[4], nv = 0;
+                    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);                  // the next item's slot table travels during the wait
+                    if (bi + gridDim.x < n_batches) nxt = __ldg(reinterpret_cast<const uint4*>(args.slot_frame) + bi + gridDim.x);
+                    if (!wait(&raw_empty[r], ph ^ 1u, 1)) break;
+                    const uint32_t fi[4] = {cur.x, cur.y, cur.z, cur.w};
+                    *reinterpret_cast<uint4*>(s_slot + r * 4) = cur;         // published to the converters by the arrive below (release)
+                    uint32_t nv = 0;
                     #pragma unroll
-                    for (int h = 0; h < 4; ++h) { fi[h] = __ldg(args.slot_frame + (size_t)bi * 4 + h); nv += fi[h] != 0xFFFFFFFFu; }
+                    for (int h = 0; h < 4; ++h) nv += fi[h] != 0xFFFFFFFFu;
                     if (nv) {
                         mbar_expect_tx(&raw_full[r], nv * FRAME_BYTES);
                         #pragma unroll
@@ -237,9 +285,10 @@ __global__ void __launch_bounds__(G::THREADS, 1) conv_sw_kernel(ConvArgs args, O
                     } else {
                         mbar_arrive(&raw_full[r]);
                     }
+                    cur = nxt;
                 } else {
                     const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1u;
-                    if (!wait(&in_empty[s], ph ^ 1u)) break;
+                    if (!wait(&in_empty[s], ph ^ 1u, 1)) break;
                     mbar_expect_tx(&in_full[s], G::STAGE_BYTES);
                     const uint8_t* src = args.in + (size_t)bi * G::STAGE_BYTES;
                     uint8_t* dst = s_in + (size_t)s * G::STAGE_BYTES;
@@ -255,31 +304,35 @@ __global__ void __launch_bounds__(G::THREADS, 1) conv_sw_kernel(ConvArgs args, O
             constexpr uint32_t CT = G::NCONV * 32;
             for (uint32_t it = 0, bi = blockIdx.x; bi < n_batches && !*abort_flag; ++it, bi += gridDim.x) {
                 const uint32_t r = it % G::NRAW, ph_r = (it / G::NRAW) & 1u, s = it % G::NSTAGE, ph_s = (it / G::NSTAGE) & 1u;
-                if (!wait(&raw_full[r], ph_r) || !wait(&in_empty[s], ph_s ^ 1u)) break;
+                if (!wait(&raw_full[r], ph_r, 1) || !wait(&in_empty[s], ph_s ^ 1u, 2)) break;
                 const uint8_t* raw = s_raw + (size_t)r * G::RAW_BYTES;
                 uint8_t* dst = s_in + (size_t)s * G::STAGE_BYTES;
-                #pragma unroll 1
-                for (uint32_t h = 0; h < 4; ++h) {
-                    const bool present = __ldg(args.slot_frame + (size_t)bi * 4 + h) != 0xFFFFFFFFu;
-                    // work item = (row pair q = y/2, X = x/4): 8 pixels = channels (y&1, x&3) of plane 2h + (q&1), row (q/2)*21 + X
-                    #pragma unroll 7
-                    for (uint32_t idx = ct; idx < 42u * 21u; idx += CT) {
-                        const uint32_t q = idx / 21u, X = idx - q * 21u;
-                        uint32_t lo = 0u, hi = 0u;
-                        if (present) {
-                            const uint8_t* p = raw + h * FRAME_BYTES + q * (2u * FRAME_W) + X * 4u;
-                            lo = *reinterpret_cast<const uint32_t*>(p);
-                            hi = *reinterpret_cast<const uint32_t*>(p + FRAME_W);
-                        }
-                        const uint2 a = u8x4_to_bf16x4(lo), b = u8x4_to_bf16x4(hi);
-                        *reinterpret_cast<uint4*>(dst + (size_t)(2u * h + (q & 1u)) * G::PLANE_BYTES + ((q >> 1) * 21u + X) * 16u) = make_uint4(a.x, a.y, b.x, b.y);
+                uint32_t present = 0;
+                #pragma unroll
+                for (uint32_t h = 0; h < 4; ++h) present |= (uint32_t)(s_slot[r * 4 + h] != 0xFFFFFFFFu) << h;
+                // work item = (slot h, row pair q = y/2, X = x/4): 8 pixels = channels (y&1, x&3) of plane 2h + (q&1), row (q/2)*21 + X
+                #pragma unroll 7
+                for (uint32_t idx = ct; idx < 4u * 882u; idx += CT) {
+                    const uint32_t h = idx / 882u, rem = idx - h * 882u, q = rem / 21u, X = rem - q * 21u;
+                    uint32_t lo = 0u, hi = 0u;
+                    if ((present >> h) & 1u) {
+                        const uint8_t* p = raw + h * FRAME_BYTES + q * (2u * FRAME_W) + X * 4u;
+                        lo = *reinterpret_cast<const uint32_t*>(p);
+                        hi = *reinterpret_cast<const uint32_t*>(p + FRAME_W);
                     }
+                    const uint2 a = u8x4_to_bf16x4(lo), b = u8x4_to_bf16x4(hi);
+                    *reinterpret_cast<uint4*>(dst + (size_t)(2u * h + (q & 1u)) * G::PLANE_BYTES + ((q >> 1) * 21u + X) * 16u) = make_uint4(a.x, a.y, b.x, b.y);
                 }
                 fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&in_full[s]); mbar_arrive(&raw_empty[r]); }
             }
         }
+    }
+    if (prof_on && (warp == 0 || warp == 4 || warp == 5 || warp == 6)) {
+        const int role = warp == 0 ? 0 : (int)warp - 3;               // 0 epilogue, 1 MMA, 2 loader, 3 converter
+        pc[0] = (unsigned long long)(clock64() - t_begin);
+        for (int i = 0; i < 8; ++i) args.prof[role * 8 + i] = pc[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -310,6 +363,156 @@ __global__ void prep_conv3_planes_kernel(const float* __restrict__ kernel /*[3][
     const int e = i & 7, n = (i >> 3) % 64, k = (i / 512) * 8 + e;
     const int tap = k / 64, ci = k % 64, dy = tap / 3, dx = tap % 3;
     w[i] = __float2bfloat16_rn(kernel[((dx * 3 + dy) * 64 + ci) * 64 + n]);
+}
+
+
+// =========================================================================================================
+// Dense 3136 -> 512 (+ ReLU) as a bulk-copy fed tcgen05 GEMM. A (conv3's output, Keras Flatten order) and W live in global
+// memory already in the shared-memory operand layout, so one stage = one contiguous bulk copy per operand:
+//   A: [M tile = item / 128][K chunk j = k / 8 (392)][item % 128][8]      (written by conv3's epilogue, OutDensePlanes)
+//   W: [N half (2)][j (392)][n % 256][8]                                  (prep_dense_planes_kernel)
+// One CTA = one (M tile, N half): 128 items x 256 outputs, K = 3136 in 49 stages of 64 through a 4-deep ring;
+// tcgen05.mma M = 128, N = 256 runs at the tensor-pipe rate (128 cycles per K = 16, measured) when fed from shared memory.
+// =========================================================================================================
+struct DenseGeom {
+    static constexpr int K = 3136, N = 512, NT = 256, KSTAGE = 64, NSTAGE = 4;
+    static constexpr int PLANES = K / 8, STAGES_K = K / KSTAGE;             // 392 planes, 49 stages
+    static constexpr int A_STAGE = (KSTAGE / 8) * TILE_M * 16;               // 16 KB
+    static constexpr int B_STAGE = (KSTAGE / 8) * NT * 16;                   // 32 KB
+    static constexpr int A_TILE_BYTES = PLANES * TILE_M * 16;                // one M tile of A
+    static constexpr int THREADS = 192;
+    static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * (A_STAGE + B_STAGE) + NT * 4 + (2 * NSTAGE + 1) * 8 + 16;
+};
+struct OutDensePlanes {              // conv3 -> dense A operand, k = (ox*7 + oy)*64 + c
+    __nv_bfloat16* out;
+    __device__ __forceinline__ void store8(uint32_t item, uint32_t ox, uint32_t oy, uint32_t c0, uint4 v) const {
+        const uint32_t j = ((ox * 7u + oy) * 64u + c0) >> 3;
+        *reinterpret_cast<uint4*>(out + (((size_t)(item >> 7) * DenseGeom::PLANES + j) * TILE_M + (item & 127u)) * 8) = v;
+    }
+};
+
+__global__ void __launch_bounds__(DenseGeom::THREADS, 1) dense_tc_kernel(const uint8_t* __restrict__ a_planes, const uint8_t* __restrict__ w_planes,
+                                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out /*[items][512]*/,
+                                                                         uint32_t n_items, unsigned int* err) {
+    using G = DenseGeom;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* const s_a = smem;
+    uint8_t* const s_b = s_a + (size_t)G::NSTAGE * G::A_STAGE;
+    float* const s_bias = reinterpret_cast<float*>(s_b + (size_t)G::NSTAGE * G::B_STAGE);
+    uint64_t* const full = reinterpret_cast<uint64_t*>(s_bias + G::NT);
+    uint64_t* const empty = full + G::NSTAGE;
+    uint64_t* const acc_full = empty + G::NSTAGE;
+    uint32_t* const s_misc = reinterpret_cast<uint32_t*>(acc_full + 1);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t mtile = blockIdx.x, nhalf = blockIdx.y;
+
+    if (tid == 0) {
+        for (int i = 0; i < G::NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    for (uint32_t i = tid; i < (uint32_t)G::NT; i += G::THREADS) s_bias[i] = bias[nhalf * G::NT + i];
+    if (warp == 4) tmem_alloc(&s_misc[0], G::NT);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_misc[0];
+    auto wait = [&](uint64_t* bar, uint32_t parity) -> bool {
+        if (mbar_wait_bounded(bar, parity)) return true;
+        if (err) atomicExch(err, 3u);
+        return false;
+    };
+
+    if (warp < 4) {
+        // epilogue: row = item, 256 columns in 8 pieces of 32
+        if (wait(acc_full, 0)) {
+            tc_fence_after();
+            const uint32_t item = mtile * TILE_M + warp * 32u + lane;
+            #pragma unroll 1
+            for (int piece = 0; piece < G::NT / 32; ++piece) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((warp * 32u) << 16) + (uint32_t)(piece * 32), v);
+                if (item < n_items) {
+                    #pragma unroll
+                    for (int c = 0; c < 32; c += 8) {
+                        float f[8];
+                        #pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = fmaxf(__uint_as_float(v[c + i]) + s_bias[piece * 32 + c + i], 0.0f);
+                        *reinterpret_cast<uint4*>(out + (size_t)item * G::N + nhalf * G::NT + piece * 32 + c) =
+                            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        constexpr uint32_t IDESC = instr_desc_bf16(TILE_M, G::NT);
+        const uint32_t tmem_u = __reduce_max_sync(0xFFFFFFFFu, tmem_base);
+        for (uint32_t st = 0; st < (uint32_t)G::STAGES_K; ++st) {
+            const uint32_t s = st % G::NSTAGE, ph = (st / G::NSTAGE) & 1u;
+            if (!__all_sync(0xFFFFFFFFu, wait(&full[s], ph))) break;
+            tc_fence_after();
+            const uint32_t a_lo0 = ((smem_u32(s_a) + s * (uint32_t)G::A_STAGE) >> 4) | ((uint32_t)(TILE_M * 16 >> 4) << 16);
+            const uint32_t b_lo0 = ((smem_u32(s_b) + s * (uint32_t)G::B_STAGE) >> 4) | ((uint32_t)(G::NT * 16 >> 4) << 16);
+            #pragma unroll
+            for (int kk = 0; kk < G::KSTAGE / 16; ++kk)
+                tc_mma_bf16_elect_lo(tmem_u, a_lo0 + (uint32_t)(2 * kk) * (TILE_M * 16 >> 4), b_lo0 + (uint32_t)(2 * kk) * (G::NT * 16 >> 4), IDESC, (st > 0 || kk > 0) ? 1u : 0u);
+            tc_commit_elect(&empty[s]);
+        }
+        tc_commit_elect(acc_full);
+    } else if (lane == 0) {
+        const uint8_t* a_src = a_planes + (size_t)mtile * G::A_TILE_BYTES;
+        const uint8_t* b_src = w_planes + (size_t)nhalf * G::PLANES * G::NT * 16;
+        for (uint32_t st = 0; st < (uint32_t)G::STAGES_K; ++st) {
+            const uint32_t s = st % G::NSTAGE, ph = (st / G::NSTAGE) & 1u;
+            if (!wait(&empty[s], ph ^ 1u)) break;
+            mbar_expect_tx(&full[s], G::A_STAGE + G::B_STAGE);
+            bulk_load(s_a + (size_t)s * G::A_STAGE, a_src + (size_t)st * G::A_STAGE, G::A_STAGE, &full[s]);
+            bulk_load(s_b + (size_t)s * G::B_STAGE, b_src + (size_t)st * G::B_STAGE, G::B_STAGE / 2, &full[s]);
+            bulk_load(s_b + (size_t)s * G::B_STAGE + G::B_STAGE / 2, b_src + (size_t)st * G::B_STAGE + G::B_STAGE / 2, G::B_STAGE / 2, &full[s]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, G::NT);
+}
+
+// Keras dense kernel [3136][512] f32 -> bf16 [N half][j][n % 256][8]
+__global__ void prep_dense_planes_kernel(const float* __restrict__ kernel, __nv_bfloat16* __restrict__ w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3136 * 512) return;
+    const int e = i & 7, n256 = (i >> 3) & 255, j = (i >> 11) % 392, half = i / (392 * 2048);
+    w[i] = __float2bfloat16_rn(kernel[(size_t)(j * 8 + e) * 512 + half * 256 + n256]);
+}
+
+// Dense 512 -> 3 + argmax, one warp per row with 16-byte loads (replaces head_kernel's 2-byte loads)
+__global__ void __launch_bounds__(256) head_vec_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w /*[3][512]*/, const float* __restrict__ bias,
+                                                       float* __restrict__ q, uint8_t* __restrict__ action, float* __restrict__ max_q, uint32_t m_total) {
+    __shared__ float sw[3 * 512];
+    for (uint32_t i = threadIdx.x; i < 3u * 512u; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t row = wid; row < m_total; row += nw) {
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+        #pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            const uint32_t k0 = (uint32_t)part * 256u + lane * 8u;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(act + (size_t)row * 512 + k0));
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float a0 = __uint_as_float(u[i] << 16), a1 = __uint_as_float(u[i] & 0xFFFF0000u);
+                const uint32_t k = k0 + 2 * i;
+                s0 += a0 * sw[k] + a1 * sw[k + 1]; s1 += a0 * sw[512 + k] + a1 * sw[512 + k + 1]; s2 += a0 * sw[1024 + k] + a1 * sw[1024 + k + 1];
+            }
+        }
+        for (int o = 16; o; o >>= 1) { s0 += __shfl_down_sync(~0u, s0, o); s1 += __shfl_down_sync(~0u, s1, o); s2 += __shfl_down_sync(~0u, s2, o); }
+        if (lane == 0) {
+            s0 += bias[0]; s1 += bias[1]; s2 += bias[2];
+            if (q) { q[(size_t)row * 3] = s0; q[(size_t)row * 3 + 1] = s1; q[(size_t)row * 3 + 2] = s2; }
+            if (action) action[row] = (uint8_t)(s1 > s0 ? (s2 > s1 ? 2 : 1) : (s2 > s0 ? 2 : 0));     // first maximum, like tf.argmax
+            if (max_q) max_q[row] = fmaxf(s0, fmaxf(s1, s2));                                          // tf.reduce_max
+        }
+    }
 }
 
 }  // namespace qnet
