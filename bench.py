@@ -378,6 +378,76 @@ def measure_extras(q, torch, env, rb, dev, stream, peak):
     ms = e0.elapsed_time(e1) / iters
     out["actor_loop"] = {"env_steps_per_sec": n / (ms * 1e-3), "minibatches_per_sec": 0.25 / (ms * 1e-3), "us_per_iteration": ms * 1e3,
                          "note": "1 step launch per iteration (actions from a device-side random policy), sample+gather B=32 f32 every 4th step; no learner"}
+    out.update(measure_qnet(q, torch, env, rb, dev, stream, actor_iter_sample=(idx, st, nx, r, a, d)))
+    return out
+
+
+QNET_FLOP_PER_OBS = 2 * (400 * 32 * 256 + 81 * 64 * 512 + 49 * 64 * 576 + 512 * 3136 + 3 * 512)   # 84x84x4 -> conv 8/4, 4/2, 3/1 -> 512 -> 3
+
+
+def _tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    except Exception:
+        return 2250.0, "nominal dense bf16"
+
+
+def measure_qnet(q, torch, env, rb, dev, stream, actor_iter_sample):
+    """the Q-network forward on tcgen05 (predict_action for every env, straight from the frame ring) and the
+    closed actor loop of BASELINE configs[4]: greedy action from the network -> ONE env-step launch -> every 4th step a
+    minibatch sample + gather. Random-init weights of the reference architecture (no checkpoints here)."""
+    out = {}
+    rng = np.random.default_rng(7)
+    w = {}
+    for name, shape in q.QNET_SHAPES.items():
+        if name.endswith("kernel"):
+            lim = np.sqrt(6.0 / (int(np.prod(shape[:-1])) + shape[-1]))
+            w[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+        else:
+            w[name] = np.zeros(shape, dtype=np.float32)
+    net = q.QNetwork(env, w)
+    n = env.n_envs
+    acts = torch.empty((1, n), dtype=torch.uint8, device=dev)
+    qv = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    for _ in range(5):
+        net.forward_device(None, n, 0, qv.data_ptr(), acts.data_ptr(), None, stream)
+    torch.cuda.synchronize()
+    reps = 50
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        net.forward_device(None, n, 0, qv.data_ptr(), acts.data_ptr(), None, stream)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    peak, src = _tensor_peak()
+    tf = QNET_FLOP_PER_OBS * n / (ms * 1e-3) / 1e12
+    out["qnet_forward"] = {"observations_per_sec": n / (ms * 1e-3), "ms_per_forward": ms, "batch": n, "dtype": "bf16 operands, f32 accumulate (TMEM)",
+                           "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "peak_source": src,
+                                        "note": "convs are shifted-window implicit GEMMs with N = 32/64: bound by the 128 B/clk shared-memory operand fetch "
+                                                "(40/48 cycles per MMA measured, tools/microbench/mma_rate.cu), not by the tensor pipe"},
+                           "kernels_per_forward": 6}
+    idx, st, nx, r, a, d = actor_iter_sample
+    rew1 = torch.empty((1, n), dtype=torch.float32, device=dev); done1 = torch.empty((1, n), dtype=torch.uint8, device=dev)
+
+    def actor_iter(i):
+        net.forward_device(None, n, 0, None, acts.data_ptr(), None, stream)                      # predict_action for every env
+        env.step_device(acts.data_ptr(), 1, rew1.data_ptr(), done1.data_ptr(), stream)
+        if rb.should_sample(i, rb.len(), 32):
+            rb.sample_device(32, 1, i, idx.data_ptr(), stream)
+            rb.gather_device(idx.data_ptr(), 32, q.LAYOUT_F32_BXYH, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
+    for i in range(8):
+        actor_iter(i)
+    torch.cuda.synchronize()
+    iters = 200
+    e0.record()
+    for i in range(iters):
+        actor_iter(i)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    out["actor_loop_qnet"] = {"env_steps_per_sec": n / (ms * 1e-3), "minibatches_per_sec": 0.25 / (ms * 1e-3), "us_per_iteration": ms * 1e3,
+                              "note": "closed loop on the GPU: Q-network forward (greedy action for all %d envs) -> 1 env-step launch -> sample+gather B=32 f32 every 4th step; no learner" % n}
+    net.close()
     return out
 
 

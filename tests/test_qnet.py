@@ -97,3 +97,26 @@ def test_qnet_forward_matches_torch_fp32(qlb, O):
     q2, _, _ = net.forward()
     assert np.abs(q2 - _torch_reference(torch, w2, obs, quantise=True)).max() <= 1e-2 * scale
     net.close(); env.close()
+
+
+@pytest.mark.parametrize("n", [1, 7, 2000])
+def test_qnet_forward_batch_sizes(qlb, n):
+    """Edge batch sizes of the shifted-window pipeline: fewer items than one conv batch (conv2 packs 2, conv3 3, the dense
+    layer 128 items per tile) and enough items that every persistent CTA runs many iterations (mbarrier phases wrap, the
+    TMEM accumulator sets and the raw / plane stage rings are reused). Same tolerance as above: 1e-2 * max|Q| against the
+    fp32 reference quantised to bf16 at the same points."""
+    torch = pytest.importorskip("torch")
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=11, replay_capacity=n * 8)
+    rng = np.random.default_rng(n)
+    env.step_many(rng.integers(0, 3, size=(5, n), dtype=np.uint8))
+    w = _random_weights(qlb, 9)
+    net = qlb.QNetwork(env, w)
+    q, action, max_q = net.forward()
+    obs = env.obs(qlb.LAYOUT_F32_BXYH)
+    ref = _torch_reference(torch, w, obs, quantise=True)
+    scale = float(np.abs(ref).max())
+    assert np.abs(q - ref).max() <= 1e-2 * scale, np.abs(q - ref).max() / scale
+    assert np.array_equal(max_q, q.max(axis=1)) and np.array_equal(action, q.argmax(axis=1).astype(np.uint8))
+    q2, _, _ = net.forward()                                               # a second pass over reused buffers gives the same bits
+    assert np.array_equal(q, q2)
+    net.close(); env.close()

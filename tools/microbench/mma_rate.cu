@@ -65,7 +65,46 @@ static void run(uint32_t lbo, uint32_t shift, const char* what) {
     cudaFree(d);
 }
 
+// TMEM read rate: NW warps (one per lane quadrant) each issue tcgen05.ld 32x32b.x32 (4 KB per instruction) back to back
+__global__ void __launch_bounds__(128, 1) tmem_read_kernel(int nwarps, int iters, long long* out, float* sink) {
+    __shared__ uint32_t tmem_slot;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    uint32_t accs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t0 = clock64();
+    if ((int)warp < nwarps) {
+        for (int it = 0; it < iters; ++it) {
+            #pragma unroll
+            for (int c = 0; c < 512; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((warp * 32u) << 16) + (uint32_t)c, v);
+                #pragma unroll
+                for (int i = 0; i < 32; ++i) accs[i & 7] ^= v[i];
+            }
+        }
+    }
+    const long long t1 = clock64();
+    uint32_t acc = 0; for (int i = 0; i < 8; ++i) acc ^= accs[i];
+    if (acc == 0x12345678u) sink[tid] = (float)acc;
+    if (tid == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+static void run_tmem(int nwarps) {
+    long long* d; float* sink; cudaMalloc(&d, 16); cudaMalloc(&sink, 4096);
+    const int iters = 50;
+    for (int rep = 0; rep < 2; ++rep) tmem_read_kernel<<<148, 128>>>(nwarps, iters, d, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    const double per = (double)h / (iters * 16);
+    printf("tmem read, %d warps: %6.1f cyc per 32x32b.x32 ld (+32 LOP) per warp -> %.0f B/clk per SM  %s\n", nwarps, per, nwarps * 4096.0 / per, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    cudaFree(d); cudaFree(sink);
+}
+
 int main() {
+    run_tmem(1); run_tmem(2); run_tmem(4);
     run<32, 0>(7056, 1, "conv1-like"); run<32, 0>(7168, 0, "aligned"); run<32, 0>(7168, 8, "8-row shift"); run<32, 1>(7056, 1, "conv1-like, single thread");
     run<64, 0>(3200, 1, "conv2-like"); run<64, 0>(3200, 0, "aligned"); run<64, 0>(3888, 1, "conv3-like"); run<64, 1>(3200, 1, "single thread");
     run<128, 0>(3200, 1, ""); run<128, 0>(3200, 0, "aligned"); run<256, 0>(3200, 1, ""); run<256, 0>(3200, 0, "aligned");
