@@ -730,6 +730,20 @@ static cudaError_t launch_gemm_tc(const Loader& ld, const __nv_bfloat16* w, cons
     return cudaGetLastError();
 }
 
+// launch with programmatic stream serialization: the kernel's prologue may overlap the tail of its predecessor in the stream
+// (every kernel launched this way calls griddepcontrol.wait before it touches anything the predecessor wrote)
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    static const bool enabled = getenv("QLC_QNET_PDL") ? atoi(getenv("QLC_QNET_PDL")) != 0 : true;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = enabled ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <class G, class Out>
 static cudaError_t launch_conv_sw(const qnet::ConvArgs& a, const Out& o, cudaStream_t s) {
     auto kern = qnet::conv_sw_kernel<G, Out>;
@@ -740,8 +754,7 @@ static cudaError_t launch_conv_sw(const qnet::ConvArgs& a, const Out& o, cudaStr
         int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const uint32_t n_batches = (a.n_items + G::B - 1) / G::B;
-    kern<<<n_batches < (uint32_t)sms ? n_batches : (uint32_t)sms, G::THREADS, G::SMEM_BYTES, s>>>(a, o);      // persistent: one CTA per SM
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3(n_batches < (uint32_t)sms ? n_batches : (uint32_t)sms), dim3(G::THREADS), G::SMEM_BYTES, s, a, o);      // persistent: one CTA per SM
 }
 
 extern "C" {
@@ -850,8 +863,7 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
     }
     GatherParams g{}; fill_gather(env, g);
     g.indices = idx_dev; g.n_items = n;
-    qnet::qnet_locate_kernel<<<(n + 127) / 128, 128, 0, s>>>(g, which ? 1u : 0u, q->slot_frame);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_pdl(qnet::qnet_locate_kernel, dim3((n + 127) / 128), dim3(128), 0, s, g, which ? 1u : 0u, q->slot_frame));
     cudaError_t e;
     const int impl = q->impl;
     if (impl >= 1) {
@@ -881,10 +893,10 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
     if (impl >= 4) {
         static bool attr_set = false;
         if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(qnet::dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qnet::DenseGeom::SMEM_BYTES)); attr_set = true; }
-        qnet::dense_tc_kernel<<<dim3((n + 127) / 128, 2), qnet::DenseGeom::THREADS, qnet::DenseGeom::SMEM_BYTES, s>>>((const uint8_t*)q->a3p, (const uint8_t*)q->w4p, q->b4, q->a4, n, q->err);
-        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(launch_pdl(qnet::dense_tc_kernel, dim3((n + 127) / 128, 2), dim3(qnet::DenseGeom::THREADS), qnet::DenseGeom::SMEM_BYTES, s, (const uint8_t*)q->a3p, (const uint8_t*)q->w4p,
+                            (const float*)q->b4, q->a4, n, q->err));
         const uint32_t hb = (n + 7) / 8;
-        qnet::head_vec_kernel<<<hb < 592u ? hb : 592u, 256, 0, s>>>(q->a4, q->w5, q->b5, q_dev, action_dev, max_q_dev, n);
+        CUDA_TRY(launch_pdl(qnet::head_vec_kernel, dim3(hb < 592u ? hb : 592u), dim3(256), 0, s, (const __nv_bfloat16*)q->a4, (const float*)q->w5, (const float*)q->b5, q_dev, action_dev, max_q_dev, n));
     } else {
         qnet::LoadRowMajorBf16 l4{q->a3, 3136u};
         e = launch_gemm_tc<128>(l4, q->w4, q->b4, q->a4, n, 3136u, 512u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("dense1: ") + cudaGetErrorString(e));

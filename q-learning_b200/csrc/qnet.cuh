@@ -125,6 +125,8 @@ struct LoadConv1FromRing {           // conv1 straight from the u8 frame ring: K
 // which frame of the ring holds ring-slot h of item b's state (obs mode: indices == NULL, item = env at the current time;
 // replay mode: logical transition index, which = 0 state / 1 next) — same rules as the gather kernels (locate()).
 __global__ void qnet_locate_kernel(GatherParams g, uint32_t which, uint32_t* slot_frame) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // programmatic dependent launch (see qnet_conv.cuh)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= g.n_items) return;
     uint64_t T; uint32_t e, k, rec;

@@ -64,6 +64,12 @@ __device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with programmaticStreamSerializationAllowed may start while its
+// predecessor in the stream is still draining; everything before pdl_wait() (barrier init, TMEM allocation, the weight copy)
+// overlaps that tail, pdl_wait() returns once the predecessor has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- layer geometry ---------------------------------------------------------------------------------------
 // ROWS = pixels of one item's (space-to-depth) input, WIN its width; PL = 16-byte channel planes per tap (channels / 8);
 // TY x TX taps; OH x OW valid outputs; N output channels; B items per batch (their rows are concatenated in a plane).
@@ -178,6 +184,11 @@ __global__ void __launch_bounds__(G::THREADS, 1) conv_sw_kernel(ConvArgs args, O
     tc_fence_after();
     const uint32_t tmem_base = s_misc[0];
     volatile uint32_t* const abort_flag = &s_misc[1];
+    if (warp == 5 && lane == 0) {                        // weights are not produced by the previous kernel: fetch them during its tail
+        mbar_expect_tx(w_full, G::W_BYTES);
+        for (int off = 0; off < G::W_BYTES; off += 16384) bulk_load(s_w + off, args.w + off, (uint32_t)(G::W_BYTES - off < 16384 ? G::W_BYTES - off : 16384), w_full);
+    }
+    pdl_wait();
     // a wait that never hangs the GPU: on time-out raise the error flag and make every role leave its loop
     const bool prof_on = args.prof != nullptr && blockIdx.x == 0 && lane == 0;
     unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -262,8 +273,6 @@ __global__ void __launch_bounds__(G::THREADS, 1) conv_sw_kernel(ConvArgs args, O
     } else if (warp == 5) {
         // ================= bulk-copy issue =================
         if (lane == 0) {
-            mbar_expect_tx(w_full, G::W_BYTES);
-            for (int off = 0; off < G::W_BYTES; off += 16384) bulk_load(s_w + off, args.w + off, (uint32_t)(G::W_BYTES - off < 16384 ? G::W_BYTES - off : 16384), w_full);
             uint4 cur = make_uint4(0u, 0u, 0u, 0u);
             if constexpr (G::FROM_RING) { if (blockIdx.x < n_batches) cur = __ldg(reinterpret_cast<const uint4*>(args.slot_frame) + blockIdx.x); }
             for (uint32_t it = 0, bi = blockIdx.x; bi < n_batches && !*abort_flag; ++it, bi += gridDim.x) {
@@ -296,6 +305,7 @@ __global__ void __launch_bounds__(G::THREADS, 1) conv_sw_kernel(ConvArgs args, O
                     for (int off = 0; off < G::STAGE_BYTES; off += CH) bulk_load(dst + off, src + off, (uint32_t)(G::STAGE_BYTES - off < CH ? G::STAGE_BYTES - off : CH), &in_full[s]);
                 }
             }
+            pdl_launch_dependents();                     // this CTA's last input is on its way: the next kernel may start its prologue
         }
     } else {
         // ================= conv1: u8 ring frames -> bf16 planes, space-to-depth by 4 =================
@@ -417,6 +427,8 @@ __global__ void __launch_bounds__(DenseGeom::THREADS, 1) dense_tc_kernel(const u
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_misc[0];
+    pdl_launch_dependents();
+    pdl_wait();
     auto wait = [&](uint64_t* bar, uint32_t parity) -> bool {
         if (mbar_wait_bounded(bar, parity)) return true;
         if (err) atomicExch(err, 3u);
@@ -490,6 +502,8 @@ __global__ void __launch_bounds__(256) head_vec_kernel(const __nv_bfloat16* __re
     __shared__ float sw[3 * 512];
     for (uint32_t i = threadIdx.x; i < 3u * 512u; i += blockDim.x) sw[i] = w[i];
     __syncthreads();
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t lane = threadIdx.x & 31u, wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
     for (uint32_t row = wid; row < m_total; row += nw) {
         float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;

@@ -18,7 +18,8 @@ METRICS = [
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
     "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor", "launch__occupancy_limit_shared_mem",
     "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
-    "smsp__inst_executed.sum", "sm__inst_executed_pipe_uniform.sum",
+    "smsp__inst_executed.sum", "sm__inst_executed_pipe_uniform.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
 ]
 UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "Tbyte": 1e12}
 
@@ -39,7 +40,7 @@ def launches(tag, path):
         except ValueError:
             pass
     tot = sum(sum(v) for v in agg.values())
-    out = ["# %s — launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, first %d launches of `python bench.py --steps 5 --warmup 3 --no-cpu-baseline`)" % (tag, sum(len(v) for v in agg.values())),
+    out = ["# %s — launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, first %d launches of `%s`)" % (tag, sum(len(v) for v in agg.values()), os.environ.get("PROFILE_CMD", "python bench.py --steps 5 --warmup 3 --no-cpu-baseline")),
            "", "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.", "",
            "| kernel | launches | total us | avg us | share |", "|---|---:|---:|---:|---:|"]
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
@@ -74,12 +75,13 @@ def kernels(tag, reps):
             per_kernel.setdefault(name, []).append(d)
     for name, ds in per_kernel.items():
         out += ["## `%s` (%d captured launches, source: %s)" % (name, len(ds), ", ".join(os.path.basename(r) for r in reps)), "",
-                "| launch | grid x block | duration us | dram read MB | dram write MB | dram %% of peak | SM %% | warps active %% | regs |", "|---|---|---:|---:|---:|---:|---:|---:|---:|"]
+                "| launch | grid x block | duration us | dram read MB | dram write MB | dram %% of peak | SM %% | warps active %% | regs | tensor pipe active %% |", "|---|---|---:|---:|---:|---:|---:|---:|---:|---:|"]
         for i, d in enumerate(ds):
-            out.append("| %d | %s x %s | %.1f | %.2f | %.2f | %.1f | %.1f | %.1f | %d |" % (
+            out.append("| %d | %s x %s | %.1f | %.2f | %.2f | %.1f | %.1f | %.1f | %d | %.1f |" % (
                 i, d.get("grid", ""), d.get("block", ""), d.get("gpu__time_duration.sum", 0), d.get("dram__bytes_read.sum", 0) / 1e6, d.get("dram__bytes_write.sum", 0) / 1e6,
                 d.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", 0), d.get("sm__throughput.avg.pct_of_peak_sustained_elapsed", 0),
-                d.get("sm__warps_active.avg.pct_of_peak_sustained_active", 0), int(d.get("launch__registers_per_thread", 0))))
+                d.get("sm__warps_active.avg.pct_of_peak_sustained_active", 0), int(d.get("launch__registers_per_thread", 0)),
+                d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0)))
         out.append("")
         # traffic per launch: median over the largest-grid launches of this kernel
         big = max(ds, key=lambda d: d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0))
