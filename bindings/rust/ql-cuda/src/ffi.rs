@@ -114,6 +114,8 @@ extern "C" {
     pub fn qlc_env_reset(env: *mut qlc_env, mask_host: *const u8, dir_x_host: *const f32) -> i32;
     pub fn qlc_env_step(env: *mut qlc_env, actions_dev: *const u8, n_steps: u32, reward_dev: *mut f32, done_dev: *mut u8, stream: *mut c_void) -> i32;
     pub fn qlc_env_step_host(env: *mut qlc_env, actions_host: *const u8, n_steps: u32, reward_host: *mut f32, done_host: *mut u8) -> i32;
+    pub fn qlc_env_step_host_submit(env: *mut qlc_env, actions_host: *const u8, n_steps: u32, reward_host: *mut f32, done_host: *mut u8) -> i32;
+    pub fn qlc_env_step_host_wait(env: *mut qlc_env, max_pending: u32) -> i32;
     pub fn qlc_env_obs(env: *mut qlc_env, layout: i32, out_dev: *mut c_void, stream: *mut c_void) -> i32;
     pub fn qlc_env_obs_host(env: *mut qlc_env, layout: i32, out_host: *mut c_void) -> i32;
     pub fn qlc_env_state_view(env: *mut qlc_env, out: *mut qlc_state_view) -> i32;

@@ -132,6 +132,14 @@ int32_t qlc_env_reset(qlc_env* env, const uint8_t* mask_host, const float* dir_x
 int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps, float* reward_dev, uint8_t* done_dev, void* stream);
 /* same with HOST buffers: validates actions (QLC_ERR_OUT_OF_RANGE), H2D, step, D2H, synchronises. */
 int32_t qlc_env_step_host(qlc_env* env, const uint8_t* actions_host, uint32_t n_steps, float* reward_host, uint8_t* done_host);
+/* Pipelined form for action streams that do not depend on the previous result (the learner's random-policy phase
+ * self_driving_tf_q_learner.rs:153-160, replayed traces): submit validates, queues the copies and the launch and returns
+ * (it blocks only while 8 steps are already in flight); qlc_env_step_host_wait blocks until at most `max_pending` (0..7) of the
+ * submitted steps are still running - the reward / done of all earlier ones are then in the caller's buffers. All three
+ * buffers must be page-locked (qlc_host_alloc, else QLC_ERR_INVALID_ARG) and stay untouched until their step has been waited
+ * for; steps execute in submission order. */
+int32_t qlc_env_step_host_submit(qlc_env* env, const uint8_t* actions_host, uint32_t n_steps, float* reward_host, uint8_t* done_host);
+int32_t qlc_env_step_host_wait(qlc_env* env, uint32_t max_pending);
 /* state(): current observation stacks of all envs, [n_envs] x layout, into a device / host buffer */
 int32_t qlc_env_obs(qlc_env* env, int32_t layout, void* out_dev, void* stream);
 int32_t qlc_env_obs_host(qlc_env* env, int32_t layout, void* out_host);

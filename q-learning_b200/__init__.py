@@ -40,7 +40,7 @@ ENVERR_WALL_DISTANCE, ENVERR_APPROX_RANGE, ENVERR_RECURSION, ENVERR_BISECTION, E
 ABI_SYMBOLS = [
     "qlc_version", "qlc_last_error_string", "qlc_device_count", "qlc_env_create", "qlc_env_destroy", "qlc_sync",
     "qlc_host_alloc", "qlc_host_free",
-    "qlc_env_reset", "qlc_env_step", "qlc_env_step_host", "qlc_env_obs", "qlc_env_obs_host", "qlc_env_state_view",
+    "qlc_env_reset", "qlc_env_step", "qlc_env_step_host", "qlc_env_step_host_submit", "qlc_env_step_host_wait", "qlc_env_obs", "qlc_env_obs_host", "qlc_env_state_view",
     "qlc_env_read_state", "qlc_env_goal_mean", "qlc_env_time", "qlc_env_error_flags",
     "qlc_replay_len", "qlc_replay_capacity", "qlc_replay_sample", "qlc_replay_gather", "qlc_replay_sample_host",
     "qlc_replay_gather_host", "qlc_replay_action_counts",
@@ -125,6 +125,8 @@ def load_library(build_if_missing=True):
         "qlc_env_reset": (i32, [vp, vp, vp]),
         "qlc_env_step": (i32, [vp, vp, u32, vp, vp, vp]),
         "qlc_env_step_host": (i32, [vp, vp, u32, vp, vp]),
+        "qlc_env_step_host_submit": (i32, [vp, vp, u32, vp, vp]),
+        "qlc_env_step_host_wait": (i32, [vp, u32]),
         "qlc_env_obs": (i32, [vp, i32, vp, vp]),
         "qlc_env_obs_host": (i32, [vp, i32, vp]),
         "qlc_env_state_view": (i32, [vp, C.POINTER(QlcStateView)]),
@@ -320,6 +322,21 @@ class BreakoutEnvironment:
             done = np.empty((k, self.n_envs), dtype=np.uint8)
         _check(self._L.qlc_env_step_host(self._h, _np_ptr(a), k, _np_ptr(reward), _np_ptr(done)))
         return reward, done
+
+    def step_many_submit(self, actions, reward, done):
+        """Pipelined step_many for action streams that do not depend on the previous result: queues the step and returns.
+        All three arrays must be page-locked (PinnedArray(...).array) and stay untouched until step_many_wait()."""
+        k = actions.shape[0]
+        if actions.dtype != np.uint8 or actions.ndim != 2 or actions.shape[1] != self.n_envs or not actions.flags.c_contiguous:
+            raise QlError("actions must be C-contiguous u8 [n_steps][n_envs]")
+        if reward.shape != (k, self.n_envs) or reward.dtype != np.float32 or done.shape != (k, self.n_envs) or done.dtype != np.uint8 \
+                or not reward.flags.c_contiguous or not done.flags.c_contiguous:
+            raise QlError("out arrays must be C-contiguous f32 / u8 [n_steps][n_envs]")
+        _check(self._L.qlc_env_step_host_submit(self._h, _np_ptr(actions), k, _np_ptr(reward), _np_ptr(done)))
+
+    def step_many_wait(self, max_pending=0):
+        """Blocks until at most `max_pending` of the submitted steps are still running (0 = all results are in)."""
+        _check(self._L.qlc_env_step_host_wait(self._h, max_pending))
 
     def step_device(self, actions_ptr, n_steps, reward_ptr=None, done_ptr=None, stream=None):
         """Asynchronous step on device buffers (raw device pointers, e.g. torch tensor .data_ptr())."""

@@ -38,6 +38,8 @@ struct qlc_env {
     unsigned int* spin_error = nullptr;
     uint32_t launch_serial = 0;
     int chunk_override = -1;                   // QLC_CHUNK: force the chunk length (0 = off)
+    uint64_t submit_seq = 0;                   // qlc_env_step_host_submit calls so far
+    cudaEvent_t submit_done[8] = {};           // completion of submit k in slot k % 8 (created on first use)
     int zero_copy = 1;                         // QLC_ZERO_COPY=0: always stage page-locked outputs through a D2H copy
     uint32_t time_slots = 0;                   // frame/record ring length in time steps (= t_cap + 4)
     uint32_t t_cap = 0;                        // replay capacity in time steps
@@ -184,6 +186,7 @@ int32_t qlc_env_destroy(qlc_env* env) {
     for (void* p : env->allocs) cudaFree(p);
     if (env->pin) cudaFreeHost(env->pin);
     if (env->dev_stage) cudaFree(env->dev_stage);
+    for (cudaEvent_t ev : env->submit_done) if (ev) cudaEventDestroy(ev);
     if (env->own_stream) cudaStreamDestroy(env->own_stream);
     delete env;
     return QLC_OK;
@@ -305,7 +308,7 @@ static bool is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-int32_t qlc_env_step_host(qlc_env* env, const uint8_t* actions_host, uint32_t n_steps, float* reward_host, uint8_t* done_host) {
+static int32_t step_host_impl(qlc_env* env, const uint8_t* actions_host, uint32_t n_steps, float* reward_host, uint8_t* done_host, bool wait) {
     if (!env || !actions_host) return fail(QLC_ERR_INVALID_ARG, "env/actions is null");
     if (n_steps == 0) return QLC_OK;
     int32_t rc = set_device(env); if (rc) return rc;
@@ -313,12 +316,16 @@ int32_t qlc_env_step_host(qlc_env* env, const uint8_t* actions_host, uint32_t n_
     uint8_t bad = 0;
     for (size_t i = 0; i < n; ++i) bad |= (uint8_t)(actions_host[i] >= QLC_ACTION_SPACE);
     if (bad) return fail(QLC_ERR_OUT_OF_RANGE, "value out of range");   // QlError, breakout_environment.rs:117
-    const size_t off_r = (n + 15) & ~(size_t)15, off_d = off_r + n * 4, total = off_d + n;
-    rc = ensure_dev_stage(env, total); if (rc) return rc;
-    uint8_t* dev = (uint8_t*)env->dev_stage;
-    cudaStream_t s = env->own_stream;
     // page-locked caller buffers (qlc_host_alloc / cudaHostRegister) are used in place; pageable ones are staged
     const bool pin_a = is_pinned(actions_host), pin_r = !reward_host || is_pinned(reward_host), pin_d = !done_host || is_pinned(done_host);
+    if (!wait && !(pin_a && pin_r && pin_d)) return fail(QLC_ERR_INVALID_ARG, "qlc_env_step_host_submit needs page-locked buffers (qlc_host_alloc)");
+    // the asynchronous form keeps several steps in flight: each gets its own slice of the device staging ring
+    const size_t off_r = (n + 15) & ~(size_t)15, off_d = off_r + n * 4, total = (off_d + n + 255) & ~(size_t)255;
+    const uint32_t slot = wait ? 0u : (uint32_t)(env->submit_seq % 2u);
+    if (!wait && env->submit_seq >= 8) CUDA_TRY(cudaEventSynchronize(env->submit_done[env->submit_seq % 8]));   // at most 8 steps in flight
+    rc = ensure_dev_stage(env, 2 * total); if (rc) return rc;
+    uint8_t* dev = (uint8_t*)env->dev_stage + slot * total;
+    cudaStream_t s = env->own_stream;
     uint8_t* pin = nullptr;
     if (!(pin_a && pin_r && pin_d)) { rc = ensure_pin(env, total); if (rc) return rc; pin = (uint8_t*)env->pin; }
     const uint8_t* actions_dev = dev;
@@ -336,9 +343,31 @@ int32_t qlc_env_step_host(qlc_env* env, const uint8_t* actions_host, uint32_t n_
     rc = qlc_env_step(env, actions_dev, n_steps, zc_r ? reward_host : (float*)(dev + off_r), zc_d ? done_host : dev + off_d, s); if (rc) return rc;
     if (reward_host && !zc_r) CUDA_TRY(cudaMemcpyAsync(pin_r ? (void*)reward_host : (void*)(pin + off_r), dev + off_r, n * 4, cudaMemcpyDeviceToHost, s));
     if (done_host && !zc_d) CUDA_TRY(cudaMemcpyAsync(pin_d ? (void*)done_host : (void*)(pin + off_d), dev + off_d, n, cudaMemcpyDeviceToHost, s));
+    if (!wait) {
+        cudaEvent_t& ev = env->submit_done[env->submit_seq % 8];
+        if (!ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(ev, s));
+        ++env->submit_seq;
+        return QLC_OK;
+    }
     CUDA_TRY(cudaStreamSynchronize(s));
     if (reward_host && !pin_r) memcpy(reward_host, pin + off_r, n * 4);
     if (done_host && !pin_d) memcpy(done_host, pin + off_d, n);
+    return QLC_OK;
+}
+
+int32_t qlc_env_step_host(qlc_env* env, const uint8_t* actions_host, uint32_t n_steps, float* reward_host, uint8_t* done_host) {
+    return step_host_impl(env, actions_host, n_steps, reward_host, done_host, true);
+}
+int32_t qlc_env_step_host_submit(qlc_env* env, const uint8_t* actions_host, uint32_t n_steps, float* reward_host, uint8_t* done_host) {
+    return step_host_impl(env, actions_host, n_steps, reward_host, done_host, false);
+}
+int32_t qlc_env_step_host_wait(qlc_env* env, uint32_t max_pending) {
+    if (!env) return fail(QLC_ERR_INVALID_ARG, "env is null");
+    if (max_pending >= 8) return fail(QLC_ERR_INVALID_ARG, "max_pending must be < 8");
+    int32_t rc = set_device(env); if (rc) return rc;
+    if (env->submit_seq <= max_pending) return QLC_OK;
+    CUDA_TRY(cudaEventSynchronize(env->submit_done[(env->submit_seq - 1 - max_pending) % 8]));   // in-order stream: older submits are done too
     return QLC_OK;
 }
 

@@ -582,3 +582,34 @@ def test_shard_of_65536_envs(qlb, O):
     assert np.array_equal(g.state_next[ok], rb.get_many(nxt[ok], qlb.LAYOUT_U8_BHYX).state)
     assert env.error_flags() & ~qlb.ENVERR_DEGENERATE == 0
     env.close()
+
+
+def test_pipelined_host_steps_equal_synchronous_ones(qlb, O):
+    """qlc_env_step_host_submit / _wait (several host-buffer steps in flight, page-locked buffers) produce the bytes of the
+    synchronous qlc_env_step_host and of the oracle; pageable buffers are refused."""
+    n, k, rounds, seed = 96, 7, 6, 31
+    acts = np.random.default_rng(seed).integers(0, 3, size=(rounds, k, n), dtype=np.uint8)
+    env_a = qlb.BreakoutEnvironment(n_envs=n, seed=seed, replay_capacity=n * 64)
+    env_s = qlb.BreakoutEnvironment(n_envs=n, seed=seed, replay_capacity=n * 64)
+    ora = O.VecEnv(n, seed=seed, replay_capacity=n * 64)
+    pa = [qlb.PinnedArray((k, n), np.uint8) for _ in range(rounds)]
+    pr = [qlb.PinnedArray((k, n), np.float32) for _ in range(rounds)]
+    pd = [qlb.PinnedArray((k, n), np.uint8) for _ in range(rounds)]
+    for i in range(rounds):
+        pa[i].array[:] = acts[i]
+        env_a.step_many_submit(pa[i].array, pr[i].array, pd[i].array)      # all rounds queued before the first wait
+    env_a.step_many_wait()
+    for i in range(rounds):
+        r, d = env_s.step_many(acts[i])
+        assert np.array_equal(pr[i].array, r) and np.array_equal(pd[i].array, d), "round %d" % i
+        for s in range(k):
+            ro, do = ora.step(acts[i, s])
+            assert np.array_equal(ro, r[s]) and np.array_equal(do, d[s])
+    _assert_state_equal(env_a.read_state(), env_s.read_state(), "pipelined vs synchronous")
+    assert np.array_equal(env_a.obs(qlb.LAYOUT_U8_BHYX), ora.obs_u8())
+    with pytest.raises(qlb.QlError):
+        env_a.step_many_submit(acts[0].copy(), np.empty((k, n), np.float32), np.empty((k, n), np.uint8))   # pageable
+    bad = qlb.PinnedArray((k, n), np.uint8); bad.array[:] = 0; bad.array[2, 5] = 3
+    with pytest.raises(qlb.QlError, match="value out of range"):
+        env_a.step_many_submit(bad.array, pr[0].array, pd[0].array)
+    env_a.close(); env_s.close()
