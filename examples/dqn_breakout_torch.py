@@ -69,7 +69,7 @@ class TorchDQNModel:
         self.net.load_state_dict(other.net.state_dict())
 
 
-def run(n_envs=1024, iterations=200, batch=32, minibatches_per_call=None, seed=0, device=0, quiet=False):
+def run(n_envs=1024, iterations=200, batch=32, minibatches_per_call=None, seed=0, device=0, quiet=False, tensor_core_actor=False, actor_sync_every=10):
     """Device-resident variant of learner.SelfDrivingQLearner.learn_iteration: same rules, tensors never leave the GPU."""
     dev = torch.device("cuda", device)
     torch.cuda.set_device(dev)
@@ -79,6 +79,9 @@ def run(n_envs=1024, iterations=200, batch=32, minibatches_per_call=None, seed=0
     rb = q.ReplayBuffer(env)
     model, target = TorchDQNModel(dev), TorchDQNModel(dev)
     target.load_from(model)
+    # optional: action selection on the library's tcgen05 Q-network, reading the frame ring directly (no f32 observation
+    # is materialised); its weights follow the torch model every `actor_sync_every` iterations
+    actor = tio.TensorCoreActor(env, model.net) if tensor_core_actor else None
     due_per_iter = n_envs // p.update_after_actions               # one minibatch per 4 env-steps (self_driving_tf_q_learner.rs:181)
     nb = minibatches_per_call or due_per_iter
     sampler = tio.DeviceSampler(rb, batch, nb, q.LAYOUT_F32_BXYH)
@@ -95,8 +98,14 @@ def run(n_envs=1024, iterations=200, batch=32, minibatches_per_call=None, seed=0
         random_mask = (eps > u) | (step_count + 1 + torch.arange(n_envs, device=dev) < p.epsilon_pure_random_steps)
         actions = a_rand
         if not bool(random_mask.all()):
-            obs = tio.observe(env, q.LAYOUT_F32_BXYH, obs)
-            actions = torch.where(random_mask, a_rand[0], model.predict_action(obs)).unsqueeze(0).contiguous()
+            if actor is not None:
+                if it % actor_sync_every == 0:
+                    actor.sync(model.net)
+                greedy = actor.predict_action()[0]
+            else:
+                obs = tio.observe(env, q.LAYOUT_F32_BXYH, obs)
+                greedy = model.predict_action(obs)
+            actions = torch.where(random_mask, a_rand[0], greedy).unsqueeze(0).contiguous()
         epsilon = max(epsilon - n_envs * delta, p.epsilon_min)
         reward, done = tio.step(env, actions)
         returns += reward[0]
@@ -121,6 +130,8 @@ def run(n_envs=1024, iterations=200, batch=32, minibatches_per_call=None, seed=0
     stats = env.stats()
     out = {"env_steps": step_count, "seconds": time.time() - t0, "episodes": int(stats["episodes"]), "train_calls": len(model.losses),
            "last_loss": float(model.losses[-1]) if model.losses else None, "epsilon": epsilon, "error_flags": env.error_flags()}
+    if actor is not None:
+        actor.close()
     env.close()
     return out
 
@@ -130,5 +141,6 @@ if __name__ == "__main__":
     ap.add_argument("--envs", type=int, default=1024)
     ap.add_argument("--iterations", type=int, default=200)
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--tensor-core-actor", action="store_true", help="greedy actions from the library's tcgen05 Q-network (weights synced from the torch model)")
     args = ap.parse_args()
-    print(run(args.envs, args.iterations, args.batch))
+    print(run(args.envs, args.iterations, args.batch, tensor_core_actor=args.tensor_core_actor))

@@ -63,3 +63,57 @@ def step(env, actions, reward=None, done=None):
         done = torch.empty((k, env.n_envs), dtype=torch.uint8, device=actions.device)
     env.step_device(actions.data_ptr(), k, reward.data_ptr(), done.data_ptr(), _stream())
     return reward, done
+
+
+def keras_weights_from_torch(net):
+    """Weights of a torch network with the reference architecture (create_ql_model_breakout_84x84x4_3_32.py:17-33; convs in
+    NCHW with H = x, W = y as in examples/dqn_breakout_torch.py) in the Keras layouts `QNetwork` takes (QNET_SHAPES)."""
+    convs = [m for m in net.modules() if isinstance(m, torch.nn.Conv2d)]
+    dense = [m for m in net.modules() if isinstance(m, torch.nn.Linear)]
+    if len(convs) != 3 or len(dense) != 2:
+        raise QlError("expected 3 Conv2d and 2 Linear layers")
+    w = {}
+    for i, c in enumerate(convs, 1):
+        w["conv%d_kernel" % i] = c.weight.detach().permute(2, 3, 1, 0).contiguous().float().cpu().numpy()      # [cout][cin][kh][kw] -> [kh][kw][cin][cout]
+        w["conv%d_bias" % i] = c.bias.detach().float().cpu().numpy()
+    d1 = dense[0].weight.detach().float()                                                                      # [512][c*49 + x*7 + y]
+    w["dense1_kernel"] = d1.view(512, 64, 7, 7).permute(2, 3, 1, 0).reshape(3136, 512).contiguous().cpu().numpy()   # Keras Flatten: (x*7 + y)*64 + c
+    w["dense1_bias"] = dense[0].bias.detach().float().cpu().numpy()
+    w["dense2_kernel"] = dense[1].weight.detach().float().t().contiguous().cpu().numpy()
+    w["dense2_bias"] = dense[1].bias.detach().float().cpu().numpy()
+    return w
+
+
+class TensorCoreActor:
+    """The inference half of DeepQLearningModel (ml_model/model.rs:29-77) on the library's tcgen05 Q-network, fed straight
+    from the frame ring: `predict_action()` for every env without materialising the f32 observation, and
+    `max_future_reward(indices)` for sampled transitions without gathering their state_next. Training stays with the
+    caller's torch model; `sync(net)` copies its weights over (bf16 operands, f32 accumulation)."""
+
+    def __init__(self, env, net):
+        from . import QNetwork
+        self.env = env
+        self.qnet = QNetwork(env, keras_weights_from_torch(net))
+        dev = torch.device("cuda", env.device)
+        self.actions = torch.empty((1, env.n_envs), dtype=torch.uint8, device=dev)
+        self.q = torch.empty((env.n_envs, 3), dtype=torch.float32, device=dev)
+
+    def sync(self, net):
+        self.qnet.set_weights(keras_weights_from_torch(net))
+
+    def predict_action(self, states=None, want_q=False):
+        """Greedy action of every env as a CUDA u8 tensor [1][n_envs] (the shape `step` takes); `states` is ignored — the
+        network reads the frames where the step kernel wrote them."""
+        self.qnet.forward_device(None, self.env.n_envs, 0, self.q.data_ptr() if want_q else None, self.actions.data_ptr(), None, _stream())
+        return self.actions
+
+    def max_future_reward(self, indices, out=None):
+        """batch_predict_max_future_reward for the state_next of the replay transitions `indices` (CUDA int32 / uint32 tensor)."""
+        n = indices.numel()
+        if out is None:
+            out = torch.empty((n,), dtype=torch.float32, device=indices.device)
+        self.qnet.forward_device(indices.data_ptr(), n, 1, None, None, out.data_ptr(), _stream())
+        return out
+
+    def close(self):
+        self.qnet.close()

@@ -171,3 +171,48 @@ def test_torch_dqn_example_runs_on_device(qlb):
     out = mod.run(n_envs=256, iterations=60, batch=32, quiet=True)
     assert out["env_steps"] == 256 * 60 and out["train_calls"] >= 50 and np.isfinite(out["last_loss"])
     assert out["epsilon"] < 1.0 and out["error_flags"] & ~qlb.ENVERR_DEGENERATE == 0
+    out = mod.run(n_envs=256, iterations=60, batch=32, quiet=True, tensor_core_actor=True)     # greedy actions from the tcgen05 Q-network
+    assert out["env_steps"] == 256 * 60 and out["train_calls"] >= 50 and np.isfinite(out["last_loss"])
+
+
+@pytest.mark.gpu
+def test_tensor_core_actor_follows_a_torch_network(qlb, O):
+    """torch_io.TensorCoreActor: weights of a torch network with the reference architecture, copied into the library's
+    tcgen05 Q-network, give the torch network's greedy actions (wherever its top-2 gap is clear) and max-Q of sampled
+    next states — read from the frame ring by index, never gathered. Tolerance 4e-2 * max|Q| (bf16 operands vs fp32)."""
+    torch = pytest.importorskip("torch")
+    import importlib
+    tio = importlib.import_module("q-learning_b200.torch_io")
+    n = 256
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=3, replay_capacity=n * 16)
+    rb = qlb.ReplayBuffer(env)
+    env.step_many(np.random.default_rng(0).integers(0, 3, size=(9, n), dtype=np.uint8))
+    torch.manual_seed(0)
+    nn = torch.nn
+    net = nn.Sequential(nn.Conv2d(4, 32, 8, stride=4), nn.ReLU(), nn.Conv2d(32, 64, 4, stride=2), nn.ReLU(), nn.Conv2d(64, 64, 3, stride=1), nn.ReLU(),
+                        nn.Flatten(), nn.Linear(3136, 512), nn.ReLU(), nn.Linear(512, 3)).cuda()
+    actor = tio.TensorCoreActor(env, net)
+    with torch.no_grad():
+        ref = net(tio.observe(env, qlb.LAYOUT_F32_BXYH).permute(0, 3, 1, 2))
+    act = actor.predict_action(want_q=True)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    assert float((actor.q - ref).abs().max()) <= 4e-2 * scale
+    top2 = ref.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 8e-2 * scale
+    assert bool(clear.any()) and torch.equal(act[0][clear], ref.argmax(dim=1).to(torch.uint8)[clear])
+    smp = tio.DeviceSampler(rb, 64).sample(0)
+    with torch.no_grad():
+        ref_next = net(smp.state_next.view(64, 84, 84, 4).permute(0, 3, 1, 2)).max(dim=1).values
+    got = actor.max_future_reward(smp.indices.view(-1))
+    torch.cuda.synchronize()
+    assert float((got - ref_next).abs().max()) <= 4e-2 * scale
+    with torch.no_grad():                                                   # new weights take effect after sync()
+        for p in net.parameters():
+            p.mul_(0.5)
+        ref2 = net(tio.observe(env, qlb.LAYOUT_F32_BXYH).permute(0, 3, 1, 2))
+    actor.sync(net)
+    actor.predict_action(want_q=True)
+    torch.cuda.synchronize()
+    assert float((actor.q - ref2).abs().max()) <= 4e-2 * float(ref2.abs().max())
+    actor.close(); env.close()
