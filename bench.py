@@ -265,7 +265,7 @@ def run_b200(args, rank, local_rank, world):
                     "frac": achieved / peak, "peak_source": peak_src, "traffic": _ncu_traffic("env_advance_kernel"),
                     "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n_envs * k_inner}
         if not args.no_extra:
-            extra = measure_extras(q, torch, env, rb, dev, stream, peak)
+            extra = measure_extras(q, torch, env, rb, dev, stream, peak, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             O.build()
@@ -299,7 +299,7 @@ def run_b200(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def measure_extras(q, torch, env, rb, dev, stream, peak):
+def measure_extras(q, torch, env, rb, dev, stream, peak, cpu_baseline=True):
     """Secondary numbers in the same run: replay sampling (configs[2]) and the 65,536-env shard (configs[3])."""
     out = {}
     per = 4 * 84 * 84
@@ -331,6 +331,14 @@ def measure_extras(q, torch, env, rb, dev, stream, peak):
             del idx, st, nx
     out["replay_sample"] = {"metric": "sampled_transitions_per_sec", "replay_len": rb.len(), "results": res,
                             "note": "sample (Philox distinct ids) + gather (s and s' stacks) on device buffers; minibatches per call = the x factor"}
+    if cpu_baseline:
+        # the reference's replay path on the host (ReplayBuffer::get_many + batch_to_multi_dim_array for state and state_next,
+        # generate_distinct_random_ids), single-threaded like the reference learner; bounded sample
+        from oracle import oracle as O
+        s_envs, s_cap, s_batch, s_nb = 64, 4096, 32, 300
+        secs = O.bench_sample(s_envs, s_cap, s_batch, s_nb, SEED)
+        out["replay_sample"]["cpu_baseline"] = {"value": s_batch * s_nb / secs, "unit": "sampled transitions/s", "cores": 1, "kind": "port",
+                                                "sample": "%d minibatches of %d (f32 [b][x][y][slot] state + state_next) from a %d-transition replay of %d envs, CPU oracle, 1 thread, %.1f s" % (s_nb, s_batch, s_cap, s_envs, secs)}
     # 65,536 envs on this GPU (configs[3] shard size), 16 env-steps per launch
     try:
         big = q.BreakoutEnvironment(n_envs=65536, seed=SEED + 1, replay_capacity=65536 * 32, device=dev.index)
