@@ -738,7 +738,9 @@ static cudaError_t launch_gemm_tc(const Loader& ld, const __nv_bfloat16* w, cons
                                   int relu, unsigned int* err, cudaStream_t s) {
     const size_t dyn = 2 * ((size_t)qnet::TILE_M * qnet::KC * 2 + (size_t)NT * qnet::KC * 2);
     auto kern = qnet::gemm_tc_kernel<NT, Loader>;
-    static int occ = 0, sms = 0;
+    static int occ_dev[64] = {}, sms_dev[64] = {};
+    int cur_dev = 0; cudaGetDevice(&cur_dev);
+    int &occ = occ_dev[cur_dev & 63], &sms = sms_dev[cur_dev & 63];
     cudaError_t e = cudaSuccess;
     if (occ == 0) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -776,14 +778,16 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 template <class G, class Out>
 static cudaError_t launch_conv_sw(const qnet::ConvArgs& a, const Out& o, cudaStream_t s) {
     auto kern = qnet::conv_sw_kernel<G, Out>;
-    static int sms = 0;
-    if (sms == 0) {
+    static int sms[64] = {};                             // per device: function attributes are per context
+    int dev = 0; cudaGetDevice(&dev);
+    int& n_sm = sms[dev & 63];
+    if (n_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
     const uint32_t n_batches = (a.n_items + G::B - 1) / G::B;
-    return launch_pdl(kern, dim3(n_batches < (uint32_t)sms ? n_batches : (uint32_t)sms), dim3(G::THREADS), G::SMEM_BYTES, s, a, o);      // persistent: one CTA per SM
+    return launch_pdl(kern, dim3(n_batches < (uint32_t)n_sm ? n_batches : (uint32_t)n_sm), dim3(G::THREADS), G::SMEM_BYTES, s, a, o);      // persistent: one CTA per SM
 }
 
 extern "C" {
@@ -920,8 +924,11 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
     }
     if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv3: ") + cudaGetErrorString(e));
     if (impl >= 4) {
-        static bool attr_set = false;
-        if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(qnet::dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qnet::DenseGeom::SMEM_BYTES)); attr_set = true; }
+        static bool attr_set[64] = {};
+        if (!attr_set[env->cfg.device & 63]) {
+            CUDA_TRY(cudaFuncSetAttribute(qnet::dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qnet::DenseGeom::SMEM_BYTES));
+            attr_set[env->cfg.device & 63] = true;
+        }
         CUDA_TRY(launch_pdl(qnet::dense_tc_kernel, dim3((n + 127) / 128, 2), dim3(qnet::DenseGeom::THREADS), qnet::DenseGeom::SMEM_BYTES, s, (const uint8_t*)q->a3p, (const uint8_t*)q->w4p,
                             (const float*)q->b4, q->a4, n, q->err));
         const uint32_t hb = (n + 7) / 8;
