@@ -201,6 +201,9 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
         for (int i = tid; i < (int)(sizeof(RasterTables) / 4); i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
+    // Programmatic dependent launch (single-step launches, qlc_api.cu): everything above touches nothing an earlier kernel
+    // wrote, so it may overlap the predecessor's tail; from here on its results (actions, env state, frame ring) are needed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         // ------------------------------- physics warp -------------------------------

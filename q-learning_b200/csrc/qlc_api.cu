@@ -256,7 +256,16 @@ static int32_t launch_advance(qlc_env* env, StepParams& p, cudaStream_t s, uint3
         void* args[] = {(void*)&env->st, (void*)&p};
         CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(32 * (R + 1)), args, dyn, s));
     } else {
-        kern<<<grid, 32 * (R + 1), dyn, s>>>(env->st, p);
+        // programmatic stream serialization: the prologue (barriers, zeroed resident frames, raster tables) may run while the
+        // previous kernel in the stream drains; the kernel waits (griddepcontrol.wait) before it reads anything that kernel wrote
+        static const bool pdl = getenv("QLC_STEP_PDL") ? atoi(getenv("QLC_STEP_PDL")) != 0 : true;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * (R + 1)); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, env->st, p));
     }
     CUDA_TRY(cudaGetLastError());
     if (n_batches * n_chunks > grid) env->work_base += n_batches * n_chunks;      // (n_items - grid) hand-outs + one failed grab per CTA
