@@ -562,6 +562,7 @@ __global__ void __launch_bounds__(32) gather_u8_kernel(GatherParams g) {
     __shared__ uint64_t bar;
     const int lane = threadIdx.x;
     const uint32_t b = blockIdx.x;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // launched with programmatic stream serialization: the indices come from the sample kernel
     uint64_t T; uint32_t e, k, rec;
     locate(g, b, T, e, k, rec);
     uint8_t* zero = sm + 5 * FRAME_BYTES;
@@ -614,6 +615,7 @@ __global__ void __launch_bounds__(GATHER_F32_THREADS) gather_f32_kernel(GatherPa
     const uint32_t b = blockIdx.x >> 1, which = blockIdx.x & 1u;   // 0 = state, 1 = next
     float4* out = reinterpret_cast<float4*>(which ? g.out_next : g.out_state);
     if (!out) return;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // launched with programmatic stream serialization: the indices come from the sample kernel
     uint64_t T; uint32_t e, k, rec;
     locate(g, b, T, e, k, rec);
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }

@@ -66,6 +66,20 @@ static int32_t ensure_pin(qlc_env* env, size_t bytes) {
     env->pin_bytes = bytes;
     return QLC_OK;
 }
+// launch with programmatic stream serialization: the kernel's prologue may overlap the tail of its predecessor in the stream
+// (every kernel launched this way calls griddepcontrol.wait before it touches anything the predecessor wrote)
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    static const bool enabled = getenv("QLC_PDL") ? atoi(getenv("QLC_PDL")) != 0 : true;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = enabled ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static int32_t ensure_dev_stage(qlc_env* env, size_t bytes) {
     if (bytes <= env->dev_stage_bytes) return QLC_OK;
     if (env->dev_stage) cudaFree(env->dev_stage);
@@ -402,9 +416,9 @@ static void fill_gather(const qlc_env* env, GatherParams& g) {
 static int32_t launch_gather(qlc_env* env, const GatherParams& g, int32_t layout, cudaStream_t s) {
     if (g.n_items == 0) return QLC_OK;
     if (layout == QLC_LAYOUT_U8_BHYX) {
-        gather_u8_kernel<<<g.n_items, 32, 6 * FRAME_BYTES, s>>>(g);
+        CUDA_TRY(launch_pdl(gather_u8_kernel, dim3(g.n_items), dim3(32), 6 * FRAME_BYTES, s, g));
     } else if (layout == QLC_LAYOUT_F32_BXYH) {
-        gather_f32_kernel<<<g.n_items * 2, GATHER_F32_THREADS, 4 * FRAME_BYTES, s>>>(g);
+        CUDA_TRY(launch_pdl(gather_f32_kernel, dim3(g.n_items * 2), dim3(GATHER_F32_THREADS), 4 * FRAME_BYTES, s, g));
     } else {
         return fail(QLC_ERR_INVALID_ARG, "unknown layout");
     }
@@ -768,20 +782,6 @@ static cudaError_t launch_gemm_tc(const Loader& ld, const __nv_bfloat16* w, cons
     if (gx > n_mtiles) gx = n_mtiles;
     kern<<<dim3(gx, n_ntiles), 128, dyn, s>>>(ld, w, bias, out, m, k, n_total, relu, err);
     return cudaGetLastError();
-}
-
-// launch with programmatic stream serialization: the kernel's prologue may overlap the tail of its predecessor in the stream
-// (every kernel launched this way calls griddepcontrol.wait before it touches anything the predecessor wrote)
-template <class... KArgs, class... Args>
-static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
-    static const bool enabled = getenv("QLC_QNET_PDL") ? atoi(getenv("QLC_QNET_PDL")) != 0 : true;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = enabled ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 template <class G, class Out>
