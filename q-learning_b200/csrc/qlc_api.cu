@@ -40,6 +40,8 @@ struct qlc_env {
     int chunk_override = -1;                   // QLC_CHUNK: force the chunk length (0 = off)
     uint64_t submit_seq = 0;                   // qlc_env_step_host_submit calls so far
     cudaEvent_t submit_done[8] = {};           // completion of submit k in slot k % 8 (created on first use)
+    cudaStream_t copy_stream = nullptr;        // pipelined submits: the H2D of step k+1 runs beside the kernel of step k
+    cudaEvent_t h2d_done[2] = {};
     int zero_copy = 1;                         // QLC_ZERO_COPY=0: always stage page-locked outputs through a D2H copy
     uint32_t time_slots = 0;                   // frame/record ring length in time steps (= t_cap + 4)
     uint32_t t_cap = 0;                        // replay capacity in time steps
@@ -201,6 +203,8 @@ int32_t qlc_env_destroy(qlc_env* env) {
     if (env->pin) cudaFreeHost(env->pin);
     if (env->dev_stage) cudaFree(env->dev_stage);
     for (cudaEvent_t ev : env->submit_done) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : env->h2d_done) if (ev) cudaEventDestroy(ev);
+    if (env->copy_stream) cudaStreamDestroy(env->copy_stream);
     if (env->own_stream) cudaStreamDestroy(env->own_stream);
     delete env;
     return QLC_OK;
@@ -354,6 +358,16 @@ static int32_t step_host_impl(qlc_env* env, const uint8_t* actions_host, uint32_
     const uint8_t* actions_dev = dev;
     if (pin_a && env->zero_copy >= 2) {
         actions_dev = actions_host;             // the physics lanes read (and prefetch) the action bytes straight from host memory
+    } else if (pin_a && !wait) {
+        // pipelined: copy on a second stream so that it overlaps the previous step's kernel; the staging slice was last read by
+        // the kernel of submit seq-2
+        if (!env->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&env->copy_stream, cudaStreamNonBlocking));
+        cudaEvent_t& hd = env->h2d_done[slot];
+        if (!hd) CUDA_TRY(cudaEventCreateWithFlags(&hd, cudaEventDisableTiming));
+        if (env->submit_seq >= 2) CUDA_TRY(cudaStreamWaitEvent(env->copy_stream, env->submit_done[(env->submit_seq - 2) % 8], 0));
+        CUDA_TRY(cudaMemcpyAsync(dev, actions_host, n, cudaMemcpyHostToDevice, env->copy_stream));
+        CUDA_TRY(cudaEventRecord(hd, env->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(s, hd, 0));
     } else if (pin_a) {
         CUDA_TRY(cudaMemcpyAsync(dev, actions_host, n, cudaMemcpyHostToDevice, s));
     } else {
