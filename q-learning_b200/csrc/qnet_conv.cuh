@@ -13,11 +13,14 @@
 //
 // One persistent CTA per SM, warp-specialised:
 //   warps 0-3  epilogue: tcgen05.ld of their TMEM lane quadrant, bias + ReLU, bf16, store in the NEXT layer's plane layout
-//   warp  4    one thread issues every tcgen05.mma of a batch (tiles x taps x K steps) and commits to mbarriers
+//   warp  4    issues every tcgen05.mma of a batch (tiles x taps x K steps) and commits to mbarriers; the whole warp runs the loop
+//              (elect.sync per instruction, votes on the waits) so that the descriptors stay in uniform registers
 //   warp  5    one thread issues the bulk copies (conv1: the four u8 ring frames of an item, raw; conv2/3: a whole stage)
 //   warps 6..  conv1 only: convert the raw u8 frames to bf16 planes (space-to-depth by 4) in shared memory
 // Input stages and TMEM accumulator sets are double-buffered, so copies, conversion, MMAs and epilogue of neighbouring
-// batches overlap. Architecture: /root/reference/src/ql-with-tensorflow/python_model/create_ql_model_breakout_84x84x4_3_32.py:17-33.
+// batches overlap. What bounds the kernels is the shared-memory operand fetch of the tensor core: an M = 128, K = 16 MMA with
+// both operands in shared memory takes max(N/2, 32 + N/4) cycles (tools/microbench/mma_rate.cu), i.e. 40 / 48 cycles at the
+// model's N = 32 / 64 instead of the tensor pipe's 16 / 32. Architecture: /root/reference/src/ql-with-tensorflow/python_model/create_ql_model_breakout_84x84x4_3_32.py:17-33.
 #pragma once
 #include "qnet.cuh"
 
