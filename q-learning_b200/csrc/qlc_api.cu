@@ -820,7 +820,7 @@ struct qlc_qnet {
     qlc_env* env = nullptr;
     __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr; float* w5 = nullptr;
     float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *b4 = nullptr, *b5 = nullptr;
-    __nv_bfloat16 *w1p = nullptr, *w2p = nullptr, *w3p = nullptr, *w4p = nullptr;   // operand-layout weights: planes [K/8][N][8]
+    __nv_bfloat16 *w1p = nullptr, *w2p = nullptr, *w3p = nullptr, *w4p = nullptr, *w4p256 = nullptr;   // operand-layout weights (dense: N tiles of 128 and of 256): planes [K/8][N][8]
     __nv_bfloat16 *a1 = nullptr, *a2 = nullptr, *a3 = nullptr, *a4 = nullptr; uint32_t* slot_frame = nullptr; unsigned int* err = nullptr;
     __nv_bfloat16 *a1p = nullptr, *a2p = nullptr, *a3p = nullptr;         // conv outputs in the next layer's operand (plane) layout
     unsigned long long* prof = nullptr;                                    // QLC_QNET_PROF: per-role cycle counters of CTA 0, printed after each forward
@@ -839,7 +839,7 @@ int32_t qlc_qnet_destroy(qlc_qnet* q) {
     cudaSetDevice(q->env->cfg.device);
     cudaDeviceSynchronize();
     qnet_free_acts(q);
-    cudaFree(q->w1); cudaFree(q->w2); cudaFree(q->w3); cudaFree(q->w4); cudaFree(q->w5); cudaFree(q->w1p); cudaFree(q->w2p); cudaFree(q->w3p); cudaFree(q->w4p);
+    cudaFree(q->w1); cudaFree(q->w2); cudaFree(q->w3); cudaFree(q->w4); cudaFree(q->w5); cudaFree(q->w1p); cudaFree(q->w2p); cudaFree(q->w3p); cudaFree(q->w4p); cudaFree(q->w4p256);
     cudaFree(q->b1); cudaFree(q->b2); cudaFree(q->b3); cudaFree(q->b4); cudaFree(q->b5); cudaFree(q->err); cudaFree(q->stage); cudaFree(q->prof);
     delete q;
     return QLC_OK;
@@ -865,7 +865,8 @@ int32_t qlc_qnet_set_weights(qlc_qnet* q, const qlc_qnet_weights* w) {
             case 2: qnet::prep_transpose_kernel<<<(576 * 64 + 255) / 256, 256>>>(q->stage, q->w3, 576, 64);
                     qnet::prep_conv3_planes_kernel<<<(576 * 64 + 255) / 256, 256>>>(q->stage, q->w3p); break;
             case 3: qnet::prep_transpose_kernel<<<(3136 * 512 + 255) / 256, 256>>>(q->stage, q->w4, 3136, 512);
-                    qnet::prep_dense_planes_kernel<<<(3136 * 512 + 255) / 256, 256>>>(q->stage, q->w4p); break;
+                    qnet::prep_dense_planes_kernel<128><<<(3136 * 512 + 255) / 256, 256>>>(q->stage, q->w4p);
+                    qnet::prep_dense_planes_kernel<256><<<(3136 * 512 + 255) / 256, 256>>>(q->stage, q->w4p256); break;
             default: qnet::prep_head_kernel<<<(3 * 512 + 255) / 256, 256>>>(q->stage, q->w5); break;
         }
         CUDA_TRY(cudaGetLastError());
@@ -884,7 +885,7 @@ int32_t qlc_qnet_create(qlc_env* env, const qlc_qnet_weights* w, qlc_qnet** out)
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     A((void**)&q->w1, 32 * 256 * 2); A((void**)&q->w2, 64 * 512 * 2); A((void**)&q->w3, 64 * 576 * 2); A((void**)&q->w4, (size_t)512 * 3136 * 2); A((void**)&q->w5, 3 * 512 * 4);
-    A((void**)&q->w1p, 32 * 256 * 2); A((void**)&q->w2p, 64 * 512 * 2); A((void**)&q->w3p, 64 * 576 * 2); A((void**)&q->w4p, (size_t)512 * 3136 * 2);
+    A((void**)&q->w1p, 32 * 256 * 2); A((void**)&q->w2p, 64 * 512 * 2); A((void**)&q->w3p, 64 * 576 * 2); A((void**)&q->w4p, (size_t)512 * 3136 * 2); A((void**)&q->w4p256, (size_t)512 * 3136 * 2);
     if (const char* v = getenv("QLC_QNET_IMPL")) q->impl = atoi(v);
     if (getenv("QLC_QNET_PROF")) A((void**)&q->prof, 3 * 32 * 8);
     A((void**)&q->b1, 32 * 4); A((void**)&q->b2, 64 * 4); A((void**)&q->b3, 64 * 4); A((void**)&q->b4, 512 * 4); A((void**)&q->b5, 3 * 4); A((void**)&q->err, 4);
@@ -949,11 +950,20 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
     if (impl >= 4) {
         static bool attr_set[64] = {};
         if (!attr_set[env->cfg.device & 63]) {
-            CUDA_TRY(cudaFuncSetAttribute(qnet::dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qnet::DenseGeom::SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(qnet::dense_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qnet::DenseGeomT<128>::SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(qnet::dense_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qnet::DenseGeomT<256>::SMEM_BYTES));
             attr_set[env->cfg.device & 63] = true;
         }
-        CUDA_TRY(launch_pdl(qnet::dense_tc_kernel, dim3((n + 127) / 128, 2), dim3(qnet::DenseGeom::THREADS), qnet::DenseGeom::SMEM_BYTES, s, (const uint8_t*)q->a3p, (const uint8_t*)q->w4p,
-                            (const float*)q->b4, q->a4, n, q->err));
+        // N tiles of 128 while (M tiles x 2) CTAs would leave SMs idle (the layer is bound by per-SM L2 ingest), 256 beyond
+        const uint32_t m_tiles = (n + 127) / 128;
+        static const int nt_force = getenv("QLC_QNET_DENSE_NT") ? atoi(getenv("QLC_QNET_DENSE_NT")) : 0;
+        const bool narrow = nt_force ? nt_force == 128 : m_tiles * 2u < (uint32_t)env->sm_count;
+        if (narrow)
+            CUDA_TRY(launch_pdl(qnet::dense_tc_kernel<128>, dim3(m_tiles, 4), dim3(qnet::DenseGeomT<128>::THREADS), qnet::DenseGeomT<128>::SMEM_BYTES, s, (const uint8_t*)q->a3p,
+                                (const uint8_t*)q->w4p, (const float*)q->b4, q->a4, n, q->err));
+        else
+            CUDA_TRY(launch_pdl(qnet::dense_tc_kernel<256>, dim3(m_tiles, 2), dim3(qnet::DenseGeomT<256>::THREADS), qnet::DenseGeomT<256>::SMEM_BYTES, s, (const uint8_t*)q->a3p,
+                                (const uint8_t*)q->w4p256, (const float*)q->b4, q->a4, n, q->err));
         const uint32_t hb = (n + 7) / 8;
         CUDA_TRY(launch_pdl(qnet::head_vec_kernel, dim3(hb < 592u ? hb : 592u), dim3(256), 0, s, (const __nv_bfloat16*)q->a4, (const float*)q->w5, (const float*)q->b5, q_dev, action_dev, max_q_dev, n));
     } else {

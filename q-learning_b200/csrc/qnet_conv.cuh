@@ -383,19 +383,24 @@ __global__ void prep_conv3_planes_kernel(const float* __restrict__ kernel /*[3][
 // Dense 3136 -> 512 (+ ReLU) as a bulk-copy fed tcgen05 GEMM. A (conv3's output, Keras Flatten order) and W live in global
 // memory already in the shared-memory operand layout, so one stage = one contiguous bulk copy per operand:
 //   A: [M tile = item / 128][K chunk j = k / 8 (392)][item % 128][8]      (written by conv3's epilogue, OutDensePlanes)
-//   W: [N half (2)][j (392)][n % 256][8]                                  (prep_dense_planes_kernel)
-// One CTA = one (M tile, N half): 128 items x 256 outputs, K = 3136 in 49 stages of 64 through a 4-deep ring;
-// tcgen05.mma M = 128, N = 256 runs at the tensor-pipe rate (128 cycles per K = 16, measured) when fed from shared memory.
+//   W: [N tile (4)][j (392)][n % 128][8]                                  (prep_dense_planes_kernel)
+// One CTA = one (M tile, N tile of NT): 128 items x NT outputs, K = 3136 in 49 stages of 64 through a 6- / 4-deep ring. The
+// layer is bound by what one SM can pull from L2 (~53 B/clk measured): with NT = 256 only 64 CTAs exist at 4,096 items and
+// each has to ingest 2.35 MB (24 us); NT = 128 gives 128 CTAs x 1.57 MB (18 us) but re-reads A twice as often, so it is
+// used while (M tiles x 2) CTAs would not fill the SMs and NT = 256 beyond. The MMAs (64 / 128 cycles per K = 16 at
+// N = 128 / 256, the tensor-pipe rate) are hidden behind the copies.
 // =========================================================================================================
-struct DenseGeom {
-    static constexpr int K = 3136, N = 512, NT = 256, KSTAGE = 64, NSTAGE = 4;
+template <int NT_>
+struct DenseGeomT {
+    static constexpr int K = 3136, N = 512, NT = NT_, KSTAGE = 64, NSTAGE = NT_ == 128 ? 6 : 4;
     static constexpr int PLANES = K / 8, STAGES_K = K / KSTAGE;             // 392 planes, 49 stages
     static constexpr int A_STAGE = (KSTAGE / 8) * TILE_M * 16;               // 16 KB
-    static constexpr int B_STAGE = (KSTAGE / 8) * NT * 16;                   // 32 KB
+    static constexpr int B_STAGE = (KSTAGE / 8) * NT * 16;                   // 16 / 32 KB
     static constexpr int A_TILE_BYTES = PLANES * TILE_M * 16;                // one M tile of A
     static constexpr int THREADS = 192;
     static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * (A_STAGE + B_STAGE) + NT * 4 + (2 * NSTAGE + 1) * 8 + 16;
 };
+using DenseGeom = DenseGeomT<128>;   // A-side constants (PLANES, A_TILE_BYTES) do not depend on NT
 struct OutDensePlanes {              // conv3 -> dense A operand, k = (ox*7 + oy)*64 + c
     __nv_bfloat16* out;
     __device__ __forceinline__ void store8(uint32_t item, uint32_t ox, uint32_t oy, uint32_t c0, uint4 v) const {
@@ -404,10 +409,11 @@ struct OutDensePlanes {              // conv3 -> dense A operand, k = (ox*7 + oy
     }
 };
 
-__global__ void __launch_bounds__(DenseGeom::THREADS, 1) dense_tc_kernel(const uint8_t* __restrict__ a_planes, const uint8_t* __restrict__ w_planes,
+template <int NT>
+__global__ void __launch_bounds__(DenseGeomT<NT>::THREADS, 1) dense_tc_kernel(const uint8_t* __restrict__ a_planes, const uint8_t* __restrict__ w_planes,
                                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out /*[items][512]*/,
                                                                          uint32_t n_items, unsigned int* err) {
-    using G = DenseGeom;
+    using G = DenseGeomT<NT>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* const s_a = smem;
     uint8_t* const s_b = s_a + (size_t)G::NSTAGE * G::A_STAGE;
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(DenseGeom::THREADS, 1) dense_tc_kernel(const u
     uint64_t* const acc_full = empty + G::NSTAGE;
     uint32_t* const s_misc = reinterpret_cast<uint32_t*>(acc_full + 1);
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    const uint32_t mtile = blockIdx.x, nhalf = blockIdx.y;
+    const uint32_t mtile = blockIdx.x, nhalf = blockIdx.y;       // nhalf: index of the N tile
 
     if (tid == 0) {
         for (int i = 0; i < G::NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -439,7 +445,7 @@ __global__ void __launch_bounds__(DenseGeom::THREADS, 1) dense_tc_kernel(const u
     };
 
     if (warp < 4) {
-        // epilogue: row = item, 256 columns in 8 pieces of 32
+        // epilogue: row = item, NT columns in pieces of 32
         if (wait(acc_full, 0)) {
             tc_fence_after();
             const uint32_t item = mtile * TILE_M + warp * 32u + lane;
@@ -491,12 +497,13 @@ __global__ void __launch_bounds__(DenseGeom::THREADS, 1) dense_tc_kernel(const u
     if (warp == 4) tmem_dealloc(tmem_base, G::NT);
 }
 
-// Keras dense kernel [3136][512] f32 -> bf16 [N half][j][n % 256][8]
+// Keras dense kernel [3136][512] f32 -> bf16 [N tile][j][n % NT][8]
+template <int NT>
 __global__ void prep_dense_planes_kernel(const float* __restrict__ kernel, __nv_bfloat16* __restrict__ w) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3136 * 512) return;
-    const int e = i & 7, n256 = (i >> 3) & 255, j = (i >> 11) % 392, half = i / (392 * 2048);
-    w[i] = __float2bfloat16_rn(kernel[(size_t)(j * 8 + e) * 512 + half * 256 + n256]);
+    const int e = i & 7, nt = (i >> 3) % NT, j = (i / (8 * NT)) % 392, tile = i / (392 * 8 * NT);
+    w[i] = __float2bfloat16_rn(kernel[(size_t)(j * 8 + e) * 512 + tile * NT + nt]);
 }
 
 // Dense 512 -> 3 + argmax, one warp per row with 16-byte loads (replaces head_kernel's 2-byte loads)
