@@ -262,7 +262,6 @@ __global__ void __launch_bounds__(G::THREADS, 1) conv_sw_kernel(ConvArgs args, O
                 const uint32_t a_lo = a_lo0 + (uint32_t)G::row0(t);                       // one row = 16 bytes = 1 address unit
                 #pragma unroll
                 for (int tap = 0; tap < G::TAPS; ++tap) {
-                    constexpr int dummy = 0; (void)dummy;
                     const uint32_t shift = (uint32_t)((tap / G::TX) * G::WIN + (tap % G::TX));
                     #pragma unroll
                     for (int kk = 0; kk < G::KSTEPS; ++kk)
