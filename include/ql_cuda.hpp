@@ -246,4 +246,55 @@ std::array<size_t, BATCH_SIZE> generate_distinct_random_ids(const ReplayBuffer& 
     return out;
 }
 
+// ---- the inference half of DeepQLearningModel (ml_model/model.rs:29-77) on the library's tensor-core Q-network ----
+// predict_action (:40-46) and batch_predict_max_future_reward (:48-57) for BreakoutState handles: the network reads the u8
+// frames in the frame ring directly, no tensor is materialised. train() (:59-71) stays with the caller, who hands updated
+// weights over with set_weights (ten f32 arrays in the Keras layouts, see qlc_qnet_weights).
+class TensorCoreQModel {
+public:
+    TensorCoreQModel(const BreakoutEnvironment& env, const qlc_qnet_weights& weights) : env_(env.handle()) { check(qlc_qnet_create(env_->get(), &weights, &q_)); }
+    ~TensorCoreQModel() { qlc_qnet_destroy(q_); }
+    TensorCoreQModel(const TensorCoreQModel&) = delete;
+    TensorCoreQModel& operator=(const TensorCoreQModel&) = delete;
+    void set_weights(const qlc_qnet_weights& weights) { check(qlc_qnet_set_weights(q_, &weights)); }
+
+    BreakoutAction predict_action(const BreakoutState& state) const {
+        std::array<float, 3> qv = q_values(state);
+        (void)qv;
+        return BreakoutActionTrait::try_from_numeric(last_action_);
+    }
+    std::array<float, 3> q_values(const BreakoutState& state) const {
+        std::array<float, 3> qv{};
+        if (state.kind() == BreakoutState::Kind::Live) {
+            if (state.time() != env_->time()) throw QlError("stale BreakoutState handle (the env has stepped since)");
+            std::vector<float> q((size_t)env_->n_envs() * 3); std::vector<uint8_t> a(env_->n_envs());
+            check(qlc_qnet_forward_host(q_, nullptr, env_->n_envs(), 0, q.data(), a.data(), nullptr));
+            std::copy(q.begin(), q.begin() + 3, qv.begin()); last_action_ = a[0];
+        } else {
+            const uint32_t idx = state.replay_index();
+            check(qlc_qnet_forward_host(q_, &idx, 1, state.kind() == BreakoutState::Kind::ReplayNext ? 1 : 0, qv.data(), &last_action_, nullptr));
+        }
+        return qv;
+    }
+    template <size_t N>
+    std::array<float, N> batch_predict_max_future_reward(const std::array<const std::shared_ptr<BreakoutState>*, N>& batch) const {
+        std::array<uint32_t, N> idx; std::array<float, N> out{};
+        const BreakoutState::Kind kind = (**batch[0]).kind();
+        if (kind == BreakoutState::Kind::Live) throw QlError("batch_predict_max_future_reward takes replay sample handles");
+        for (size_t b = 0; b < N; ++b) {
+            const BreakoutState& s = **batch[b];
+            if (s.kind() != kind) throw QlError("mixed state kinds in one batch");
+            if (s.time() != env_->time()) throw QlError("stale replay sample (the env has stepped since get_many)");
+            idx[b] = s.replay_index();
+        }
+        check(qlc_qnet_forward_host(q_, idx.data(), (uint32_t)N, kind == BreakoutState::Kind::ReplayNext ? 1 : 0, nullptr, nullptr, out.data()));
+        return out;
+    }
+
+private:
+    std::shared_ptr<EnvHandle> env_;
+    qlc_qnet* q_ = nullptr;
+    mutable uint8_t last_action_ = 0;
+};
+
 }  // namespace ql

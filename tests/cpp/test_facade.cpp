@@ -19,6 +19,15 @@ int main() {
         BreakoutEnvironment env(84, 84, history_buffer_len, /*seed=*/2024);
         ReplayBuffer replay(env, history_buffer_len, 100);
         CHECK(env.episode_reward_goal_mean() == 59.0f, "goal mean");
+        // the model's inference half on the tensor cores (random weights of the reference architecture)
+        std::vector<float> w1(8 * 8 * 4 * 32), b1(32, 0.01f), w2(4 * 4 * 32 * 64), b2(64, 0.01f), w3(3 * 3 * 64 * 64), b3(64, 0.01f), w4((size_t)3136 * 512), b4(512, 0.01f), w5(512 * 3), b5(3, 0.0f);
+        {
+            uint64_t r = 99;
+            auto fill = [&](std::vector<float>& v, float scale) { for (float& x : v) { r = r * 6364136223846793005ULL + 1442695040888963407ULL; x = scale * ((float)((r >> 40) & 0xFFFF) / 32768.0f - 1.0f); } };
+            fill(w1, 0.02f); fill(w2, 0.05f); fill(w3, 0.05f); fill(w4, 0.02f); fill(w5, 0.05f);
+        }
+        const qlc_qnet_weights weights{w1.data(), b1.data(), w2.data(), b2.data(), w3.data(), b3.data(), w4.data(), b4.data(), w5.data(), b5.data()};
+        TensorCoreQModel model(env, weights);
         struct Row { uint8_t a; float r; bool d; };
         std::vector<Row> history;
         uint64_t lcg = 12345, calls = 0;
@@ -60,6 +69,22 @@ int main() {
                         for (size_t k = 0; k < BATCH; ++k)
                             if (indices[k] == indices[i] + 1 && !history[indices[i]].d)
                                 for (size_t p = 0; p < per; ++p) CHECK(tn.data[i * per + p] == ts.data[k * per + p], "s'(t) != s(t+1)");
+                    // model inference on sample handles: max-Q of s'(t) equals max-Q of s(t+1) inside an episode, finite everywhere
+                    const std::array<float, BATCH> mq_next = model.batch_predict_max_future_reward<BATCH>(sn), mq_state = model.batch_predict_max_future_reward<BATCH>(st);
+                    for (size_t i = 0; i < BATCH; ++i) {
+                        CHECK(mq_next[i] == mq_next[i] && mq_state[i] == mq_state[i], "max-Q is NaN");
+                        for (size_t k = 0; k < BATCH; ++k)
+                            if (indices[k] == indices[i] + 1 && !history[indices[i]].d) CHECK(mq_next[i] == mq_state[k], "maxQ(s'(t)) != maxQ(s(t+1))");
+                    }
+                    if (trained == 0) {
+                        const std::array<float, 3> qv = model.q_values(*state);                    // live state == s' of the newest transition
+                        const BreakoutAction greedy = model.predict_action(*state);
+                        const uint8_t g = BreakoutActionTrait::numeric(greedy);
+                        CHECK(qv[g] >= qv[0] && qv[g] >= qv[1] && qv[g] >= qv[2], "predict_action is not the arg max");
+                        BreakoutState newest(env.handle(), BreakoutState::Kind::ReplayNext, (uint32_t)(replay.len() - 1), state->time());
+                        const std::array<float, 3> qn = model.q_values(newest);
+                        CHECK(qn[0] == qv[0] && qn[1] == qv[1] && qn[2] == qv[2], "live state and newest state_next differ");
+                    }
                     trained += 1;
                 }
                 if (done) break;
