@@ -5,9 +5,11 @@
 pub mod ffi;
 
 mod env;
+mod model;
 mod replay;
 
 pub use env::{BreakoutAction, CudaBreakoutEnvironment, CudaBreakoutState, StateKind};
+pub use model::{QNetWeights, TensorCoreQModel};
 pub use replay::{generate_distinct_random_ids, BufferSample, ReplayBuffer};
 
 use ql::prelude::QlError;
