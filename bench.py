@@ -32,6 +32,7 @@ BYTES_PER_ENV_STEP = 7154      # 7056 frame + 41+41 state + 1 ac
 BYTES_PER_SAMPLE_U8 = 91744    # 5 frames read + 2 x 4 frames written + 16 B scalars
 BYTES_PER_SAMPLE_F32 = 261088  # 5 frames read + 2 x 4 f32 frames written + 16 B scalars
 SEED = 20261018
+QNET_FLOP_PER_OBS = 2 * (400 * 32 * 256 + 81 * 64 * 512 + 49 * 64 * 576 + 512 * 3136 + 3 * 512)   # 84x84x4 -> conv 8/4, 4/2, 3/1 -> 512 -> 3
 
 
 def _peaks():
@@ -366,6 +367,23 @@ def measure_extras(q, torch, env, rb, dev, stream, peak, cpu_baseline=True):
         e1.record(); torch.cuda.synchronize()
         ms1 = e0.elapsed_time(e1) / 100
         out["envs_65536"]["single_step_launch"] = {"env_steps_per_sec": 65536 / (ms1 * 1e-3), "us_per_launch": ms1 * 1e3}
+        # closed actor loop on the big shard: Q-network forward for all 65,536 envs -> one env-step launch
+        net = q.QNetwork(big, _random_qnet_weights(q))
+        acts1 = torch.empty((1, 65536), dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            net.forward_device(None, 65536, 0, None, acts1.data_ptr(), None, stream)
+            big.step_device(acts1.data_ptr(), 1, None, None, stream)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            net.forward_device(None, 65536, 0, None, acts1.data_ptr(), None, stream)
+            big.step_device(acts1.data_ptr(), 1, None, None, stream)
+        e1.record(); torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / 20
+        out["envs_65536"]["actor_loop_qnet"] = {"env_steps_per_sec": 65536 / (ms2 * 1e-3), "ms_per_iteration": ms2,
+                                                "qnet_tflops": QNET_FLOP_PER_OBS * 65536 / (ms2 * 1e-3) / 1e12,
+                                                "note": "Q-network forward (greedy action for every env) + 1 env-step launch per iteration"}
+        net.close()
         big.close()
     except Exception as ex:  # e.g. not enough free HBM next to the main shard
         out["envs_65536"] = {"error": str(ex)}
@@ -412,7 +430,6 @@ def measure_extras(q, torch, env, rb, dev, stream, peak, cpu_baseline=True):
     return out
 
 
-QNET_FLOP_PER_OBS = 2 * (400 * 32 * 256 + 81 * 64 * 512 + 49 * 64 * 576 + 512 * 3136 + 3 * 512)   # 84x84x4 -> conv 8/4, 4/2, 3/1 -> 512 -> 3
 
 
 def _tensor_peak():
@@ -423,12 +440,9 @@ def _tensor_peak():
         return 2250.0, "nominal dense bf16"
 
 
-def measure_qnet(q, torch, env, rb, dev, stream, actor_iter_sample):
-    """SURVEY.md 8f-3: the Q-network forward on tcgen05 (predict_action for every env, straight from the frame ring) and the
-    closed actor loop of BASELINE configs[4]: greedy action from the network -> ONE env-step launch -> every 4th step a
-    minibatch sample + gather. Random-init weights of the reference architecture (no checkpoints here)."""
-    out = {}
-    rng = np.random.default_rng(7)
+def _random_qnet_weights(q, seed=7):
+    """random-init weights of the reference architecture (glorot-uniform kernels like Keras, zero biases)"""
+    rng = np.random.default_rng(seed)
     w = {}
     for name, shape in q.QNET_SHAPES.items():
         if name.endswith("kernel"):
@@ -436,6 +450,15 @@ def measure_qnet(q, torch, env, rb, dev, stream, actor_iter_sample):
             w[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
         else:
             w[name] = np.zeros(shape, dtype=np.float32)
+    return w
+
+
+def measure_qnet(q, torch, env, rb, dev, stream, actor_iter_sample):
+    """SURVEY.md 8f-3: the Q-network forward on tcgen05 (predict_action for every env, straight from the frame ring) and the
+    closed actor loop of BASELINE configs[4]: greedy action from the network -> ONE env-step launch -> every 4th step a
+    minibatch sample + gather. Random-init weights of the reference architecture (no checkpoints here)."""
+    out = {}
+    w = _random_qnet_weights(q)
     net = q.QNetwork(env, w)
     n = env.n_envs
     acts = torch.empty((1, n), dtype=torch.uint8, device=dev)

@@ -85,7 +85,11 @@ def kernels(tag, reps):
         out.append("")
         # traffic per launch: median over the largest-grid launches of this kernel
         big = max(ds, key=lambda d: d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0))
-        traffic[name.split("<")[0]] = big.get("dram__bytes_read.sum", 0) + big.get("dram__bytes_write.sum", 0)
+        key = name.split("<")[0]
+        if "conv_sw_kernel" in key:                     # one template, three layers: tell them apart by the rows-per-item parameter
+            key = {"441": "qnet_conv1", "100": "qnet_conv2", "81": "qnet_conv3"}.get(name.split("ConvGeom<")[1].split(",")[0].strip(), key)
+        key = key.replace("qnet::", "")
+        traffic[key] = big.get("dram__bytes_read.sum", 0) + big.get("dram__bytes_write.sum", 0)
     open(os.path.join(ROOT, "profiles", tag + "_kernels.md"), "w").write("\n".join(out) + "\n")
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
 
