@@ -822,6 +822,7 @@ struct qlc_qnet {
     float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *b4 = nullptr, *b5 = nullptr;
     __nv_bfloat16 *w1p = nullptr, *w2p = nullptr, *w3p = nullptr, *w4p = nullptr, *w4p256 = nullptr;   // operand-layout weights (dense: N tiles of 128 and of 256): planes [K/8][N][8]
     __nv_bfloat16 *a1 = nullptr, *a2 = nullptr, *a3 = nullptr, *a4 = nullptr; uint32_t* slot_frame = nullptr; unsigned int* err = nullptr;
+    float4* head_partial = nullptr; uint32_t* head_count = nullptr;       // dense epilogue -> fused head (per-N-tile partials, per-row tickets)
     __nv_bfloat16 *a1p = nullptr, *a2p = nullptr, *a3p = nullptr;         // conv outputs in the next layer's operand (plane) layout
     unsigned long long* prof = nullptr;                                    // QLC_QNET_PROF: per-role cycle counters of CTA 0, printed after each forward
     int impl = 4;                                                          // how many convs run as shifted-window kernels (QLC_QNET_IMPL, A/B testing)
@@ -830,8 +831,8 @@ struct qlc_qnet {
 };
 
 static void qnet_free_acts(qlc_qnet* q) {
-    cudaFree(q->a1); cudaFree(q->a2); cudaFree(q->a3); cudaFree(q->a4); cudaFree(q->slot_frame); cudaFree(q->a1p); cudaFree(q->a2p); cudaFree(q->a3p);
-    q->a1 = q->a2 = q->a3 = q->a4 = q->a1p = q->a2p = q->a3p = nullptr; q->slot_frame = nullptr; q->cap_items = 0;
+    cudaFree(q->a1); cudaFree(q->a2); cudaFree(q->a3); cudaFree(q->a4); cudaFree(q->slot_frame); cudaFree(q->a1p); cudaFree(q->a2p); cudaFree(q->a3p); cudaFree(q->head_partial); cudaFree(q->head_count);
+    q->a1 = q->a2 = q->a3 = q->a4 = q->a1p = q->a2p = q->a3p = nullptr; q->head_partial = nullptr; q->head_count = nullptr; q->slot_frame = nullptr; q->cap_items = 0;
 }
 
 int32_t qlc_qnet_destroy(qlc_qnet* q) {
@@ -915,6 +916,9 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
         CUDA_TRY(cudaMalloc(&q->a1p, a1p_bytes)); CUDA_TRY(cudaMalloc(&q->a2p, a2p_bytes));
         const size_t a3p_bytes = (size_t)((n + 127) / 128) * qnet::DenseGeom::A_TILE_BYTES;
         CUDA_TRY(cudaMalloc(&q->a3p, a3p_bytes)); CUDA_TRY(cudaMemset(q->a3p, 0, a3p_bytes));
+        const size_t rows_padded = (size_t)((n + 127) / 128) * 128;
+        CUDA_TRY(cudaMalloc(&q->head_partial, 4 * rows_padded * sizeof(float4))); CUDA_TRY(cudaMalloc(&q->head_count, rows_padded * 4));
+        CUDA_TRY(cudaMemset(q->head_count, 0, rows_padded * 4));
         CUDA_TRY(cudaMemset(q->a1p, 0, a1p_bytes)); CUDA_TRY(cudaMemset(q->a2p, 0, a2p_bytes));     // rows of a partial last batch are read (never used)
         q->cap_items = n;
     }
@@ -958,14 +962,15 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
         const uint32_t m_tiles = (n + 127) / 128;
         static const int nt_force = getenv("QLC_QNET_DENSE_NT") ? atoi(getenv("QLC_QNET_DENSE_NT")) : 0;
         const bool narrow = nt_force ? nt_force == 128 : m_tiles * 2u < (uint32_t)env->sm_count;
+        // the head (Dense 512 -> 3, argmax, max) runs in the dense epilogue; rows_padded is that of the allocation (cap_items)
+        const qnet::HeadArgs head{q->w5, q->b5, q->head_partial, q->head_count, ((q->cap_items + 127u) / 128u) * 128u, q_dev, action_dev, max_q_dev};
+        __nv_bfloat16* hidden = nullptr;                                   // the 512 hidden activations are not needed outside the kernel
         if (narrow)
             CUDA_TRY(launch_pdl(qnet::dense_tc_kernel<128>, dim3(m_tiles, 4), dim3(qnet::DenseGeomT<128>::THREADS), qnet::DenseGeomT<128>::SMEM_BYTES, s, (const uint8_t*)q->a3p,
-                                (const uint8_t*)q->w4p, (const float*)q->b4, q->a4, n, q->err));
+                                (const uint8_t*)q->w4p, (const float*)q->b4, hidden, n, q->err, head));
         else
             CUDA_TRY(launch_pdl(qnet::dense_tc_kernel<256>, dim3(m_tiles, 2), dim3(qnet::DenseGeomT<256>::THREADS), qnet::DenseGeomT<256>::SMEM_BYTES, s, (const uint8_t*)q->a3p,
-                                (const uint8_t*)q->w4p256, (const float*)q->b4, q->a4, n, q->err));
-        const uint32_t hb = (n + 7) / 8;
-        CUDA_TRY(launch_pdl(qnet::head_vec_kernel, dim3(hb < 592u ? hb : 592u), dim3(256), 0, s, (const __nv_bfloat16*)q->a4, (const float*)q->w5, (const float*)q->b5, q_dev, action_dev, max_q_dev, n));
+                                (const uint8_t*)q->w4p256, (const float*)q->b4, hidden, n, q->err, head));
     } else {
         qnet::LoadRowMajorBf16 l4{q->a3, 3136u};
         e = launch_gemm_tc<128>(l4, q->w4, q->b4, q->a4, n, 3136u, 512u, 1, q->err, s); if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("dense1: ") + cudaGetErrorString(e));

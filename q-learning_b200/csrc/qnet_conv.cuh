@@ -397,7 +397,15 @@ struct DenseGeomT {
     static constexpr int B_STAGE = (KSTAGE / 8) * NT * 16;                   // 16 / 32 KB
     static constexpr int A_TILE_BYTES = PLANES * TILE_M * 16;                // one M tile of A
     static constexpr int THREADS = 192;
-    static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * (A_STAGE + B_STAGE) + NT * 4 + (2 * NSTAGE + 1) * 8 + 16;
+    static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * (A_STAGE + B_STAGE) + NT * 4 + 3 * NT * 4 + (2 * NSTAGE + 1) * 8 + 16;
+};
+struct HeadArgs {                    // Dense 512 -> 3 (+ argmax / max) fused into the dense layer's epilogue
+    const float* w;                  // [3][512] f32 (prep_head_kernel)
+    const float* bias;               // [3]
+    float4* partial;                 // [N tiles][rows_padded]: per-N-tile partial dot products of every row
+    uint32_t* row_count;             // [rows_padded], zero between forwards: how many N tiles have delivered a row
+    uint32_t rows_padded;
+    float* q; uint8_t* action; float* max_q;   // outputs (any may be NULL)
 };
 using DenseGeom = DenseGeomT<128>;   // A-side constants (PLANES, A_TILE_BYTES) do not depend on NT
 struct OutDensePlanes {              // conv3 -> dense A operand, k = (ox*7 + oy)*64 + c
@@ -410,14 +418,15 @@ struct OutDensePlanes {              // conv3 -> dense A operand, k = (ox*7 + oy
 
 template <int NT>
 __global__ void __launch_bounds__(DenseGeomT<NT>::THREADS, 1) dense_tc_kernel(const uint8_t* __restrict__ a_planes, const uint8_t* __restrict__ w_planes,
-                                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out /*[items][512]*/,
-                                                                         uint32_t n_items, unsigned int* err) {
+                                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out /*[items][512] or NULL*/,
+                                                                         uint32_t n_items, unsigned int* err, HeadArgs head) {
     using G = DenseGeomT<NT>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* const s_a = smem;
     uint8_t* const s_b = s_a + (size_t)G::NSTAGE * G::A_STAGE;
     float* const s_bias = reinterpret_cast<float*>(s_b + (size_t)G::NSTAGE * G::B_STAGE);
-    uint64_t* const full = reinterpret_cast<uint64_t*>(s_bias + G::NT);
+    float* const s_w5 = s_bias + G::NT;                  // [3][NT]: this N tile's slice of the head weights
+    uint64_t* const full = reinterpret_cast<uint64_t*>(s_w5 + 3 * G::NT);
     uint64_t* const empty = full + G::NSTAGE;
     uint64_t* const acc_full = empty + G::NSTAGE;
     uint32_t* const s_misc = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -430,6 +439,7 @@ __global__ void __launch_bounds__(DenseGeomT<NT>::THREADS, 1) dense_tc_kernel(co
         fence_mbar_init();
     }
     for (uint32_t i = tid; i < (uint32_t)G::NT; i += G::THREADS) s_bias[i] = bias[nhalf * G::NT + i];
+    for (uint32_t i = tid; i < 3u * G::NT; i += G::THREADS) s_w5[i] = head.w[(i / G::NT) * G::N + nhalf * G::NT + i % G::NT];
     if (warp == 4) tmem_alloc(&s_misc[0], G::NT);
     tc_fence_before();
     __syncthreads();
@@ -444,10 +454,13 @@ __global__ void __launch_bounds__(DenseGeomT<NT>::THREADS, 1) dense_tc_kernel(co
     };
 
     if (warp < 4) {
-        // epilogue: row = item, NT columns in pieces of 32
+        // epilogue: row = item, NT columns in pieces of 32: bias + ReLU, bf16; the head (Dense 512 -> 3) is applied to the rounded
+        // activations on the fly. Each N tile leaves a partial dot product per row; the tile that delivers a row last (per-row
+        // ticket) adds the partials in tile order - deterministic - and writes Q, the greedy action and max Q.
         if (wait(acc_full, 0)) {
             tc_fence_after();
             const uint32_t item = mtile * TILE_M + warp * 32u + lane;
+            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
             #pragma unroll 1
             for (int piece = 0; piece < G::NT / 32; ++piece) {
                 uint32_t v[32];
@@ -455,12 +468,38 @@ __global__ void __launch_bounds__(DenseGeomT<NT>::THREADS, 1) dense_tc_kernel(co
                 if (item < n_items) {
                     #pragma unroll
                     for (int c = 0; c < 32; c += 8) {
-                        float f[8];
+                        uint32_t pk[4];
                         #pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = fmaxf(__uint_as_float(v[c + i]) + s_bias[piece * 32 + c + i], 0.0f);
-                        *reinterpret_cast<uint4*>(out + (size_t)item * G::N + nhalf * G::NT + piece * 32 + c) =
-                            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                        for (int i = 0; i < 8; i += 2) {
+                            const int col = piece * 32 + c + i;
+                            const uint32_t p2 = pack_bf16(fmaxf(__uint_as_float(v[c + i]) + s_bias[col], 0.0f), fmaxf(__uint_as_float(v[c + i + 1]) + s_bias[col + 1], 0.0f));
+                            pk[i >> 1] = p2;
+                            const float h0 = __uint_as_float(p2 << 16), h1 = __uint_as_float(p2 & 0xFFFF0000u);      // the bf16-rounded activations
+                            s0 += h0 * s_w5[col] + h1 * s_w5[col + 1];
+                            s1 += h0 * s_w5[G::NT + col] + h1 * s_w5[G::NT + col + 1];
+                            s2 += h0 * s_w5[2 * G::NT + col] + h1 * s_w5[2 * G::NT + col + 1];
+                        }
+                        if (out) *reinterpret_cast<uint4*>(out + (size_t)item * G::N + nhalf * G::NT + piece * 32 + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
+                }
+            }
+            if (item < n_items) {
+                constexpr uint32_t NTILES = G::N / G::NT;
+                head.partial[(size_t)nhalf * head.rows_padded + item] = make_float4(s0, s1, s2, 0.0f);
+                __threadfence();
+                if (atomicAdd(&head.row_count[item], 1u) == NTILES - 1u) {
+                    __threadfence();
+                    float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f;
+                    #pragma unroll
+                    for (uint32_t t = 0; t < NTILES; ++t) {
+                        const float4 p = __ldcg(&head.partial[(size_t)t * head.rows_padded + item]);
+                        q0 += p.x; q1 += p.y; q2 += p.z;
+                    }
+                    q0 += head.bias[0]; q1 += head.bias[1]; q2 += head.bias[2];
+                    if (head.q) { head.q[(size_t)item * 3] = q0; head.q[(size_t)item * 3 + 1] = q1; head.q[(size_t)item * 3 + 2] = q2; }
+                    if (head.action) head.action[item] = (uint8_t)(q1 > q0 ? (q2 > q1 ? 2 : 1) : (q2 > q0 ? 2 : 0));     // first maximum, like tf.argmax
+                    if (head.max_q) head.max_q[item] = fmaxf(q0, fmaxf(q1, q2));                                          // tf.reduce_max
+                    head.row_count[item] = 0u;                         // ready for the next forward pass
                 }
             }
         }
