@@ -479,7 +479,7 @@ def measure_qnet(q, torch, env, rb, dev, stream, actor_iter_sample):
                            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "peak_source": src,
                                         "note": "convs are shifted-window implicit GEMMs with N = 32/64: bound by the 128 B/clk shared-memory operand fetch "
                                                 "(40/48 cycles per MMA measured, tools/microbench/mma_rate.cu), not by the tensor pipe"},
-                           "kernels_per_forward": 5}
+                           "kernels_per_forward": 4}
     idx, st, nx, r, a, d = actor_iter_sample
     rew1 = torch.empty((1, n), dtype=torch.float32, device=dev); done1 = torch.empty((1, n), dtype=torch.uint8, device=dev)
 

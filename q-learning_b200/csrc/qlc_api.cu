@@ -924,19 +924,20 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
     }
     GatherParams g{}; fill_gather(env, g);
     g.indices = idx_dev; g.n_items = n;
-    CUDA_TRY(launch_pdl(qnet::qnet_locate_kernel, dim3((n + 127) / 128), dim3(128), 0, s, g, which ? 1u : 0u, q->slot_frame));
     cudaError_t e;
     const int impl = q->impl;
     if (impl >= 1) {
-        qnet::ConvArgs a{(const uint8_t*)q->w1p, q->b1, env->frames, q->slot_frame, n, q->err, q->prof};
+        // conv1's loader works out where each item's four frames are (the gather kernels' locate()) - no separate kernel
+        qnet::ConvArgs a{(const uint8_t*)q->w1p, q->b1, env->frames, g, which ? 1u : 0u, n, q->err, q->prof};
         e = impl >= 2 ? launch_conv_sw<qnet::Conv1Geom>(a, qnet::OutConv2Planes{q->a1p}, s) : launch_conv_sw<qnet::Conv1Geom>(a, qnet::OutXYC{q->a1, 20, 20, 32}, s);
     } else {
+        CUDA_TRY(launch_pdl(qnet::qnet_locate_kernel, dim3((n + 127) / 128), dim3(128), 0, s, g, which ? 1u : 0u, q->slot_frame));
         qnet::LoadConv1FromRing l1{env->frames, q->slot_frame};
         e = launch_gemm_tc<32>(l1, q->w1, q->b1, q->a1, n * 400u, 256u, 32u, 1, q->err, s);
     }
     if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv1: ") + cudaGetErrorString(e));
     if (impl >= 2) {
-        qnet::ConvArgs a{(const uint8_t*)q->w2p, q->b2, (const uint8_t*)q->a1p, nullptr, n, q->err, q->prof ? q->prof + 32 : nullptr};
+        qnet::ConvArgs a{(const uint8_t*)q->w2p, q->b2, (const uint8_t*)q->a1p, GatherParams{}, 0u, n, q->err, q->prof ? q->prof + 32 : nullptr};
         e = impl >= 3 ? launch_conv_sw<qnet::Conv2Geom>(a, qnet::OutConv3Planes{q->a2p}, s) : launch_conv_sw<qnet::Conv2Geom>(a, qnet::OutXYC{q->a2, 9, 9, 64}, s);
     } else {
         qnet::LoadConvNHWC l2{q->a1, 20, 20, 32, 9, 9, 4, 4, 2};
@@ -944,7 +945,7 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
     }
     if (e != cudaSuccess) return fail(QLC_ERR_CUDA, std::string("conv2: ") + cudaGetErrorString(e));
     if (impl >= 3) {
-        qnet::ConvArgs a{(const uint8_t*)q->w3p, q->b3, (const uint8_t*)q->a2p, nullptr, n, q->err, q->prof ? q->prof + 64 : nullptr};
+        qnet::ConvArgs a{(const uint8_t*)q->w3p, q->b3, (const uint8_t*)q->a2p, GatherParams{}, 0u, n, q->err, q->prof ? q->prof + 64 : nullptr};
         e = impl >= 4 ? launch_conv_sw<qnet::Conv3Geom>(a, qnet::OutDensePlanes{q->a3p}, s) : launch_conv_sw<qnet::Conv3Geom>(a, qnet::OutXYC{q->a3, 7, 7, 64}, s);
     } else {
         qnet::LoadConvNHWC l3{q->a2, 9, 9, 64, 7, 7, 3, 3, 1};

@@ -135,7 +135,8 @@ struct ConvArgs {
     const uint8_t* w;                // prepared weights: bf16 [K/8 planes][N][8], K = tap * (8 PL) + channel
     const float* bias;               // [N]
     const uint8_t* in;               // FROM_RING: the u8 frame ring; else the plane buffer written by the previous layer
-    const uint32_t* slot_frame;      // FROM_RING: [item][4] frame number of ring slot h, ~0u = all zero
+    GatherParams g;                  // FROM_RING: where the items are (current observations, or replay transitions by logical index)
+    uint32_t which;                  // FROM_RING: 0 = the state of the item, 1 = its state_next
     uint32_t n_items;
     unsigned int* err;
     unsigned long long* prof;        // optional (QLC_QNET_PROF): CTA 0 writes per-role cycle counters [4 roles][8]
@@ -275,13 +276,26 @@ __global__ void __launch_bounds__(G::THREADS, 1) conv_sw_kernel(ConvArgs args, O
     } else if (warp == 5) {
         // ================= bulk-copy issue =================
         if (lane == 0) {
+            // which frame of the ring holds ring slot h of an item's stack (~0u: not written yet in this episode, all zero) - the
+            // rules of the gather kernels (locate(), kernels.cuh); one or two global loads per item, issued ahead of the wait below
+            auto slot_table = [&](uint32_t item) -> uint4 {
+                uint64_t T; uint32_t e, k, rec;
+                locate(args.g, item, T, e, k, rec);
+                uint32_t f[4];
+                #pragma unroll
+                for (uint32_t h = 0; h < 4; ++h) {
+                    const uint32_t d = args.which ? ((k - h) & 3u) : (((k - h - 1u) & 3u) + 1u);
+                    f[h] = d <= k ? (uint32_t)((T - d) % args.g.time_slots) * args.g.n_envs + e : 0xFFFFFFFFu;
+                }
+                return make_uint4(f[0], f[1], f[2], f[3]);
+            };
             uint4 cur = make_uint4(0u, 0u, 0u, 0u);
-            if constexpr (G::FROM_RING) { if (blockIdx.x < n_batches) cur = __ldg(reinterpret_cast<const uint4*>(args.slot_frame) + blockIdx.x); }
+            if constexpr (G::FROM_RING) { if (blockIdx.x < n_batches) cur = slot_table(blockIdx.x); }
             for (uint32_t it = 0, bi = blockIdx.x; bi < n_batches && !*abort_flag; ++it, bi += gridDim.x) {
                 if constexpr (G::FROM_RING) {
                     const uint32_t r = it % G::NRAW, ph = (it / G::NRAW) & 1u;
-                    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);                  // the next item's slot table travels during the wait
-                    if (bi + gridDim.x < n_batches) nxt = __ldg(reinterpret_cast<const uint4*>(args.slot_frame) + bi + gridDim.x);
+                    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);                  // the next item's slot table is worked out before the wait
+                    if (bi + gridDim.x < n_batches) nxt = slot_table(bi + gridDim.x);
                     if (!wait(&raw_empty[r], ph ^ 1u, 1)) break;
                     const uint32_t fi[4] = {cur.x, cur.y, cur.z, cur.w};
                     *reinterpret_cast<uint4*>(s_slot + r * 4) = cur;         // published to the converters by the arrive below (release)
