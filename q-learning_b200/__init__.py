@@ -480,8 +480,10 @@ class ReplayBuffer:
         _check(self._L.qlc_replay_sample_host(self._env._h, batch, call_index, _np_ptr(out)))
         return out
 
-    def get_many(self, indices, layout=LAYOUT_F32_BXYH, want_state=True, want_next=True):
-        """get_many (:126-137) + batch_to_multi_dim_array for state and state_next, into host arrays."""
+    def get_many(self, indices, layout=LAYOUT_F32_BXYH, want_state=True, want_next=True, reuse=False):
+        """get_many (:126-137) + batch_to_multi_dim_array for state and state_next, into host arrays.
+        reuse=True returns views on page-locked buffers owned by this object (the device copies straight into them; valid
+        until the next get_many(reuse=True) of the same size) instead of fresh pageable arrays."""
         idx = np.ascontiguousarray(indices, dtype=np.uint32)
         n = idx.size
         if layout == LAYOUT_U8_BHYX:
@@ -490,8 +492,16 @@ class ReplayBuffer:
             shape, dt = (n, FRAME_W, FRAME_H, NUM_FRAMES), np.float32
         else:
             raise QlError("unknown layout")
-        s = np.empty(shape, dtype=dt) if want_state else None
-        sn = np.empty(shape, dtype=dt) if want_next else None
+        if reuse:
+            key = (n, layout)
+            if getattr(self, "_pinned_key", None) != key:
+                self._pinned = (PinnedArray(shape, dt), PinnedArray(shape, dt))
+                self._pinned_key = key
+            s = self._pinned[0].array if want_state else None
+            sn = self._pinned[1].array if want_next else None
+        else:
+            s = np.empty(shape, dtype=dt) if want_state else None
+            sn = np.empty(shape, dtype=dt) if want_next else None
         reward = np.empty(n, dtype=np.float32)
         action = np.empty(n, dtype=np.uint8)
         done = np.empty(n, dtype=np.uint8)

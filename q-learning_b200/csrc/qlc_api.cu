@@ -576,10 +576,14 @@ int32_t qlc_replay_gather_host(qlc_env* env, const uint32_t* idx_host, uint32_t 
     rc = qlc_replay_gather(env, (const uint32_t*)(dev + o_idx), n, layout, state_host ? dev + o_s : nullptr, next_host ? dev + o_n : nullptr,
                            (float*)(dev + o_r), dev + o_a, dev + o_d, s);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(pin + o_s, dev + o_s, total - o_s, cudaMemcpyDeviceToHost, s));
+    // the big outputs go straight into page-locked caller buffers (qlc_host_alloc); pageable ones through the pinned staging
+    const bool pin_s = state_host && is_pinned(state_host), pin_n = next_host && is_pinned(next_host);
+    if (state_host) CUDA_TRY(cudaMemcpyAsync(pin_s ? state_host : (void*)(pin + o_s), dev + o_s, ib * n, cudaMemcpyDeviceToHost, s));
+    if (next_host) CUDA_TRY(cudaMemcpyAsync(pin_n ? next_host : (void*)(pin + o_n), dev + o_n, ib * n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(pin + o_r, dev + o_r, total - o_r, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    if (state_host) memcpy(state_host, pin + o_s, ib * n);
-    if (next_host) memcpy(next_host, pin + o_n, ib * n);
+    if (state_host && !pin_s) memcpy(state_host, pin + o_s, ib * n);
+    if (next_host && !pin_n) memcpy(next_host, pin + o_n, ib * n);
     if (reward_host) memcpy(reward_host, pin + o_r, (size_t)n * 4);
     if (action_host) memcpy(action_host, pin + o_a, n);
     if (done_host) memcpy(done_host, pin + o_d, n);

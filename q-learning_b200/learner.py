@@ -111,7 +111,7 @@ class SelfDrivingQLearner:
             for _ in range(due):
                 indices = self.replay_buffer.generate_distinct_random_ids(self.batch_size, self._sample_calls)
                 self._sample_calls += 1
-                sample = self.replay_buffer.get_many(indices, LAYOUT_F32_BXYH)
+                sample = self.replay_buffer.get_many(indices, LAYOUT_F32_BXYH, reuse=True)    # page-locked buffers, overwritten by the next minibatch
                 max_future = np.asarray(self.stabilized_model.batch_predict_max_future_reward(sample.state_next), dtype=np.float32)
                 updated_q = sample.reward + max_future * np.float32(p.gamma)              # add_arrays / array_mul in f32 (:192,:298-315)
                 updated_q = np.where(sample.done != 0, sample.reward, updated_q).astype(np.float32)   # terminal steps (:195-199)
