@@ -1012,7 +1012,12 @@ int32_t qlc_qnet_forward_host(qlc_qnet* q, const uint32_t* idx_host, uint32_t n,
     CUDA_TRY(cudaStreamSynchronize(s));
     unsigned int herr = 0;
     CUDA_TRY(cudaMemcpy(&herr, q->err, 4, cudaMemcpyDeviceToHost));
-    if (herr) return fail(QLC_ERR_CUDA, "qnet: an MMA completion barrier timed out");
+    if (herr) {
+        // a pass that gave up may have left per-row tickets of the fused head behind: start the next one clean
+        if (q->head_count) cudaMemset(q->head_count, 0, (size_t)((q->cap_items + 127u) / 128u) * 128u * 4);
+        cudaMemset(q->err, 0, 4);
+        return fail(QLC_ERR_CUDA, "qnet: an MMA completion barrier timed out");
+    }
     return QLC_OK;
 }
 
