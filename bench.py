@@ -263,7 +263,8 @@ def run_b200(args, rank, local_rank, world):
         launch_ms = ms / args.steps
         achieved = BYTES_PER_ENV_STEP * n_envs * k_inner / (launch_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "env_advance_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "peak_source": peak_src, "traffic": _ncu_traffic("env_advance_kernel"),
+                    "frac": achieved / peak, "peak_source": peak_src, "frac_of_nominal_8tbs": achieved / 8000.0,   # north_star quotes the ~8 TB/s datasheet figure
+                    "traffic": _ncu_traffic("env_advance_kernel"),
                     "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n_envs * k_inner}
         if not args.no_extra:
             extra = measure_extras(q, torch, env, rb, dev, stream, peak, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
@@ -328,6 +329,7 @@ def measure_extras(q, torch, env, rb, dev, stream, peak, cpu_baseline=True):
             rate = n / (ms * 1e-3)
             res["batch%d_x%d_%s" % (batch, n_batches, name)] = {
                 "transitions_per_sec": rate, "ms_per_call": ms, "achieved_gbs": rate * bps / 1e9, "frac_of_peak": rate * bps / 1e9 / peak,
+                "frac_of_nominal_8tbs": rate * bps / 1e9 / 8000.0,
                 "bytes_per_transition": bps, "kernels_per_call": 2}
             del idx, st, nx
     out["replay_sample"] = {"metric": "sampled_transitions_per_sec", "replay_len": rb.len(), "results": res,
