@@ -120,3 +120,33 @@ def test_qnet_forward_batch_sizes(qlb, n):
     q2, _, _ = net.forward()                                               # a second pass over reused buffers gives the same bits
     assert np.array_equal(q, q2)
     net.close(); env.close()
+
+
+def test_closed_actor_loop_is_bitwise_reproducible(qlb):
+    """Q-network -> greedy action -> env step, all on the device (no host in the loop): two runs from the same seed and
+    weights end in the same bits (state, pixels, reward sum, action histogram). The fused head adds its per-tile partials
+    in tile order, so nothing in the loop depends on scheduling."""
+    torch = pytest.importorskip("torch")
+
+    def run():
+        n, iters = 300, 120
+        env = qlb.BreakoutEnvironment(n_envs=n, seed=9, replay_capacity=n * 32)
+        net = qlb.QNetwork(env, _random_weights(qlb, 5))
+        s = torch.cuda.current_stream().cuda_stream
+        acts = torch.empty((1, n), dtype=torch.uint8, device="cuda")
+        rew = torch.empty((1, n), dtype=torch.float32, device="cuda")
+        total, hist = torch.zeros((), device="cuda"), torch.zeros(3, device="cuda")
+        for _ in range(iters):
+            net.forward_device(None, n, 0, None, acts.data_ptr(), None, s)
+            env.step_device(acts.data_ptr(), 1, rew.data_ptr(), None, s)
+            total += rew.sum(); hist += torch.bincount(acts[0].long(), minlength=3).float()
+        torch.cuda.synchronize()
+        st = env.read_state()
+        out = ({k: st[k].copy() for k in st}, env.obs(qlb.LAYOUT_U8_BHYX), float(total), hist.tolist())
+        net.close(); env.close()
+        return out
+    a, b = run(), run()
+    assert a[2] == b[2] and a[3] == b[3] and np.array_equal(a[1], b[1])
+    for k in a[0]:
+        assert np.array_equal(a[0][k], b[0][k]), k
+    assert sum(a[3]) == 300 * 120 and max(a[3]) < 300 * 120      # the policy is not constant
