@@ -105,6 +105,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _config(n_envs, k_inner, replay_capacity, world):
+    """the workload both arms name: BASELINE.json configs[1] (4,096 envs on one B200) with the configs[2] replay ring behind it"""
+    return {"workload": "%d Breakout envs per GPU: step+render+84x84 u8 frame+4-frame stack append+replay insert, %d env-steps per launch, uniform random action stream" % (n_envs, k_inner),
+            "envs_per_gpu": n_envs, "steps_per_launch": k_inner, "replay_capacity": replay_capacity,
+            "l2": "each step writes %.2f GB of frames (> 126 MB L2); ring of %.1f GB" % (n_envs * k_inner * 7056 / 1e9, (replay_capacity // n_envs + 4) * n_envs * 7056 / 1e9),
+            "parallelism": "env-sharded x%d, no data-path collective" % world}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path. The Rust crate cannot be built in this image
     (no cargo/rustc; its renderer is unimplemented!()), so this times the oracle port on all host cores."""
@@ -113,7 +121,7 @@ def run_reference(args, rank, world):
     from oracle import oracle as O
     O.build()
     cores = os.cpu_count() or 1
-    sample_envs, sample_steps = ENVS_PER_GPU, 8            # bounded sample of one bench step: 4096 envs x 8 env-steps
+    sample_envs, sample_steps = args.envs, max(1, args.steps_per_launch // 8)   # bounded sample of one bench step: every env, 1/8 of its env-steps
     for _ in range(args.warmup):
         O.bench_env_steps(sample_envs, 2, SEED, cores)
     t = 0.0
@@ -121,13 +129,13 @@ def run_reference(args, rank, world):
         t += O.bench_env_steps(sample_envs, sample_steps, SEED, cores)
     units = sample_envs * sample_steps * args.steps
     value = units / t
-    sample = "each step = %d envs x %d env-steps of the same workload (1/8 of a GPU bench step), %d OpenMP threads" % (sample_envs, sample_steps, cores)
+    sample = ("each step = %d envs x %d env-steps of the same workload (1/8 of a GPU bench step: step+render+grayscale+4-frame ring+"
+              "per-step state clone, the reference's CPU path restated in C), %d OpenMP threads" % (sample_envs, sample_steps, cores))
     line = {
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "4096 Breakout envs: step+render+84x84 grayscale+4-frame stack+per-step state clone, random policy (CPU, oracle port of the reference path)",
-                   "envs": sample_envs, "steps_per_launch": sample_steps},
+        "config": _config(args.envs, args.steps_per_launch, args.replay_capacity, 1),
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -284,10 +292,7 @@ def run_b200(args, rank, local_rank, world):
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%d Breakout envs per GPU: step+render+84x84 u8 frame+4-frame stack append+replay insert, %d env-steps per launch, uniform random action stream" % (n_envs, k_inner),
-                       "envs_per_gpu": n_envs, "steps_per_launch": k_inner, "replay_capacity": args.replay_capacity,
-                       "l2": "each step writes %.2f GB of frames (> 126 MB L2); ring of %.1f GB" % (n_envs * k_inner * 7056 / 1e9, (args.replay_capacity // n_envs + 4) * n_envs * 7056 / 1e9),
-                       "parallelism": "env-sharded x%d, no data-path collective" % world},
+            "config": _config(n_envs, k_inner, args.replay_capacity, world),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": e2e_bytes[0], "d2h_bytes_per_step": e2e_bytes[1],
                     "timing": "perf_counter around %d pipelined host-buffer C-ABI steps (qlc_env_step_host_submit per step, two page-locked buffer sets, qlc_env_step_host_wait(1) + a host read of the previous step's result per step), max over ranks" % e2e_steps,
@@ -310,7 +315,7 @@ def measure_extras(q, torch, env, rb, dev, stream, peak, cpu_baseline=True):
     out = {}
     per = 4 * 84 * 84
     res = {}
-    for batch, n_batches in ((32, 1), (32, 256), (512, 16)):
+    for batch, n_batches in ((32, 1), (512, 1), (32, 256), (512, 16)):
         for layout, name, bps, dt in ((q.LAYOUT_U8_BHYX, "u8", BYTES_PER_SAMPLE_U8, torch.uint8), (q.LAYOUT_F32_BXYH, "f32", BYTES_PER_SAMPLE_F32, torch.float32)):
             n = batch * n_batches
             idx = torch.empty((n,), dtype=torch.int32, device=dev)
