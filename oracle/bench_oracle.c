@@ -81,3 +81,23 @@ double orc_bench_sample(uint32_t n_envs, size_t capacity, uint32_t batch, uint32
     free(s); free(sn); free(r); free(a); free(d); free(idx); free(actions); free(reward); free(done); orc_vec_free(v);
     return t1 - t0;
 }
+
+/* full-size parity leg (tests only): envs never interact (mechanics.rs has no shared state) and these sub-shards carry no
+ * replay, so a shard of independent envs is stepped as `n_parts` sub-shards with the same global env ids, one host thread
+ * each. actions / reward / done are [n_steps][n_total]; part p owns columns [offsets[p], offsets[p] + its n_envs). */
+void orc_parts_run(orc_vec** parts, const uint32_t* offsets, const uint32_t* sizes, int n_parts, uint32_t n_total, uint32_t n_steps,
+                   const uint8_t* actions, float* reward, uint8_t* done) {
+    #pragma omp parallel for schedule(dynamic, 1)
+    for (int p = 0; p < n_parts; ++p)
+        for (uint32_t t = 0; t < n_steps; ++t) {
+            const size_t row = (size_t)t * n_total + offsets[p];
+            orc_vec_step_range(parts[p], 0, sizes[p], actions + row, reward + row, done + row);
+        }
+}
+
+/* [n_steps][n_envs] block of the synthetic random policy stream (same values as orc_synthetic_action one by one) */
+void orc_synthetic_actions_fill(uint64_t seed, uint32_t env_id_base, uint32_t n_envs, uint32_t t0, uint32_t n_steps, uint8_t* out) {
+    #pragma omp parallel for
+    for (uint32_t t = 0; t < n_steps; ++t)
+        for (uint32_t e = 0; e < n_envs; ++e) out[(size_t)t * n_envs + e] = orc_synthetic_action(seed, env_id_base + e, t0 + t);
+}

@@ -94,6 +94,8 @@ def lib():
         L.orc_env_goal_mean.restype = C.c_float
         L.orc_bench_env_steps.restype = C.c_double
         L.orc_bench_env_steps.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, vp]
+        L.orc_parts_run.argtypes = [vp, vp, vp, C.c_int, C.c_uint32, C.c_uint32, vp, vp, vp]
+        L.orc_synthetic_actions_fill.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
         L.orc_bench_sample.restype = C.c_double
         L.orc_bench_sample.argtypes = [C.c_uint32, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint64, vp]
         for name in ("orc_collision_test_left_wall", "orc_collision_test_right_wall", "orc_collision_test_top_wall"):
@@ -112,11 +114,8 @@ def _p(a):
 
 def synthetic_actions(seed, env_id_base, n_envs, t0, n_steps):
     """[n_steps][n_envs] u8 synthetic random policy (Philox stream 'ACTI'), the bench's action stream."""
-    L = lib()
     out = np.empty((n_steps, n_envs), dtype=np.uint8)
-    for t in range(n_steps):
-        for e in range(n_envs):
-            out[t, e] = L.orc_synthetic_action(seed, env_id_base + e, t0 + t)
+    lib().orc_synthetic_actions_fill(seed, env_id_base, n_envs, t0, n_steps, _p(out))
     return out
 
 
@@ -252,6 +251,40 @@ class VecEnv:
 
     def min_episode_reward(self):
         return self.L.orc_replay_min_episode_reward(self.replay)
+
+
+class ShardedVecEnv:
+    """A shard of independent envs (no replay) split into sub-shards that keep their global env ids, stepped on one host
+    thread each — the same trajectories as one VecEnv, for full-size parity runs (4,096 envs x 10,000 steps)."""
+
+    def __init__(self, n_envs, seed=0, env_id_base=0, parts=None):
+        parts = max(1, min(n_envs, parts or 4 * (os.cpu_count() or 1)))
+        self.n = n_envs
+        bounds = [n_envs * p // parts for p in range(parts + 1)]
+        self.offsets = np.array(bounds[:-1], dtype=np.uint32)
+        self.sizes = np.array([bounds[p + 1] - bounds[p] for p in range(parts)], dtype=np.uint32)
+        self.parts = [VecEnv(int(self.sizes[p]), seed=seed, env_id_base=env_id_base + int(self.offsets[p])) for p in range(parts)]
+        self.handles = (C.c_void_p * parts)(*[v.h for v in self.parts])
+
+    def run(self, actions):
+        """actions [T][n] -> reward [T][n] f32, done [T][n] u8"""
+        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        assert a.ndim == 2 and a.shape[1] == self.n
+        reward = np.empty(a.shape, dtype=np.float32)
+        done = np.empty(a.shape, dtype=np.uint8)
+        lib().orc_parts_run(self.handles, _p(self.offsets), _p(self.sizes), len(self.parts), self.n, a.shape[0], _p(a), _p(reward), _p(done))
+        return reward, done
+
+    def state(self):
+        st = [v.state() for v in self.parts]
+        return {k: np.concatenate([s[k] for s in st]) for k in st[0]}
+
+    def obs_u8(self):
+        return np.concatenate([v.obs_u8() for v in self.parts])
+
+    def close(self):
+        for v in self.parts:
+            v.close()
 
 
 def bench_env_steps(n_envs, n_steps, seed=1, threads=1):

@@ -176,3 +176,23 @@ def test_episode_window(O):
     assert env.avg_episode_reward() == pytest.approx(float(np.float32(w.sum()) / 5))
     assert env.min_episode_reward() == w.min()
     env.close()
+
+
+def test_sharded_vec_env_equals_one_vec_env(O):
+    """oracle.ShardedVecEnv (the threaded full-size parity leg) is the single VecEnv bit for bit; the block action fill equals
+    the one-by-one stream."""
+    n, T, seed = 203, 260, 17
+    acts = O.synthetic_actions(seed, 40, n, 3, T)
+    L = O.lib()
+    for t, e in ((0, 0), (5, 77), (T - 1, n - 1)):
+        assert acts[t, e] == L.orc_synthetic_action(seed, 40 + e, 3 + t)
+    one, many = O.VecEnv(n, seed=seed, env_id_base=40), O.ShardedVecEnv(n, seed=seed, env_id_base=40, parts=6)
+    r2, d2 = many.run(acts)
+    for t in range(T):
+        r, d = one.step(acts[t])
+        assert np.array_equal(r, r2[t]) and np.array_equal(d, d2[t])
+    a, b = one.state(), many.state()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(one.obs_u8(), many.obs_u8()) and d2.sum() > 0
+    one.close(); many.close()
