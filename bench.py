@@ -264,6 +264,7 @@ def run_b200(args, rank, local_rank, world):
     e2e_check += float(r_host.sum()) + float(pr2.array.sum())          # the read-back results are consumed on the host
     e2e_sync_value = units_per_step * e2e_steps / dt_sync
 
+    loops = {} if args.no_extra else measure_actor_loops(q, torch, dist if distributed else None, env, rb, dev, stream, world, barrier)
     extra = {}
     cpu_baseline = None
     if rank == 0:
@@ -303,11 +304,70 @@ def run_b200(args, rank, local_rank, world):
             "env_error_flags": env.error_flags(),
         }
         line.update(extra)
+        line.update(loops)
         print(json.dumps(line), flush=True)
     env.close()
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def measure_actor_loops(q, torch, dist, env, rb, dev, stream, world, barrier):
+    """BASELINE configs[4] without the (out-of-scope) learner, on EVERY rank (env + replay shards, no data-path collective),
+    device-timed, max over ranks:
+    (1) actor_loop: per iteration a fresh action batch from a device-side policy stand-in (uniform random, like the learner's
+        first 50k steps), ONE env-step launch, and on every 4th step (the learner's gate, self_driving_tf_q_learner.rs:181) a
+        distinct-index sample + f32 [32,84,84,4] s/s' gather;
+    (2) actor_loop_qnet: the same with the greedy action of the tcgen05 Q-network forward over all envs (closed loop on the GPU)."""
+    per = 4 * 84 * 84
+    n = env.n_envs
+    idx = torch.empty((32,), dtype=torch.int32, device=dev)
+    st = torch.empty((32, per), dtype=torch.float32, device=dev); nx = torch.empty((32, per), dtype=torch.float32, device=dev)
+    r = torch.empty((32,), dtype=torch.float32, device=dev); a = torch.empty((32,), dtype=torch.uint8, device=dev); d = torch.empty((32,), dtype=torch.uint8, device=dev)
+    rew1 = torch.empty((1, n), dtype=torch.float32, device=dev); done1 = torch.empty((1, n), dtype=torch.uint8, device=dev)
+    acts = torch.empty((1, n), dtype=torch.uint8, device=dev)
+    net = q.QNetwork(env, _random_qnet_weights(q))
+
+    def sample_every_4th(i):
+        if rb.should_sample(i, rb.len(), 32):
+            rb.sample_device(32, 1, i, idx.data_ptr(), stream)
+            rb.gather_device(idx.data_ptr(), 32, q.LAYOUT_F32_BXYH, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
+
+    def iter_random(i):
+        ra = torch.randint(0, 3, (1, n), dtype=torch.uint8, device=dev)
+        env.step_device(ra.data_ptr(), 1, rew1.data_ptr(), done1.data_ptr(), stream)
+        sample_every_4th(i)
+
+    def iter_qnet(i):
+        net.forward_device(None, n, 0, None, acts.data_ptr(), None, stream)                      # predict_action for every env
+        env.step_device(acts.data_ptr(), 1, rew1.data_ptr(), done1.data_ptr(), stream)
+        sample_every_4th(i)
+
+    res = []
+    for fn, iters in ((iter_random, 400), (iter_qnet, 200)):
+        for i in range(8):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        barrier()
+        res.append(e0.elapsed_time(e1) / iters)
+    net.close()
+    if world > 1:
+        t = torch.tensor(res, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res = [float(x) for x in t.tolist()]
+    scope = "%d GPU(s), %d envs each, slowest rank" % (world, n)
+    return {
+        "actor_loop": {"env_steps_per_sec": world * n / (res[0] * 1e-3), "minibatches_per_sec": world * 0.25 / (res[0] * 1e-3), "us_per_iteration": res[0] * 1e3, "n_gpus": world,
+                       "note": "1 step launch per iteration (actions from a device-side random policy), sample+gather B=32 f32 every 4th step; no learner; " + scope},
+        "actor_loop_qnet": {"env_steps_per_sec": world * n / (res[1] * 1e-3), "minibatches_per_sec": world * 0.25 / (res[1] * 1e-3), "us_per_iteration": res[1] * 1e3, "n_gpus": world,
+                            "qnet_tflops_per_gpu": QNET_FLOP_PER_OBS * n / (res[1] * 1e-3) / 1e12,
+                            "note": "closed loop on the GPU: Q-network forward (greedy action for all envs) -> 1 env-step launch -> sample+gather B=32 f32 every 4th step; no learner; " + scope},
+    }
 
 
 def measure_extras(q, torch, env, rb, dev, stream, peak, cpu_baseline=True):
@@ -336,10 +396,17 @@ def measure_extras(q, torch, env, rb, dev, stream, peak, cpu_baseline=True):
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
             rate = n / (ms * 1e-3)
+            # the gather kernel alone (indices of the last sample call): its own roofline, without the latency-bound sample kernel
+            e0.record()
+            for c in range(reps):
+                rb.gather_device(idx.data_ptr(), n, layout, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
+            e1.record(); torch.cuda.synchronize()
+            ms_g = e0.elapsed_time(e1) / reps
             res["batch%d_x%d_%s" % (batch, n_batches, name)] = {
                 "transitions_per_sec": rate, "ms_per_call": ms, "achieved_gbs": rate * bps / 1e9, "frac_of_peak": rate * bps / 1e9 / peak,
                 "frac_of_nominal_8tbs": rate * bps / 1e9 / 8000.0,
-                "bytes_per_transition": bps, "kernels_per_call": 2}
+                "bytes_per_transition": bps, "kernels_per_call": 2,
+                "gather_kernel_alone": {"ms_per_launch": ms_g, "achieved_gbs": n * bps / (ms_g * 1e-3) / 1e9, "frac_of_peak": n * bps / (ms_g * 1e-3) / 1e9 / peak}}
             del idx, st, nx
     out["replay_sample"] = {"metric": "sampled_transitions_per_sec", "replay_len": rb.len(), "results": res,
                             "note": "sample (Philox distinct ids) + gather (s and s' stacks) on device buffers; minibatches per call = the x factor"}
@@ -410,34 +477,7 @@ def measure_extras(q, torch, env, rb, dev, stream, peak, cpu_baseline=True):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 500
     out["single_step_launch"] = {"env_steps_per_sec": env.n_envs / (ms * 1e-3), "us_per_launch": ms * 1e3}
-    # actor-loop shape of BASELINE configs[4] without the (out-of-scope) learner: per iteration a fresh action batch from a
-    # device-side policy stand-in (uniform random, like the learner's first 50k steps), ONE env-step launch, and on every
-    # 4th step (the learner's gate, self_driving_tf_q_learner.rs:181) a distinct-index sample + f32 [32,84,84,4] s/s' gather.
-    n = env.n_envs
-    idx = torch.empty((32,), dtype=torch.int32, device=dev)
-    st = torch.empty((32, per), dtype=torch.float32, device=dev); nx = torch.empty((32, per), dtype=torch.float32, device=dev)
-    r = torch.empty((32,), dtype=torch.float32, device=dev); a = torch.empty((32,), dtype=torch.uint8, device=dev); d = torch.empty((32,), dtype=torch.uint8, device=dev)
-    rew1 = torch.empty((1, n), dtype=torch.float32, device=dev); done1 = torch.empty((1, n), dtype=torch.uint8, device=dev)
-
-    def actor_iter(i):
-        acts = torch.randint(0, 3, (1, n), dtype=torch.uint8, device=dev)
-        env.step_device(acts.data_ptr(), 1, rew1.data_ptr(), done1.data_ptr(), stream)
-        if rb.should_sample(i, rb.len(), 32):
-            rb.sample_device(32, 1, i, idx.data_ptr(), stream)
-            rb.gather_device(idx.data_ptr(), 32, q.LAYOUT_F32_BXYH, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
-    for i in range(8):
-        actor_iter(i)
-    torch.cuda.synchronize()
-    iters = 400
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        actor_iter(i)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    out["actor_loop"] = {"env_steps_per_sec": n / (ms * 1e-3), "minibatches_per_sec": 0.25 / (ms * 1e-3), "us_per_iteration": ms * 1e3,
-                         "note": "1 step launch per iteration (actions from a device-side random policy), sample+gather B=32 f32 every 4th step; no learner"}
-    out.update(measure_qnet(q, torch, env, rb, dev, stream, actor_iter_sample=(idx, st, nx, r, a, d)))
+    out.update(measure_qnet(q, torch, env, dev, stream))
     return out
 
 
@@ -464,10 +504,9 @@ def _random_qnet_weights(q, seed=7):
     return w
 
 
-def measure_qnet(q, torch, env, rb, dev, stream, actor_iter_sample):
-    """the Q-network forward on tcgen05 (predict_action for every env, straight from the frame ring) and the
-    closed actor loop of BASELINE configs[4]: greedy action from the network -> ONE env-step launch -> every 4th step a
-    minibatch sample + gather. Random-init weights of the reference architecture (no checkpoints here)."""
+def measure_qnet(q, torch, env, dev, stream):
+    """the Q-network forward on tcgen05 (predict_action for every env, straight from the frame ring).
+    Random-init weights of the reference architecture (no checkpoints here)."""
     out = {}
     w = _random_qnet_weights(q)
     net = q.QNetwork(env, w)
@@ -491,26 +530,6 @@ def measure_qnet(q, torch, env, rb, dev, stream, actor_iter_sample):
                                         "note": "convs are shifted-window implicit GEMMs with N = 32/64: bound by the 128 B/clk shared-memory operand fetch "
                                                 "(40/48 cycles per MMA measured, tools/microbench/mma_rate.cu), not by the tensor pipe"},
                            "kernels_per_forward": 4}
-    idx, st, nx, r, a, d = actor_iter_sample
-    rew1 = torch.empty((1, n), dtype=torch.float32, device=dev); done1 = torch.empty((1, n), dtype=torch.uint8, device=dev)
-
-    def actor_iter(i):
-        net.forward_device(None, n, 0, None, acts.data_ptr(), None, stream)                      # predict_action for every env
-        env.step_device(acts.data_ptr(), 1, rew1.data_ptr(), done1.data_ptr(), stream)
-        if rb.should_sample(i, rb.len(), 32):
-            rb.sample_device(32, 1, i, idx.data_ptr(), stream)
-            rb.gather_device(idx.data_ptr(), 32, q.LAYOUT_F32_BXYH, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
-    for i in range(8):
-        actor_iter(i)
-    torch.cuda.synchronize()
-    iters = 200
-    e0.record()
-    for i in range(iters):
-        actor_iter(i)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    out["actor_loop_qnet"] = {"env_steps_per_sec": n / (ms * 1e-3), "minibatches_per_sec": 0.25 / (ms * 1e-3), "us_per_iteration": ms * 1e3,
-                              "note": "closed loop on the GPU: Q-network forward (greedy action for all %d envs) -> 1 env-step launch -> sample+gather B=32 f32 every 4th step; no learner" % n}
     net.close()
     return out
 
