@@ -312,7 +312,9 @@ int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps,
     const uint32_t sms = (uint32_t)env->sm_count;
     if (cfg == 0) {
         if (n_steps >= 8u && p.n_envs >= sms * 16u && p.n_envs <= sms * 96u) { cfg = 5; chunk = n_steps / 4u; chunk = chunk < 4u ? 4u : (chunk > 16u ? 16u : chunk); }
-        else cfg = (p.n_envs <= sms * 32u || n_steps < 4u) ? 1 : 5;
+        else if (n_steps < 4u) cfg = p.n_envs <= sms * 20u ? 5 : 2;    // learner-driven launches (latency bound; tools/step_latency_ab.py): 8-env batches
+                                                                        // while they fit one resident wave, else 16-env batches, 2 CTAs per SM
+        else cfg = p.n_envs <= sms * 32u ? 1 : 5;
     }
     switch (cfg) {
         case 1: rc = launch_advance<8, 4, 4, 1>(env, p, s, chunk); break;    // <= 32 envs / batch, 1 CTA / SM
