@@ -471,7 +471,20 @@ def test_replay_config_1m_transitions(qlb, O):
         f = rb.get_many(idx[:16], qlb.LAYOUT_F32_BXYH)
         assert np.array_equal(f.state, np.transpose(g.state[:16], (0, 3, 2, 1)).astype(np.float32))
         assert np.array_equal(f.state_next, np.transpose(g.state_next[:16], (0, 3, 2, 1)).astype(np.float32))
-    # whole envs against the oracle FIFO (capacity t_cap for a single env == the same time window)
+    # EVERY row of a sampled minibatch of 512 against the oracle: the env of each sampled row is replayed on the CPU with a
+    # FIFO of the same time window (capacity t_cap for a single env), its row j = idx // n gathered there
+    idx = rb.generate_distinct_random_ids(512, 9)
+    g = rb.get_many(idx, qlb.LAYOUT_U8_BHYX)
+    for e in np.unique(idx % n):
+        rows = np.nonzero(idx % n == e)[0]
+        o = O.VecEnv(1, seed=seed, env_id_base=int(e), replay_capacity=t_cap)
+        for t in range(T):
+            o.step(acts[t, e:e + 1])
+        og = o.get_many((idx[rows] // n).astype(np.uint32), "u8")
+        assert np.array_equal(g.state[rows], og["state"]) and np.array_equal(g.state_next[rows], og["state_next"]), "env %d" % e
+        assert np.array_equal(g.reward[rows], og["reward"]) and np.array_equal(g.action[rows], og["action"]) and np.array_equal(g.done[rows], og["done"])
+        o.close()
+    # whole envs against the oracle FIFO
     for e in (0, 1777, n - 1):
         o = O.VecEnv(1, seed=seed, env_id_base=e, replay_capacity=t_cap)
         for t in range(T):
@@ -550,27 +563,29 @@ def test_checkpoint_resume_is_bit_identical(qlb, O, tmp_path):
 
 
 def test_shard_of_65536_envs(qlb, O):
-    """BASELINE configs[3] shard size: 65,536 envs on one GPU (multi-wave, unchunked 8-env batches) — spot-checked envs
-    against the oracle, frame values, statistics identities, replay chaining."""
-    n, seed, k = 65536, 909, 48
-    env = qlb.BreakoutEnvironment(n_envs=n, seed=seed, env_id_base=1_000_000, replay_capacity=n * 16)
+    """BASELINE configs[3] shard size: 65,536 envs on one GPU (multi-wave launches, a single-step launch in between), EVERY env
+    against the oracle (threaded sub-shards with the same global env ids): reward / done of all 3.1e6 env-steps, the complete
+    final state and the 4-frame stacks of all envs; then statistics identities and replay chaining on the 1 M-transition ring."""
+    n, seed, k, base = 65536, 909, 48, 1_000_000
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=seed, env_id_base=base, replay_capacity=n * 16)
     rb = qlb.ReplayBuffer(env)
+    ora = O.ShardedVecEnv(n, seed=seed, env_id_base=base)
     rng = np.random.default_rng(12)
     acts = rng.integers(0, 3, size=(k, n), dtype=np.uint8)
     reward, done = env.step_many(acts[:16])
-    r2, d2 = env.step_many(acts[16:17])          # a single-step launch in between (32-env batches)
+    r2, d2 = env.step_many(acts[16:17])          # a single-step launch in between
     r3, d3 = env.step_many(acts[17:])
     reward = np.concatenate([reward, r2, r3]); done = np.concatenate([done, d2, d3])
+    ro, do = ora.run(acts)
+    bad = np.nonzero((reward != ro) | (done != do))
+    assert bad[0].size == 0, "reward/done differ first at step %d env %d" % (bad[0][0], bad[1][0])
     st = env.read_state()
-    for e in (0, 7, 4095, 32768, 65535):
-        o = O.VecEnv(1, seed=seed, env_id_base=1_000_000 + e)
-        for t in range(k):
-            r, d = o.step(acts[t, e:e + 1])
-            assert r[0] == reward[t, e] and d[0] == done[t, e], (e, t)
-        so = o.state()
-        for key in STATE_F32 + STATE_INT:
-            assert so[key][0] == st[key][e], (key, e)
-        o.close()
+    _assert_state_equal(st, ora.state(), "65536 envs", nan_ok=True)
+    obs = env.obs(qlb.LAYOUT_U8_BHYX)
+    for part, off, size in zip(ora.parts, ora.offsets, ora.sizes):           # part by part: the stacks are 1.85 GB per side
+        assert np.array_equal(obs[int(off):int(off) + int(size)], part.obs_u8()), "frame stacks differ in envs %d.." % off
+    del obs
+    ora.close()
     s = env.stats()
     assert s["steps"] == n * k and s["episodes"] == int(done.sum())
     assert s["sum_return"] + int(st["score"].sum()) == int(reward.sum())
