@@ -264,6 +264,7 @@ def run_b200(args, rank, local_rank, world):
     e2e_check += float(r_host.sum()) + float(pr2.array.sum())          # the read-back results are consumed on the host
     e2e_sync_value = units_per_step * e2e_steps / dt_sync
 
+    replay = None if args.no_extra else measure_replay_sampling(q, torch, dist if distributed else None, rb, dev, stream, world, barrier)
     loops = {} if args.no_extra else measure_actor_loops(q, torch, dist if distributed else None, env, rb, dev, stream, world, barrier)
     extra = {}
     cpu_baseline = None
@@ -276,7 +277,7 @@ def run_b200(args, rank, local_rank, world):
                     "traffic": _ncu_traffic("env_advance_kernel"),
                     "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n_envs * k_inner}
         if not args.no_extra:
-            extra = measure_extras(q, torch, env, rb, dev, stream, peak, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+            extra = measure_extras(q, torch, env, rb, dev, stream, peak, replay, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             O.build()
@@ -370,11 +371,13 @@ def measure_actor_loops(q, torch, dist, env, rb, dev, stream, world, barrier):
     }
 
 
-def measure_extras(q, torch, env, rb, dev, stream, peak, cpu_baseline=True):
-    """Secondary numbers in the same run: replay sampling (configs[2]) and the 65,536-env shard (configs[3])."""
-    out = {}
+def measure_replay_sampling(q, torch, dist, rb, dev, stream, world, barrier):
+    """BASELINE configs[2] on EVERY rank (one replay shard per GPU, no cross-GPU gather): Philox distinct-index sample + gather of
+    the s and s' frame stacks into device buffers, u8 [b][slot][y][x] and the reference's f32 [b][x][y][slot]; device-timed,
+    max over ranks, whole-job transitions/s. The gather kernel is also timed alone (its own roofline, without the latency-bound
+    sample kernel; indices of the last sample call, 8,192 transitions read 289 MB of frames > L2)."""
     per = 4 * 84 * 84
-    res = {}
+    keys, times = [], []
     for batch, n_batches in ((32, 1), (512, 1), (32, 256), (512, 16)):
         for layout, name, bps, dt in ((q.LAYOUT_U8_BHYX, "u8", BYTES_PER_SAMPLE_U8, torch.uint8), (q.LAYOUT_F32_BXYH, "f32", BYTES_PER_SAMPLE_F32, torch.float32)):
             n = batch * n_batches
@@ -382,34 +385,74 @@ def measure_extras(q, torch, env, rb, dev, stream, peak, cpu_baseline=True):
             st = torch.empty((n, per), dtype=dt, device=dev); nx = torch.empty((n, per), dtype=dt, device=dev)
             r = torch.empty((n,), dtype=torch.float32, device=dev); a = torch.empty((n,), dtype=torch.uint8, device=dev); d = torch.empty((n,), dtype=torch.uint8, device=dev)
 
+            def gather():
+                rb.gather_device(idx.data_ptr(), n, layout, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
+
             def once(c):
                 rb.sample_device(batch, n_batches, c, idx.data_ptr(), stream)
-                rb.gather_device(idx.data_ptr(), n, layout, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
+                gather()
             for c in range(3):
                 once(c)
-            torch.cuda.synchronize()
             reps = 30
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
             e0.record()
             for c in range(reps):
                 once(10 + c)
-            e1.record(); torch.cuda.synchronize()
+            e1.record()
+            barrier()
             ms = e0.elapsed_time(e1) / reps
-            rate = n / (ms * 1e-3)
-            # the gather kernel alone (indices of the last sample call): its own roofline, without the latency-bound sample kernel
             e0.record()
             for c in range(reps):
-                rb.gather_device(idx.data_ptr(), n, layout, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
-            e1.record(); torch.cuda.synchronize()
-            ms_g = e0.elapsed_time(e1) / reps
-            res["batch%d_x%d_%s" % (batch, n_batches, name)] = {
-                "transitions_per_sec": rate, "ms_per_call": ms, "achieved_gbs": rate * bps / 1e9, "frac_of_peak": rate * bps / 1e9 / peak,
-                "frac_of_nominal_8tbs": rate * bps / 1e9 / 8000.0,
-                "bytes_per_transition": bps, "kernels_per_call": 2,
-                "gather_kernel_alone": {"ms_per_launch": ms_g, "achieved_gbs": n * bps / (ms_g * 1e-3) / 1e9, "frac_of_peak": n * bps / (ms_g * 1e-3) / 1e9 / peak}}
+                gather()
+            e1.record()
+            barrier()
+            keys.append((batch, n_batches, name, bps, n))
+            times += [ms, e0.elapsed_time(e1) / reps]
             del idx, st, nx
-    out["replay_sample"] = {"metric": "sampled_transitions_per_sec", "replay_len": rb.len(), "results": res,
-                            "note": "sample (Philox distinct ids) + gather (s and s' stacks) on device buffers; minibatches per call = the x factor"}
+    # end to end through the reference-facing host calls (generate_distinct_random_ids -> get_many + batch_to_multi_dim_array into
+    # page-locked host arrays the caller reads): index D2H, gather kernel, D2H of both stacks and the scalars, every call
+    host_keys, host_check = [], 0.0
+    for batch in (32, 512):
+        for layout, name, isz in ((q.LAYOUT_U8_BHYX, "u8", 1), (q.LAYOUT_F32_BXYH, "f32", 4)):
+            for c in range(3):
+                rb.get_many(rb.generate_distinct_random_ids(batch, c), layout, reuse=True)
+            barrier()
+            reps = 20
+            t0 = time.perf_counter()
+            for c in range(reps):
+                g = rb.get_many(rb.generate_distinct_random_ids(batch, 100 + c), layout, reuse=True)
+                host_check += float(g.reward.sum()) + float(g.state_next[batch - 1].ravel()[-1])
+            times.append((time.perf_counter() - t0) / reps * 1e3)
+            host_keys.append((batch, name, batch * (2 * per * isz + 4 + 1 + 1 + 4)))
+    if world > 1:
+        t = torch.tensor(times, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times = [float(x) for x in t.tolist()]
+    peak, _ = _peaks()
+    res = {}
+    e2e_host = {}
+    for i, (batch, name, d2h) in enumerate(host_keys):
+        ms = times[2 * len(keys) + i]
+        e2e_host["batch%d_%s" % (batch, name)] = {"transitions_per_sec": world * batch / (ms * 1e-3), "ms_per_minibatch": ms, "d2h_bytes_per_minibatch": d2h,
+                                                   "d2h_gbs_per_gpu": d2h / (ms * 1e-3) / 1e9}
+    for i, (batch, n_batches, name, bps, n) in enumerate(keys):
+        ms, ms_g = times[2 * i], times[2 * i + 1]
+        rate = n / (ms * 1e-3)                       # per GPU, slowest rank
+        res["batch%d_x%d_%s" % (batch, n_batches, name)] = {
+            "transitions_per_sec": world * rate, "ms_per_call": ms, "achieved_gbs_per_gpu": rate * bps / 1e9, "frac_of_peak": rate * bps / 1e9 / peak,
+            "frac_of_nominal_8tbs": rate * bps / 1e9 / 8000.0, "bytes_per_transition": bps, "kernels_per_call": 2,
+            "gather_kernel_alone": {"ms_per_launch": ms_g, "achieved_gbs_per_gpu": n * bps / (ms_g * 1e-3) / 1e9, "frac_of_peak": n * bps / (ms_g * 1e-3) / 1e9 / peak}}
+    return {"metric": "sampled_transitions_per_sec", "n_gpus": world, "replay_len_per_gpu": rb.len(), "results": res,
+            "e2e_host": dict(e2e_host, timing="perf_counter around ReplayBuffer.generate_distinct_random_ids + get_many(reuse=True) per minibatch (host index array in, "
+                                              "page-locked host stacks out, read on the host), max over ranks; bound by the D2H copy of the stacks", result_checksum=host_check),
+            "note": "sample (Philox distinct ids) + gather (s and s' stacks) on device buffers, every rank on its own replay shard, max over ranks; "
+                    "transitions_per_sec is the whole job, GB/s and fractions are per GPU; minibatches per call = the x factor"}
+
+
+def measure_extras(q, torch, env, rb, dev, stream, peak, replay, cpu_baseline=True):
+    """Secondary numbers in the same run (rank 0): the CPU baseline of the replay path and the 65,536-env shard (configs[3])."""
+    out = {"replay_sample": replay}
     if cpu_baseline:
         # the reference's replay path on the host (ReplayBuffer::get_many + batch_to_multi_dim_array for state and state_next,
         # generate_distinct_random_ids), single-threaded like the reference learner; bounded sample
