@@ -26,7 +26,7 @@ def child():
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     child(); sys.exit(0)
-cases = [({"QLC_ADVANCE_CFG": str(c)}, n, n * 16) for n in (256, 1024, 2368, 4096, 8192, 16384, 65536) for c in (1, 2, 3, 4, 5, 6)]
+cases = [({"QLC_ADVANCE_CFG": str(c)}, n, n * 16) for n in (1024, 4096, 16384, 65536) for c in (1, 2, 5)]
 if len(sys.argv) > 1 and sys.argv[1] == "breakdown":
     cases = [({}, 4096, 4096 * 16), ({}, 4096, 1 << 20), ({"QLC_STEP_PDL": "0"}, 4096, 1 << 20),
              ({"QLC_DEBUG_SKIP": "1"}, 4096, 1 << 20), ({"QLC_DEBUG_SKIP": "2"}, 4096, 1 << 20),
