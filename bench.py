@@ -407,8 +407,33 @@ def measure_replay_sampling(q, torch, dist, rb, dev, stream, world, barrier):
                 gather()
             e1.record()
             barrier()
+            ms_g = e0.elapsed_time(e1) / reps
+            # sampling of call c+1 on a second stream while call c is gathered (two index buffers): hides the latency-bound sample kernel
+            ms_p = 0.0
+            if n_batches > 1:
+                side = torch.cuda.Stream(device=dev)
+                main = torch.cuda.current_stream()
+                idx2 = (idx, torch.empty_like(idx))
+                ev_s = (torch.cuda.Event(), torch.cuda.Event()); ev_g = (torch.cuda.Event(), torch.cuda.Event())
+                side.wait_stream(main)
+                rb.sample_device(batch, n_batches, 50, idx2[0].data_ptr(), side.cuda_stream); ev_s[0].record(side)
+                barrier()
+                e0.record()
+                for c in range(reps):
+                    cur = c & 1
+                    if c >= 1:
+                        side.wait_event(ev_g[1 - cur])           # gather c-1 has read the buffer the next sample overwrites
+                    rb.sample_device(batch, n_batches, 51 + c, idx2[1 - cur].data_ptr(), side.cuda_stream); ev_s[1 - cur].record(side)
+                    main.wait_event(ev_s[cur])
+                    rb.gather_device(idx2[cur].data_ptr(), n, layout, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
+                    ev_g[cur].record(main)
+                e1.record()
+                barrier()
+                ms_p = e0.elapsed_time(e1) / reps
+                side.synchronize()
+                del idx2
             keys.append((batch, n_batches, name, bps, n))
-            times += [ms, e0.elapsed_time(e1) / reps]
+            times += [ms, ms_g, ms_p]
             del idx, st, nx
     # end to end through the reference-facing host calls (generate_distinct_random_ids -> get_many + batch_to_multi_dim_array into
     # page-locked host arrays the caller reads): index D2H, gather kernel, D2H of both stacks and the scalars, every call
@@ -433,16 +458,19 @@ def measure_replay_sampling(q, torch, dist, rb, dev, stream, world, barrier):
     res = {}
     e2e_host = {}
     for i, (batch, name, d2h) in enumerate(host_keys):
-        ms = times[2 * len(keys) + i]
+        ms = times[3 * len(keys) + i]
         e2e_host["batch%d_%s" % (batch, name)] = {"transitions_per_sec": world * batch / (ms * 1e-3), "ms_per_minibatch": ms, "d2h_bytes_per_minibatch": d2h,
                                                    "d2h_gbs_per_gpu": d2h / (ms * 1e-3) / 1e9}
     for i, (batch, n_batches, name, bps, n) in enumerate(keys):
-        ms, ms_g = times[2 * i], times[2 * i + 1]
+        ms, ms_g, ms_p = times[3 * i], times[3 * i + 1], times[3 * i + 2]
         rate = n / (ms * 1e-3)                       # per GPU, slowest rank
         res["batch%d_x%d_%s" % (batch, n_batches, name)] = {
             "transitions_per_sec": world * rate, "ms_per_call": ms, "achieved_gbs_per_gpu": rate * bps / 1e9, "frac_of_peak": rate * bps / 1e9 / peak,
             "frac_of_nominal_8tbs": rate * bps / 1e9 / 8000.0, "bytes_per_transition": bps, "kernels_per_call": 2,
             "gather_kernel_alone": {"ms_per_launch": ms_g, "achieved_gbs_per_gpu": n * bps / (ms_g * 1e-3) / 1e9, "frac_of_peak": n * bps / (ms_g * 1e-3) / 1e9 / peak}}
+        if ms_p > 0.0:
+            res["batch%d_x%d_%s" % (batch, n_batches, name)]["sample_prefetched_on_second_stream"] = {
+                "transitions_per_sec": world * n / (ms_p * 1e-3), "ms_per_call": ms_p, "frac_of_peak": n * bps / (ms_p * 1e-3) / 1e9 / peak}
     return {"metric": "sampled_transitions_per_sec", "n_gpus": world, "replay_len_per_gpu": rb.len(), "results": res,
             "e2e_host": dict(e2e_host, timing="perf_counter around ReplayBuffer.generate_distinct_random_ids + get_many(reuse=True) per minibatch (host index array in, "
                                               "page-locked host stacks out, read on the host), max over ranks; bound by the D2H copy of the stacks", result_checksum=host_check),
