@@ -75,7 +75,7 @@ def kernels(tag, reps):
             per_kernel.setdefault(name, []).append(d)
     for name, ds in per_kernel.items():
         out += ["## `%s` (%d captured launches, source: %s)" % (name, len(ds), ", ".join(os.path.basename(r) for r in reps)), "",
-                "| launch | grid x block | duration us | dram read MB | dram write MB | dram %% of peak | SM %% | warps active %% | regs | tensor pipe active %% |", "|---|---|---:|---:|---:|---:|---:|---:|---:|---:|"]
+                "| launch | grid x block | duration us | dram read MB | dram write MB | dram % of peak | SM % | warps active % | regs | tensor pipe active % |", "|---|---|---:|---:|---:|---:|---:|---:|---:|---:|"]
         for i, d in enumerate(ds):
             out.append("| %d | %s x %s | %.1f | %.2f | %.2f | %.1f | %.1f | %.1f | %d | %.1f |" % (
                 i, d.get("grid", ""), d.get("block", ""), d.get("gpu__time_duration.sum", 0), d.get("dram__bytes_read.sum", 0) / 1e6, d.get("dram__bytes_write.sum", 0) / 1e6,
