@@ -242,6 +242,30 @@ def test_replay_parity(qlb, O, n_envs, capacity, steps):
     env.close()
 
 
+
+def test_host_gather_into_page_locked_buffers(qlb, O):
+    """get_many(reuse=True): the stacks are copied straight into page-locked host arrays owned by the ReplayBuffer — same bytes as
+    the pageable path and as the oracle, both layouts, changing batch sizes."""
+    n, seed, steps = 48, 19, 70
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=seed, replay_capacity=n * 32)
+    rb = qlb.ReplayBuffer(env)
+    ora = O.VecEnv(n, seed=seed, replay_capacity=n * 32)
+    acts = O.synthetic_actions(seed, 0, n, 0, steps)
+    env.step_many(acts)
+    for t in range(steps):
+        ora.step(acts[t])
+    for batch, call in ((32, 0), (7, 1), (32, 2), (200, 3)):
+        idx = rb.generate_distinct_random_ids(batch, call)
+        for layout, name in ((qlb.LAYOUT_U8_BHYX, "u8"), (qlb.LAYOUT_F32_BXYH, "f32")):
+            g = rb.get_many(idx, layout, reuse=True)
+            h = rb.get_many(idx, layout)
+            o = ora.get_many(idx, name)
+            assert np.array_equal(g.state, o["state"]) and np.array_equal(g.state_next, o["state_next"])
+            assert np.array_equal(g.state, h.state) and np.array_equal(g.state_next, h.state_next)
+            assert np.array_equal(g.reward, o["reward"]) and np.array_equal(g.action, o["action"]) and np.array_equal(g.done, o["done"])
+    env.close(); ora.close()
+
+
 @pytest.mark.parametrize("length_steps,batch", [(40, 32), (5, 32), (200, 512), (33, 1024)])
 def test_sampler_parity(qlb, O, length_steps, batch):
     """generate_distinct_random_ids: distinct, in range (the reference's own property test :346-361) and equal to
