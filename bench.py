@@ -482,6 +482,13 @@ def measure_extras(q, torch, env, rb, dev, stream, peak, replay, cpu_baseline=Tr
     """Secondary numbers in the same run (rank 0): the CPU baseline of the replay path and the 65,536-env shard (configs[3])."""
     out = {"replay_sample": replay}
     if cpu_baseline:
+        # the reference's learn_episode data path without the model (one env, one thread, like the reference learner): step_as_rc +
+        # ReplayBuffer::add + every 4th step sample 32 + tensorise state and state_next
+        from oracle import oracle as O
+        a_steps = 12000                                         # about 5 s of single-thread CPU work
+        a_secs = O.bench_actor_loop(a_steps, 4096, 32, SEED)
+        out["actor_loop_cpu_baseline"] = {"value": a_steps / a_secs, "unit": "env-steps/s", "minibatches_per_sec": 0.25 * a_steps / a_secs, "cores": 1, "kind": "port",
+                                          "sample": "%d env-steps of one env: step+render+grayscale+ring+state clone+replay add, every 4th step sample 32 distinct + f32 tensorisation of state and state_next (no model), CPU oracle, 1 thread, %.1f s" % (a_steps, a_secs)}
         # the reference's replay path on the host (ReplayBuffer::get_many + batch_to_multi_dim_array for state and state_next,
         # generate_distinct_random_ids), single-threaded like the reference learner; bounded sample
         from oracle import oracle as O

@@ -101,3 +101,32 @@ void orc_synthetic_actions_fill(uint64_t seed, uint32_t env_id_base, uint32_t n_
     for (uint32_t t = 0; t < n_steps; ++t)
         for (uint32_t e = 0; e < n_envs; ++e) out[(size_t)t * n_envs + e] = orc_synthetic_action(seed, env_id_base + e, t0 + t);
 }
+
+/* actor-loop leg (BASELINE configs[4] without the model): the reference's learn_episode data path for ONE env on one thread
+ * (self_driving_tf_q_learner.rs:141-233) — step_as_rc (step, draw, grayscale, ring add, state clone), ReplayBuffer::add, and on
+ * every 4th step once len > batch (:181) generate_distinct_random_ids + get_many + batch_to_multi_dim_array for state and
+ * state_next (f32 [b][x][y][slot]); random policy, auto-reset like the episode loop. Returns seconds for n_steps env-steps. */
+double orc_bench_actor_loop(uint32_t n_steps, size_t capacity, uint32_t batch, uint64_t seed, uint64_t* checksum) {
+    orc_vec* v = orc_vec_new(1, seed, 0, 0, capacity, 100);
+    const size_t per = (size_t)84 * 84 * 4;
+    float* s = (float*)malloc(batch * per * sizeof(float)); float* sn = (float*)malloc(batch * per * sizeof(float));
+    float* r = (float*)malloc(batch * sizeof(float)); uint8_t* a = (uint8_t*)malloc(batch); uint8_t* d = (uint8_t*)malloc(batch);
+    uint32_t* idx = (uint32_t*)malloc(batch * sizeof(uint32_t));
+    orc_replay* rp = orc_vec_replay(v);
+    uint64_t sum = 0, calls = 0;
+    double t0 = now_s();
+    for (uint32_t t = 0; t < n_steps; ++t) {
+        uint8_t act = orc_synthetic_action(seed, 0, t); float rew; uint8_t dn;
+        orc_vec_step(v, &act, &rew, &dn);
+        if (t % 4 == 0 && orc_replay_len(rp) > batch) {
+            orc_sample_distinct(seed, calls++, (uint32_t)orc_replay_len(rp), batch, idx);
+            orc_replay_get_many_f32(rp, idx, batch, s, sn, r, a, d);
+            sum += (uint64_t)s[per / 2] + (uint64_t)sn[per / 3] + idx[0];
+        }
+        sum += (uint64_t)rew;
+    }
+    double t1 = now_s();
+    if (checksum) *checksum = sum + calls;
+    free(s); free(sn); free(r); free(a); free(d); free(idx); orc_vec_free(v);
+    return t1 - t0;
+}

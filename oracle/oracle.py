@@ -96,6 +96,8 @@ def lib():
         L.orc_bench_env_steps.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, vp]
         L.orc_parts_run.argtypes = [vp, vp, vp, C.c_int, C.c_uint32, C.c_uint32, vp, vp, vp]
         L.orc_synthetic_actions_fill.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+        L.orc_bench_actor_loop.restype = C.c_double
+        L.orc_bench_actor_loop.argtypes = [C.c_uint32, C.c_size_t, C.c_uint32, C.c_uint64, vp]
         L.orc_bench_sample.restype = C.c_double
         L.orc_bench_sample.argtypes = [C.c_uint32, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint64, vp]
         for name in ("orc_collision_test_left_wall", "orc_collision_test_right_wall", "orc_collision_test_top_wall"):
@@ -296,3 +298,9 @@ def bench_env_steps(n_envs, n_steps, seed=1, threads=1):
 def bench_sample(n_envs, capacity, batch, n_batches, seed=1):
     chk = C.c_uint64(0)
     return lib().orc_bench_sample(n_envs, capacity, batch, n_batches, seed, C.byref(chk))
+
+
+def bench_actor_loop(n_steps, capacity=4096, batch=32, seed=1):
+    """seconds for n_steps env-steps of the reference's learn_episode data path (one env, one thread, no model)"""
+    chk = C.c_uint64(0)
+    return lib().orc_bench_actor_loop(n_steps, capacity, batch, seed, C.byref(chk))
