@@ -5,6 +5,8 @@
 #include "qnet.cuh"
 #include "qnet_conv.cuh"
 
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges cost a few ns unless a tool (ncu --nvtx, nsys) is attached
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,6 +25,13 @@ static int32_t fail(int32_t code, const std::string& msg) { g_last_error = msg; 
         if (_e != cudaSuccess)                                                                               \
             return fail(QLC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
     } while (0)
+
+// one NVTX range per public entry point that launches work ("qlc_env_step", "qlc_replay_gather", ...): lets ncu / nsys filter by call
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define QLC_RANGE(name) NvtxRange _qlc_nvtx_range(name)
 
 struct qlc_env {
     qlc_config cfg;
@@ -218,6 +227,7 @@ int32_t qlc_sync(qlc_env* env, void* stream) {
 }
 
 int32_t qlc_env_reset(qlc_env* env, const uint8_t* mask_host, const float* dir_x_host) {
+    QLC_RANGE("qlc_env_reset");
     if (!env) return fail(QLC_ERR_INVALID_ARG, "env is null");
     int32_t rc = set_device(env); if (rc) return rc;
     const uint32_t n = env->cfg.n_envs;
@@ -293,6 +303,7 @@ static int32_t launch_advance(qlc_env* env, StepParams& p, cudaStream_t s, uint3
 extern "C" {
 
 int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps, float* reward_dev, uint8_t* done_dev, void* stream) {
+    QLC_RANGE("qlc_env_step");
     if (!env || !actions_dev) return fail(QLC_ERR_INVALID_ARG, "env/actions is null");
     if (n_steps == 0) return QLC_OK;
     int32_t rc = set_device(env); if (rc) return rc;
@@ -338,6 +349,7 @@ static bool is_pinned(const void* p) {
 }
 
 static int32_t step_host_impl(qlc_env* env, const uint8_t* actions_host, uint32_t n_steps, float* reward_host, uint8_t* done_host, bool wait) {
+    QLC_RANGE(wait ? "qlc_env_step_host" : "qlc_env_step_host_submit");
     if (!env || !actions_host) return fail(QLC_ERR_INVALID_ARG, "env/actions is null");
     if (n_steps == 0) return QLC_OK;
     int32_t rc = set_device(env); if (rc) return rc;
@@ -445,6 +457,7 @@ static int32_t launch_gather(qlc_env* env, const GatherParams& g, int32_t layout
 static size_t item_bytes(int32_t layout) { return layout == QLC_LAYOUT_F32_BXYH ? (size_t)FRAME_BYTES * 4 * sizeof(float) : (size_t)FRAME_BYTES * 4; }
 
 int32_t qlc_env_obs(qlc_env* env, int32_t layout, void* out_dev, void* stream) {
+    QLC_RANGE("qlc_env_obs");
     if (!env || !out_dev) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
     if (((uintptr_t)out_dev & 15) != 0) return fail(QLC_ERR_INVALID_ARG, "output must be 16-byte aligned");
     int32_t rc = set_device(env); if (rc) return rc;
@@ -454,6 +467,7 @@ int32_t qlc_env_obs(qlc_env* env, int32_t layout, void* out_dev, void* stream) {
 }
 
 int32_t qlc_env_obs_host(qlc_env* env, int32_t layout, void* out_host) {
+    QLC_RANGE("qlc_env_obs_host");
     if (!env || !out_host) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
     if (layout != QLC_LAYOUT_U8_BHYX && layout != QLC_LAYOUT_F32_BXYH) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
     int32_t rc = set_device(env); if (rc) return rc;
@@ -524,6 +538,7 @@ int32_t qlc_replay_capacity(qlc_env* env, uint64_t* cap) {
 }
 
 int32_t qlc_replay_sample(qlc_env* env, uint32_t batch, uint32_t n_batches, uint64_t call_index, uint32_t* idx_dev, void* stream) {
+    QLC_RANGE("qlc_replay_sample");
     if (!env || !idx_dev) return fail(QLC_ERR_INVALID_ARG, "env/idx is null");
     if (batch == 0 || batch > SAMPLE_MAX_BATCH) return fail(QLC_ERR_INVALID_ARG, "batch must be in 1..1024");
     if (n_batches == 0) return QLC_OK;
@@ -538,6 +553,7 @@ int32_t qlc_replay_sample(qlc_env* env, uint32_t batch, uint32_t n_batches, uint
 
 int32_t qlc_replay_gather(qlc_env* env, const uint32_t* idx_dev, uint32_t n, int32_t layout, void* state_dev, void* next_dev,
                           float* reward_dev, uint8_t* action_dev, uint8_t* done_dev, void* stream) {
+    QLC_RANGE("qlc_replay_gather");
     if (!env || !idx_dev) return fail(QLC_ERR_INVALID_ARG, "env/idx is null");
     if ((((uintptr_t)state_dev) | ((uintptr_t)next_dev)) & 15) return fail(QLC_ERR_INVALID_ARG, "outputs must be 16-byte aligned");
     int32_t rc = set_device(env); if (rc) return rc;
@@ -548,6 +564,7 @@ int32_t qlc_replay_gather(qlc_env* env, const uint32_t* idx_dev, uint32_t n, int
 }
 
 int32_t qlc_replay_sample_host(qlc_env* env, uint32_t batch, uint64_t call_index, uint32_t* idx_host) {
+    QLC_RANGE("qlc_replay_sample_host");
     if (!env || !idx_host) return fail(QLC_ERR_INVALID_ARG, "env/idx is null");
     int32_t rc = set_device(env); if (rc) return rc;
     rc = ensure_dev_stage(env, (size_t)batch * 4); if (rc) return rc;
@@ -559,6 +576,7 @@ int32_t qlc_replay_sample_host(qlc_env* env, uint32_t batch, uint64_t call_index
 
 int32_t qlc_replay_gather_host(qlc_env* env, const uint32_t* idx_host, uint32_t n, int32_t layout, void* state_host, void* next_host,
                                float* reward_host, uint8_t* action_host, uint8_t* done_host) {
+    QLC_RANGE("qlc_replay_gather_host");
     if (!env || !idx_host) return fail(QLC_ERR_INVALID_ARG, "env/idx is null");
     if (layout != QLC_LAYOUT_U8_BHYX && layout != QLC_LAYOUT_F32_BXYH) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
     if (n == 0) return QLC_OK;
@@ -681,6 +699,7 @@ static std::vector<CkptArray> ckpt_arrays(qlc_env* env) {
 }  // namespace
 
 int32_t qlc_env_save(qlc_env* env, const char* path) {
+    QLC_RANGE("qlc_env_save");
     if (!env || !path) return fail(QLC_ERR_INVALID_ARG, "env/path is null");
     int32_t rc = set_device(env); if (rc) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
@@ -706,6 +725,7 @@ int32_t qlc_env_save(qlc_env* env, const char* path) {
 }
 
 int32_t qlc_env_load(qlc_env* env, const char* path) {
+    QLC_RANGE("qlc_env_load");
     if (!env || !path) return fail(QLC_ERR_INVALID_ARG, "env/path is null");
     int32_t rc = set_device(env); if (rc) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
@@ -905,6 +925,7 @@ int32_t qlc_qnet_create(qlc_env* env, const qlc_qnet_weights* w, qlc_qnet** out)
 }
 
 int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32_t which, float* q_dev, uint8_t* action_dev, float* max_q_dev, void* stream) {
+    QLC_RANGE("qlc_qnet_forward");
     if (!q) return fail(QLC_ERR_INVALID_ARG, "qnet is null");
     qlc_env* env = q->env;
     int32_t rc = set_device(env); if (rc) return rc;
@@ -996,6 +1017,7 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
 }
 
 int32_t qlc_qnet_forward_host(qlc_qnet* q, const uint32_t* idx_host, uint32_t n, int32_t which, float* q_host, uint8_t* action_host, float* max_q_host) {
+    QLC_RANGE("qlc_qnet_forward_host");
     if (!q) return fail(QLC_ERR_INVALID_ARG, "qnet is null");
     qlc_env* env = q->env;
     int32_t rc = set_device(env); if (rc) return rc;
