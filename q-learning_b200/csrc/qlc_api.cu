@@ -354,9 +354,6 @@ static int32_t step_host_impl(qlc_env* env, const uint8_t* actions_host, uint32_
     if (n_steps == 0) return QLC_OK;
     int32_t rc = set_device(env); if (rc) return rc;
     const size_t n = (size_t)env->cfg.n_envs * n_steps;
-    uint8_t bad = 0;
-    for (size_t i = 0; i < n; ++i) bad |= (uint8_t)(actions_host[i] >= QLC_ACTION_SPACE);
-    if (bad) return fail(QLC_ERR_OUT_OF_RANGE, "value out of range");   // QlError, breakout_environment.rs:117
     // page-locked caller buffers (qlc_host_alloc / cudaHostRegister) are used in place; pageable ones are staged
     const bool pin_a = is_pinned(actions_host), pin_r = !reward_host || is_pinned(reward_host), pin_d = !done_host || is_pinned(done_host);
     if (!wait && !(pin_a && pin_r && pin_d)) return fail(QLC_ERR_INVALID_ARG, "qlc_env_step_host_submit needs page-locked buffers (qlc_host_alloc)");
@@ -387,6 +384,14 @@ static int32_t step_host_impl(qlc_env* env, const uint8_t* actions_host, uint32_
     } else {
         memcpy(pin, actions_host, n);
         CUDA_TRY(cudaMemcpyAsync(dev, pin, n, cudaMemcpyHostToDevice, s));
+    }
+    // validate while the copy is in flight; nothing has been launched yet, so a bad action leaves the env untouched
+    uint8_t bad = 0;
+    for (size_t i = 0; i < n; ++i) bad |= (uint8_t)(actions_host[i] >= QLC_ACTION_SPACE);
+    if (bad) {
+        cudaStreamSynchronize(s);                                                   // the staging copy must not outlive the caller's buffer
+        if (env->copy_stream) cudaStreamSynchronize(env->copy_stream);
+        return fail(QLC_ERR_OUT_OF_RANGE, "value out of range");                    // QlError, breakout_environment.rs:117
     }
     // page-locked outputs are written by the kernel itself (zero-copy stores over PCIe while it runs, UVA pointers);
     // pageable ones go through device staging + a device->host copy
