@@ -89,3 +89,54 @@ def test_contact_distance_and_normal_via_zero_length_probe(O):
         assert abs(nx - ve[0]) < 1e-4 and abs(ny - ve[1]) < 1e-4
         checked += 1
     assert checked == 4000
+
+
+def test_trajectory_invariants(O):
+    """What every Breakout trajectory of the reference satisfies, whatever the arithmetic details: the ball stays between the
+    walls and under the ceiling (up to the contact prediction), moves 4.0 per step along straight legs, bricks only ever
+    disappear and each one scores 1 (mechanics.rs:150-162), the paddle stays on the board at |speed| <= 160 in 0.001 steps
+    (:553-587,612-649), an episode ends exactly when the ball passes the paddle line or no brick is left (:131-135)."""
+    n, steps, seed = 48, 2500, 21
+    env = O.VecEnv(n, seed=seed)
+    acts = O.synthetic_actions(seed, 0, n, 0, steps)
+    # half of the envs track the ball so that episodes last and bricks get hit
+    prev = env.state()
+    total_hits = 0
+    for t in range(steps):
+        a = acts[t].copy()
+        track = np.arange(n) < n // 2
+        centre = (prev["pad_min_x"] + prev["pad_max_x"]) / 2
+        a[track] = np.where(prev["ball_cx"][track] < centre[track] - 5, 1, np.where(prev["ball_cx"][track] > centre[track] + 5, 2, 0))
+        reward, done = env.step(a)
+        cur = env.state()
+        fresh = done != 0                                       # auto-reset: these envs show a new episode now
+        live = ~fresh & (cur["err"] == 0) & (prev["err"] == 0)
+        # bricks only disappear, one point each; reward is the score difference
+        gone = prev["bricks"] & ~cur["bricks"]
+        assert not np.any((cur["bricks"] & ~prev["bricks"])[live])
+        hits = np.array([bin(int(x)).count("1") for x in gone])
+        assert np.array_equal(hits[live], reward[live].astype(np.int64))
+        assert np.array_equal((cur["score"] - prev["score"])[live], hits[live])
+        total_hits += int(hits[live].sum())
+        # ball inside the walls / under the ceiling (0.8 contact prediction + rounding), paddle on the board
+        assert np.all(cur["ball_cx"][live] >= 10.0 - 1e-3) and np.all(cur["ball_cx"][live] <= 590.0 + 1e-3)
+        assert np.all(cur["ball_cy"][live] >= 10.0 - 1e-3)
+        assert np.all(cur["pad_min_x"] >= 0.0) and np.all(cur["pad_max_x"] <= 600.0)
+        assert np.allclose((cur["pad_max_x"] - cur["pad_min_x"]), 60.0, atol=1e-3)
+        sp = cur["pad_speed"]
+        assert np.all(np.abs(sp) <= 160.0) and np.allclose(sp * 1000.0, np.round(sp * 1000.0), atol=1e-2)
+        # a leg without a bounce moves the ball by exactly |mv| = 200 * 0.02 = 4 in its direction
+        same_dir = live & (cur["ball_dx"] == prev["ball_dx"]) & (cur["ball_dy"] == prev["ball_dy"])
+        moved = np.hypot(cur["ball_cx"] - prev["ball_cx"], cur["ball_cy"] - prev["ball_cy"])
+        assert np.allclose(moved[same_dir], 4.0, atol=1e-3)
+        # with bounces the path is folded, never longer - once the direction is a unit vector: until the first bounce of an episode it
+        # is (dx, -1), |.| = 1.01..1.06, and the reference advances the centre by direction * way (mechanics.rs:166), i.e. a bit further
+        unit = np.abs(np.hypot(prev["ball_dx"], prev["ball_dy"]) - 1.0) < 1e-5
+        assert np.all(moved[live & unit] <= 4.0 + 1e-3)
+        assert np.all(moved[live & ~unit] <= 4.0 * 1.07)
+        # an unfinished env has its ball above the paddle line and bricks left
+        assert np.all(cur["ball_cy"][~fresh & (cur["finished"] == 0)] < 575.0) and np.all(cur["bricks"][~fresh & (cur["finished"] == 0)] != 0)
+        prev = cur
+    st = env.stats()
+    assert st["episodes"] > n and total_hits > 200                # random play loses quickly, tracking play hits bricks
+    env.close()
