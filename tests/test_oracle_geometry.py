@@ -140,3 +140,63 @@ def test_trajectory_invariants(O):
     st = env.stats()
     assert st["episodes"] > n and total_hits > 200                # random play loses quickly, tracking play hits bricks
     env.close()
+
+
+def _raster_numpy(cx, cy, pmin, pmax, bricks):
+    """The raster spec of DESIGN.md section 5, restated with whole-frame numpy float32 arrays (no loops over shapes' bounding
+    boxes, no conservative bounds): bricks luma 96, ball ring luma 236 on top, paddle luma 255 on top."""
+    f = np.float32
+    px = (np.arange(84, dtype=np.float32) + f(0.5))[None, :]
+    py = (np.arange(84, dtype=np.float32) + f(0.5))[:, None]
+    sc = lambda v: f(f(v) * f(84.0)) / f(600.0)
+    img = np.zeros((84, 84), dtype=np.uint8)
+    for b in range(60):
+        if (int(bricks) >> b) & 1:
+            r, k = divmod(b, 20)
+            x0, x1 = sc(30.0 + 27.0 * k), sc(55.0 + 27.0 * k)
+            y0, y1 = sc(35.0 + 27.0 * r), sc(60.0 + 27.0 * r)
+            img[((px >= x0) & (px < x1)) & ((py >= y0) & (py < y1))] = 96
+    bx, by, rs = sc(cx), sc(cy), sc(10.0)
+    dx, dy = px - bx, py - by
+    d2 = dx * dx + dy * dy
+    out2, in2 = f(rs + f(1.0)) * f(rs + f(1.0)), f(rs - f(1.0)) * f(rs - f(1.0))
+    img[(d2 <= out2) & (d2 >= in2)] = 236
+    x0, x1, y0, y1 = sc(pmin), sc(pmax), sc(565.0), sc(575.0)
+    img[((px >= x0) & (px < x1)) & ((py >= y0) & (py < y1))] = 255
+    return img
+
+
+def test_rendered_frames_follow_the_raster_spec(O):
+    """Every newest frame of 30 envs over 220 steps (tracking play: bricks disappear, the ball visits the brick band, the
+    walls and the paddle) equals the raster spec restated independently in numpy; the frame lands in ring slot (k-1) mod 4
+    and older slots keep older frames (frame_ring_buffer.rs:53-63)."""
+    n, steps, seed = 30, 220, 8
+    env = O.VecEnv(n, seed=seed)
+    acts = O.synthetic_actions(seed, 0, n, 0, steps)
+    prev = env.state()
+    last = {}
+    checked = 0
+    for t in range(steps):
+        a = acts[t].copy()
+        centre = (prev["pad_min_x"] + prev["pad_max_x"]) / 2
+        a[: n // 2] = np.where(prev["ball_cx"][: n // 2] < centre[: n // 2] - 5, 1, np.where(prev["ball_cx"][: n // 2] > centre[: n // 2] + 5, 2, 0))
+        _, done = env.step(a)
+        cur = env.state()
+        obs = env.obs_u8()
+        for e in range(n):
+            k = int(cur["episode_step"][e])
+            if done[e] or k == 0:
+                last.pop(e, None)
+                continue                                        # restarted on this step: the stack was cleared
+            want = _raster_numpy(cur["ball_cx"][e], cur["ball_cy"][e], cur["pad_min_x"][e], cur["pad_max_x"][e], cur["bricks"][e])
+            slot = (k - 1) % 4
+            assert np.array_equal(obs[e, slot], want), "env %d step %d" % (e, t)
+            if e in last and k >= 2:
+                assert np.array_equal(obs[e, (k - 2) % 4], last[e])          # the previous frame is still in its slot
+            if k < 4:
+                assert not obs[e, k:].any()                                  # slots not written yet in this episode are zero
+            last[e] = want
+            checked += 1
+        prev = cur
+    assert checked > 0.9 * n * steps
+    env.close()
