@@ -306,7 +306,7 @@ def run_b200(args, rank, local_rank, world):
             "env_error_flags_note": "OR of the sticky per-env flags after all launches of this run (1 wall-distance assert, 2 approximation range, 4 reflection bound, "
                                     "8 bisection bound, 16 degenerate contact, 32 bad action, 64 hand-over time-out): states in which the reference panics or "
                                     "recurses without bound (mechanics.rs:265,284,303,361-389,511); %d of %d envs flagged on rank 0; the oracle raises the same flags "
-                                    "on the same steps (test_rare_events_parity, tools/soak.py)" % (int((env.read_state()["err"] != 0).sum()), n_envs),
+                                    "on the same steps (test_rare_events_parity, test_soak)" % (int((env.read_state()["err"] != 0).sum()), n_envs),
         }
         line.update(extra)
         line.update(loops)

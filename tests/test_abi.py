@@ -75,6 +75,13 @@ def test_product_does_not_touch_the_oracle():
                 assert "liboracle" not in text and "breakout_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
     out = subprocess.run(["ldd", os.path.join(pkg, "libqlcuda.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+    # nor do the measurement scripts, the examples or the bindings: only tests/, __graft_entry__.smoke() and bench.py's CPU legs do
+    for sub in ("tools", "examples", "bindings", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith((".py", ".sh", ".cu", ".cpp", ".h", ".hpp", ".rs")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, os.path.join(sub, f)
 
 
 def test_action_enum(qlb):
