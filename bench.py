@@ -28,11 +28,17 @@ import numpy as np
 ENVS_PER_GPU = 4096            # BASELINE.json configs[1]
 STEPS_PER_LAUNCH = 64          # env-steps per env per launch: 4096*64*7056 B = 1.85 GB of frames per bench step (>> 126 MB L2)
 REPLAY_CAPACITY = 1 << 20      # 1M transitions (configs[2]) = 256 time steps of 4096 envs, 7.4 GB of frames
-BYTES_PER_ENV_STEP = 7154      # 7056 frame + 41+41 state + 1 action + 4 reward + 1 done + ~10 record
+BYTES_PER_ENV_STEP = 7066      # frame 7,056 + action 1 + reward 4 + done 1 + replay record 4 (SURVEY.md 8(d) minus the per-launch state)
+STATE_BYTES_PER_ENV = 53       # 7 f32 + u64 brick mask + 4 u32 + 1 u8: read once and written once per LAUNCH, not per step
 BYTES_PER_SAMPLE_U8 = 91744    # 5 frames read + 2 x 4 frames written + 16 B scalars
 BYTES_PER_SAMPLE_F32 = 261088  # 5 frames read + 2 x 4 f32 frames written + 16 B scalars
 SEED = 20261018
 QNET_FLOP_PER_OBS = 2 * (400 * 32 * 256 + 81 * 64 * 512 + 49 * 64 * 576 + 512 * 3136 + 3 * 512)   # 84x84x4 -> conv 8/4, 4/2, 3/1 -> 512 -> 3
+
+
+def launch_bytes(n_envs, k_inner):
+    """algorithmic bytes of ONE step launch, exact: 7,066 B per env-step + 2 x 53 B of env state per env"""
+    return BYTES_PER_ENV_STEP * n_envs * k_inner + 2 * STATE_BYTES_PER_ENV * n_envs
 
 
 def _peaks():
@@ -153,11 +159,14 @@ def run_b200(args, rank, local_rank, world):
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if not os.environ.get("QLC_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: stdout carries ONE JSON line
+        # NCCL_DEBUG / NCCL_DEBUG_FILE are left as the launcher set them (the driver reads the rank count out of NCCL's log);
+        # the JSON line is the LAST line rank 0 writes to stdout.
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
+    build = q.build_info()
+    if build.get("profiling") != "0":
+        raise SystemExit("bench.py: libqlcuda.so is an ablation build (-DQLC_PROFILING honours QLC_DEBUG_SKIP); bench numbers need the release build")
     n_envs, k_inner = args.envs, args.steps_per_launch
     env = q.BreakoutEnvironment(n_envs=n_envs, seed=SEED, env_id_base=rank * n_envs,   # = sharding.shard_range(rank, world, world * n_envs)[0]
                                 replay_capacity=args.replay_capacity, device=local_rank)
@@ -264,6 +273,7 @@ def run_b200(args, rank, local_rank, world):
     e2e_check += float(r_host.sum()) + float(pr2.array.sum())          # the read-back results are consumed on the host
     e2e_sync_value = units_per_step * e2e_steps / dt_sync
 
+    stats_every_step = None if args.no_extra else measure_stats_reduce_every_step(q, torch, dist if distributed else None, env, launch, stream, rank, world, dev, barrier, args.steps)
     replay = None if args.no_extra else measure_replay_sampling(q, torch, dist if distributed else None, rb, dev, stream, world, barrier)
     loops = {} if args.no_extra else measure_actor_loops(q, torch, dist if distributed else None, env, rb, dev, stream, world, barrier)
     extra = {}
@@ -271,11 +281,12 @@ def run_b200(args, rank, local_rank, world):
     if rank == 0:
         peak, peak_src = _peaks()
         launch_ms = ms / args.steps
-        achieved = BYTES_PER_ENV_STEP * n_envs * k_inner / (launch_ms * 1e-3) / 1e9
+        achieved = launch_bytes(n_envs, k_inner) / (launch_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "env_advance_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "peak_source": peak_src, "frac_of_nominal_8tbs": achieved / 8000.0,   # north_star quotes the ~8 TB/s datasheet figure
                     "traffic": _ncu_traffic("env_advance_kernel"),
-                    "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n_envs * k_inner}
+                    "algorithmic_bytes_per_launch": launch_bytes(n_envs, k_inner),
+                    "algorithmic_bytes_formula": "7066 B x envs x steps_per_launch + 106 B x envs (state read + written once per launch)"}
         if not args.no_extra:
             extra = measure_extras(q, torch, env, rb, dev, stream, peak, replay, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
         if world == 1 and not args.no_cpu_baseline:
@@ -301,6 +312,7 @@ def run_b200(args, rank, local_rank, world):
                     "synchronous_call": {"value": e2e_sync_value, "unit": "env-steps/s", "note": "qlc_env_step_host: submit + wait per step (what a caller whose next actions depend on the result uses)"},
                     "result_checksum": e2e_check},
             "gpu_launches": args.steps,
+            "library": dict(build, note="profiling=0: release build, QLC_DEBUG_SKIP is compiled out; src_hash = sha256 of the sources the binary was built from"),
             "episode_stats": dict(stats, reduced_with="nccl all_reduce (2 tiny calls, off the step path)" if distributed else "single rank"),
             "env_error_flags": env.error_flags(),
             "env_error_flags_note": "OR of the sticky per-env flags after all launches of this run (1 wall-distance assert, 2 approximation range, 4 reflection bound, "
@@ -310,11 +322,66 @@ def run_b200(args, rank, local_rank, world):
         }
         line.update(extra)
         line.update(loops)
+        if stats_every_step:
+            line["stats_reduce_every_step"] = stats_every_step
         print(json.dumps(line), flush=True)
     env.close()
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def measure_stats_reduce_every_step(q, torch, dist, env, launch, stream, rank, world, dev, barrier, steps):
+    """The episode-stat reduction THROUGH THE C ABI (qlc_comm_init: NCCL bound by dlopen inside libqlcuda.so; one ncclAllGather of
+    5 doubles + a combine kernel on the communicator's low-priority side stream) enqueued after EVERY bench step, against the
+    same launches without it: it must not be on the step path. The 128-byte NCCL id travels over the host's own channel
+    (here torch.distributed broadcast; a Rust host would use a file or a socket)."""
+    steps = max(20, min(steps, 300))
+
+    def timed(with_reduce):
+        for _ in range(5):
+            launch()
+            if with_reduce:
+                env.stats_allreduce(stream)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            launch()
+            if with_reduce:
+                env.stats_allreduce(stream)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    ms_without = timed(False)
+    if dist is not None:
+        ident = [q.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        env.comm_init(rank, world, ident[0])
+    else:
+        env.comm_init(0, 1, q.comm_unique_id())            # a real one-rank NCCL communicator
+    ms_with = timed(True)
+    ms_without2 = timed(False)
+    env.stats_allreduce(stream)
+    g = env.stats_global(wait=True)
+    local = env.stats()
+    info = env.comm_info()
+    if dist is not None:                                    # cross-check against torch.distributed's own reduction
+        t = torch.tensor([local["sum_return"], local["episodes"], local["steps"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        ok = [int(x) for x in t.tolist()] == [g["sum_return"], g["episodes"], g["steps"]]
+    else:
+        ok = g == local
+    return {"ms_per_step_with": ms_with, "ms_per_step_without": min(ms_without, ms_without2), "ms_per_step_without_before_after": [ms_without, ms_without2],
+            "overhead_frac": ms_with / min(ms_without, ms_without2) - 1.0, "steps": steps, "nccl_version": info["nccl_version"], "nccl_ranks": info["nccl_ranks"],
+            "world": world, "matches_torch_distributed": bool(ok), "global": g,
+            "note": "qlc_stats_allreduce after every bench step (C ABI; NCCL via dlopen; side stream, snapshot taken by the step kernel's last CTA), max over ranks"}
 
 
 def measure_actor_loops(q, torch, dist, env, rb, dev, stream, world, barrier):
@@ -334,9 +401,8 @@ def measure_actor_loops(q, torch, dist, env, rb, dev, stream, world, barrier):
     net = q.QNetwork(env, _random_qnet_weights(q))
 
     def sample_every_4th(i):
-        if rb.should_sample(i, rb.len(), 32):
-            rb.sample_device(32, 1, i, idx.data_ptr(), stream)
-            rb.gather_device(idx.data_ptr(), 32, q.LAYOUT_F32_BXYH, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
+        if rb.should_sample(i, rb.len(), 32):              # ONE launch: the gather kernel draws the distinct indices itself
+            rb.sample_gather_device(32, 1, i, q.LAYOUT_F32_BXYH, idx.data_ptr(), st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
 
     def iter_random(i):
         ra = torch.randint(0, 3, (1, n), dtype=torch.uint8, device=dev)
@@ -368,7 +434,7 @@ def measure_actor_loops(q, torch, dist, env, rb, dev, stream, world, barrier):
     scope = "%d GPU(s), %d envs each, slowest rank" % (world, n)
     return {
         "actor_loop": {"env_steps_per_sec": world * n / (res[0] * 1e-3), "minibatches_per_sec": world * 0.25 / (res[0] * 1e-3), "us_per_iteration": res[0] * 1e3, "n_gpus": world,
-                       "note": "1 step launch per iteration (actions from a device-side random policy), sample+gather B=32 f32 every 4th step; no learner; " + scope},
+                       "note": "1 step launch per iteration (actions from a device-side random policy), one-launch sample+gather B=32 f32 every 4th step; no learner; " + scope},
         "actor_loop_qnet": {"env_steps_per_sec": world * n / (res[1] * 1e-3), "minibatches_per_sec": world * 0.25 / (res[1] * 1e-3), "us_per_iteration": res[1] * 1e3, "n_gpus": world,
                             "qnet_tflops_per_gpu": QNET_FLOP_PER_OBS * n / (res[1] * 1e-3) / 1e12,
                             "note": "closed loop on the GPU: Q-network forward (greedy action for all envs) -> 1 env-step launch -> sample+gather B=32 f32 every 4th step; no learner; " + scope},
@@ -377,9 +443,9 @@ def measure_actor_loops(q, torch, dist, env, rb, dev, stream, world, barrier):
 
 def measure_replay_sampling(q, torch, dist, rb, dev, stream, world, barrier):
     """BASELINE configs[2] on EVERY rank (one replay shard per GPU, no cross-GPU gather): Philox distinct-index sample + gather of
-    the s and s' frame stacks into device buffers, u8 [b][slot][y][x] and the reference's f32 [b][x][y][slot]; device-timed,
-    max over ranks, whole-job transitions/s. The gather kernel is also timed alone (its own roofline, without the latency-bound
-    sample kernel; indices of the last sample call, 8,192 transitions read 289 MB of frames > L2)."""
+    the s and s' frame stacks into device buffers in ONE kernel launch (the gather kernel derives the indices), u8 [b][slot][y][x]
+    and the reference's f32 [b][x][y][slot]; device-timed, max over ranks, whole-job transitions/s. The gather with GIVEN indices
+    (get_many; those of the last call) is timed beside it; 8,192 transitions read 289 MB of frames > L2."""
     per = 4 * 84 * 84
     keys, times = [], []
     for batch, n_batches in ((32, 1), (512, 1), (32, 256), (512, 16)):
@@ -392,9 +458,8 @@ def measure_replay_sampling(q, torch, dist, rb, dev, stream, world, barrier):
             def gather():
                 rb.gather_device(idx.data_ptr(), n, layout, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
 
-            def once(c):
-                rb.sample_device(batch, n_batches, c, idx.data_ptr(), stream)
-                gather()
+            def once(c):                                   # sample + gather: ONE kernel launch
+                rb.sample_gather_device(batch, n_batches, c, layout, idx.data_ptr(), st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
             for c in range(3):
                 once(c)
             reps = 30
@@ -412,48 +477,29 @@ def measure_replay_sampling(q, torch, dist, rb, dev, stream, world, barrier):
             e1.record()
             barrier()
             ms_g = e0.elapsed_time(e1) / reps
-            # sampling of call c+1 on a second stream while call c is gathered (two index buffers): hides the latency-bound sample kernel
             ms_p = 0.0
-            if n_batches > 1:
-                side = torch.cuda.Stream(device=dev)
-                main = torch.cuda.current_stream()
-                idx2 = (idx, torch.empty_like(idx))
-                ev_s = (torch.cuda.Event(), torch.cuda.Event()); ev_g = (torch.cuda.Event(), torch.cuda.Event())
-                side.wait_stream(main)
-                rb.sample_device(batch, n_batches, 50, idx2[0].data_ptr(), side.cuda_stream); ev_s[0].record(side)
-                barrier()
-                e0.record()
-                for c in range(reps):
-                    cur = c & 1
-                    if c >= 1:
-                        side.wait_event(ev_g[1 - cur])           # gather c-1 has read the buffer the next sample overwrites
-                    rb.sample_device(batch, n_batches, 51 + c, idx2[1 - cur].data_ptr(), side.cuda_stream); ev_s[1 - cur].record(side)
-                    main.wait_event(ev_s[cur])
-                    rb.gather_device(idx2[cur].data_ptr(), n, layout, st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
-                    ev_g[cur].record(main)
-                e1.record()
-                barrier()
-                ms_p = e0.elapsed_time(e1) / reps
-                side.synchronize()
-                del idx2
             keys.append((batch, n_batches, name, bps, n))
             times += [ms, ms_g, ms_p]
             del idx, st, nx
-    # end to end through the reference-facing host calls (generate_distinct_random_ids -> get_many + batch_to_multi_dim_array into
-    # page-locked host arrays the caller reads): index D2H, gather kernel, D2H of both stacks and the scalars, every call
+    # end to end through the reference-facing host calls, in the reference's call pattern: the learner draws the ids itself on the
+    # host (its private generate_distinct_random_ids, self_driving_tf_q_learner.rs:183,276-296), then get_many +
+    # batch_to_multi_dim_array for state_next and state into page-locked host arrays the caller reads. f32 stacks cross PCIe as u8
+    # (1/4 of the bytes) and are widened into the caller's arrays by the library's host pool.
     host_keys, host_check = [], 0.0
+    host_rng = np.random.default_rng(SEED)
     for batch in (32, 512):
         for layout, name, isz in ((q.LAYOUT_U8_BHYX, "u8", 1), (q.LAYOUT_F32_BXYH, "f32", 4)):
             for c in range(3):
-                rb.get_many(rb.generate_distinct_random_ids(batch, c), layout, reuse=True)
+                rb.get_many(host_rng.choice(rb.len(), size=batch, replace=False).astype(np.uint32), layout, reuse=True)
             barrier()
             reps = 20
             t0 = time.perf_counter()
             for c in range(reps):
-                g = rb.get_many(rb.generate_distinct_random_ids(batch, 100 + c), layout, reuse=True)
+                ids = host_rng.choice(rb.len(), size=batch, replace=False).astype(np.uint32)
+                g = rb.get_many(ids, layout, reuse=True)
                 host_check += float(g.reward.sum()) + float(g.state_next[batch - 1].ravel()[-1])
             times.append((time.perf_counter() - t0) / reps * 1e3)
-            host_keys.append((batch, name, batch * (2 * per * isz + 4 + 1 + 1 + 4)))
+            host_keys.append((batch, name, batch * (2 * per + 4 + 1 + 1), batch * 2 * per * isz))
     if world > 1:
         t = torch.tensor(times, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -461,25 +507,34 @@ def measure_replay_sampling(q, torch, dist, rb, dev, stream, world, barrier):
     peak, _ = _peaks()
     res = {}
     e2e_host = {}
-    for i, (batch, name, d2h) in enumerate(host_keys):
+    for i, (batch, name, d2h, host_bytes) in enumerate(host_keys):
         ms = times[3 * len(keys) + i]
         e2e_host["batch%d_%s" % (batch, name)] = {"transitions_per_sec": world * batch / (ms * 1e-3), "ms_per_minibatch": ms, "d2h_bytes_per_minibatch": d2h,
-                                                   "d2h_gbs_per_gpu": d2h / (ms * 1e-3) / 1e9}
+                                                   "host_tensor_bytes_per_minibatch": host_bytes, "host_tensor_gbs_per_gpu": host_bytes / (ms * 1e-3) / 1e9}
     for i, (batch, n_batches, name, bps, n) in enumerate(keys):
         ms, ms_g, ms_p = times[3 * i], times[3 * i + 1], times[3 * i + 2]
         rate = n / (ms * 1e-3)                       # per GPU, slowest rank
         res["batch%d_x%d_%s" % (batch, n_batches, name)] = {
             "transitions_per_sec": world * rate, "ms_per_call": ms, "achieved_gbs_per_gpu": rate * bps / 1e9, "frac_of_peak": rate * bps / 1e9 / peak,
-            "frac_of_nominal_8tbs": rate * bps / 1e9 / 8000.0, "bytes_per_transition": bps, "kernels_per_call": 2,
+            "frac_of_nominal_8tbs": rate * bps / 1e9 / 8000.0, "bytes_per_transition": bps, "kernels_per_call": 1,
             "gather_kernel_alone": {"ms_per_launch": ms_g, "achieved_gbs_per_gpu": n * bps / (ms_g * 1e-3) / 1e9, "frac_of_peak": n * bps / (ms_g * 1e-3) / 1e9 / peak}}
         if ms_p > 0.0:
             res["batch%d_x%d_%s" % (batch, n_batches, name)]["sample_prefetched_on_second_stream"] = {
                 "transitions_per_sec": world * n / (ms_p * 1e-3), "ms_per_call": ms_p, "frac_of_peak": n * bps / (ms_p * 1e-3) / 1e9 / peak}
     return {"metric": "sampled_transitions_per_sec", "n_gpus": world, "replay_len_per_gpu": rb.len(), "results": res,
-            "e2e_host": dict(e2e_host, timing="perf_counter around ReplayBuffer.generate_distinct_random_ids + get_many(reuse=True) per minibatch (host index array in, "
-                                              "page-locked host stacks out, read on the host), max over ranks; bound by the D2H copy of the stacks", result_checksum=host_check),
-            "note": "sample (Philox distinct ids) + gather (s and s' stacks) on device buffers, every rank on its own replay shard, max over ranks; "
+            "e2e_host": dict(e2e_host, timing="perf_counter around host-drawn distinct ids + ReplayBuffer.get_many(reuse=True) per minibatch (host index array in, "
+                                              "page-locked host stacks out, read on the host), max over ranks; stacks cross PCIe as u8, f32 ones are widened by %d host threads" % _host_threads(),
+                             result_checksum=host_check),
+            "note": "qlc_replay_sample_gather: Philox distinct ids drawn inside the gather kernel + s and s' stacks, ONE launch per call, device buffers, every rank on its own replay shard, max over ranks; "
                     "transitions_per_sec is the whole job, GB/s and fractions are per GPU; minibatches per call = the x factor"}
+
+
+def _host_threads():
+    n = os.environ.get("QLC_HOST_THREADS")
+    if n and int(n) > 0:
+        return int(n)
+    ranks = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(1, min(8, (os.cpu_count() or 2) // (2 * max(ranks, 1))))
 
 
 def measure_extras(q, torch, env, rb, dev, stream, peak, replay, cpu_baseline=True):
@@ -516,8 +571,8 @@ def measure_extras(q, torch, env, rb, dev, stream, peak, replay, cpu_baseline=Tr
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         rate = 65536 * k / (ms * 1e-3)
-        out["envs_65536"] = {"env_steps_per_sec": rate, "ms_per_launch": ms, "steps_per_launch": k, "achieved_gbs": rate * BYTES_PER_ENV_STEP / 1e9,
-                             "frac_of_peak": rate * BYTES_PER_ENV_STEP / 1e9 / peak}
+        out["envs_65536"] = {"env_steps_per_sec": rate, "ms_per_launch": ms, "steps_per_launch": k, "achieved_gbs": launch_bytes(65536, k) / (ms * 1e-3) / 1e9,
+                             "frac_of_peak": launch_bytes(65536, k) / (ms * 1e-3) / 1e9 / peak}
         for _ in range(3):
             big.step_device(acts.data_ptr(), 1, None, None, stream)
         torch.cuda.synchronize()

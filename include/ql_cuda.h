@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define QLC_VERSION 100
+#define QLC_VERSION 200
 
 /* status codes */
 #define QLC_OK                0
@@ -36,6 +36,7 @@ extern "C" {
 #define QLC_ERR_OUT_OF_RANGE  3   /* QlError("value out of range"): action >= 3, index >= len (breakout_environment.rs:112-119) */
 #define QLC_ERR_NO_DEVICE     4   /* no CUDA device / not an sm_100 part: there is NO CPU fallback */
 #define QLC_ERR_NOT_ENOUGH    5   /* replay shorter than the batch (assert at self_driving_tf_q_learner.rs:282) */
+#define QLC_ERR_COMM          6   /* NCCL could not be loaded (dlopen) or an NCCL call failed */
 
 /* BreakoutAction::numeric (breakout_environment.rs:104-110) */
 #define QLC_ACTION_NONE  0
@@ -60,8 +61,22 @@ extern "C" {
 /* output layouts of the state gather (ToMultiDimArray) */
 #define QLC_LAYOUT_U8_BHYX   0  /* [b][slot h][y][x] u8  — fast path, frame-major                     */
 #define QLC_LAYOUT_F32_BXYH  1  /* [b][x][y][slot h] f32 — BreakoutState::batch_to_multi_dim_array, value = u8 as f32 */
+#define QLC_LAYOUT_U8_BXYH   2  /* [b][x][y][slot h] u8  — the same element order at 1/4 of the bytes (the *_host calls move
+                                   this over PCIe and widen to f32 on the host; a GPU consumer can widen it itself) */
 
 typedef struct qlc_env qlc_env;      /* opaque: N envs + their frame ring + replay shard on one GPU */
+
+/* A state handle: what `Clone` of a BreakoutState is on the host (state_as_rc / step_as_rc, prelude.rs:36,52-58) - two
+ * integers naming frames in the HBM frame ring instead of 4 x 7,056 copied pixels. It names the observation of env `env`
+ * after `time` env-steps, `k` of them in the current episode (k = 0 right after reset: an all-zero stack,
+ * breakout_environment.rs:177-180): frames F_{time-d}, d = 1..min(k,4), in ring slot (k-d) mod 4 (frame_ring_buffer.rs:53-63).
+ * A handle stays usable while those frames are in the ring, i.e. for replay_capacity / n_envs further steps - exactly as
+ * long as the reference's ReplayBuffer keeps the Rc it wraps when step_buffer_len <= replay_capacity. */
+typedef struct qlc_obs_handle {
+    uint64_t time;
+    uint32_t k;
+    uint32_t env;
+} qlc_obs_handle;
 
 typedef struct qlc_config {
     uint32_t struct_size;            /* = sizeof(qlc_config) */
@@ -111,6 +126,9 @@ typedef struct qlc_episode_stats {
 
 /* ---- lifecycle ---- */
 int32_t qlc_version(void);
+/* "src_hash=<sha256 of the sources the library was built from>;profiling=<0|1>;" - profiling=1 marks an ablation build
+ * (-DQLC_PROFILING) in which QLC_DEBUG_SKIP can remove work from the step kernel; release builds ignore that variable. */
+const char* qlc_build_info(void);
 const char* qlc_last_error_string(void);
 int32_t qlc_device_count(int32_t* count);
 int32_t qlc_env_create(const qlc_config* cfg, qlc_env** out);         /* BreakoutEnvironment::new + ReplayBuffer::new */
@@ -125,7 +143,8 @@ int32_t qlc_host_free(void* p);
 /* reset(): mask_host NULL = all envs, else n_envs bytes (non-zero = reset). dir_x_host NULL = draw the initial
  * ball direction from the env's Philox stream (mechanics.rs:103), else n_envs explicit values. Synchronous. */
 int32_t qlc_env_reset(qlc_env* env, const uint8_t* mask_host, const float* dir_x_host);
-/* step() x n_steps for all envs in ONE launch. actions_dev [n_steps][n_envs] u8 (device);
+/* step() x n_steps for all envs in ONE launch (launches of more steps than the frame ring has time slots,
+ * replay_capacity / n_envs + 4, are split at that length). actions_dev [n_steps][n_envs] u8 (device);
  * reward_dev [n_steps][n_envs] f32 and done_dev [n_steps][n_envs] u8 (device, either may be NULL).
  * Each step also renders the 84x84 u8 frame into the frame ring and writes the replay transition record
  * (ReplayBuffer::add). Asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
@@ -147,6 +166,14 @@ int32_t qlc_env_state_view(qlc_env* env, qlc_state_view* out);
 int32_t qlc_env_read_state(qlc_env* env, const qlc_state_host* out);
 float   qlc_env_goal_mean(void);                                      /* episode_reward_goal_mean() = 59 */
 int32_t qlc_env_time(qlc_env* env, uint64_t* steps_taken);
+/* lives[n_envs]: the reference game has no lives counter - the episode ends the first time the ball passes the paddle
+ * (mechanics.rs:131-135) - so this is 1 while an env is not finished and 0 once it is. Synchronous. */
+int32_t qlc_env_lives_host(qlc_env* env, uint8_t* lives_host);
+/* batch_to_multi_dim_array for state handles (breakout_environment.rs:56-77): the stacks of n handles, [n] x layout, into a
+ * device / host buffer. The host form checks every handle (QLC_ERR_OUT_OF_RANGE: "stale state handle"); on the device path
+ * a dead handle gives an all-zero stack. */
+int32_t qlc_obs_gather(qlc_env* env, const qlc_obs_handle* handles_dev, uint32_t n, int32_t layout, void* out_dev, void* stream);
+int32_t qlc_obs_gather_host(qlc_env* env, const qlc_obs_handle* handles_host, uint32_t n, int32_t layout, void* out_host);
 int32_t qlc_env_error_flags(qlc_env* env, uint32_t* or_of_all);
 
 /* ---- ReplayBuffer (replay_buffer.rs:53-146) ---- */
@@ -157,13 +184,21 @@ int32_t qlc_replay_capacity(qlc_env* env, uint64_t* capacity);
 int32_t qlc_replay_sample(qlc_env* env, uint32_t batch, uint32_t n_batches, uint64_t call_index, uint32_t* idx_dev, void* stream);
 /* get_many + batch_to_multi_dim_array: gather n transitions by logical index (0 = oldest). state_dev / next_dev
  * [n] x layout (either may be NULL), reward_dev [n] f32, action_dev [n] u8, done_dev [n] u8 (any may be NULL).
- * Indices are not range-checked on the device path (an index >= len sets QLC_ENVERR-free zero output). */
+ * Indices are not range-checked on the device path: an index >= len gives all-zero stacks and zero scalars. */
 int32_t qlc_replay_gather(qlc_env* env, const uint32_t* idx_dev, uint32_t n, int32_t layout,
                           void* state_dev, void* next_dev, float* reward_dev, uint8_t* action_dev, uint8_t* done_dev, void* stream);
-/* host-buffer forms (range-check indices: QLC_ERR_OUT_OF_RANGE; copies inside; synchronous) */
+/* generate_distinct_random_ids + get_many + batch_to_multi_dim_array in ONE kernel launch (self_driving_tf_q_learner.rs:181-185):
+ * every CTA of the gather kernel derives the index of its own item from the Philox stream (seed, call_index + minibatch) -
+ * the same indices qlc_replay_sample gives. Items = n_batches x batch; idx_out_dev [n_batches][batch] u32 may be NULL. */
+int32_t qlc_replay_sample_gather(qlc_env* env, uint32_t batch, uint32_t n_batches, uint64_t call_index, int32_t layout, uint32_t* idx_out_dev,
+                                 void* state_dev, void* next_dev, float* reward_dev, uint8_t* action_dev, uint8_t* done_dev, void* stream);
+/* host-buffer forms (range-check indices: QLC_ERR_OUT_OF_RANGE; copies inside; synchronous). QLC_LAYOUT_F32_BXYH stacks cross
+ * PCIe as u8 and are widened into the caller's buffer by a small host thread pool (QLC_HOST_THREADS; bit-identical). */
 int32_t qlc_replay_sample_host(qlc_env* env, uint32_t batch, uint64_t call_index, uint32_t* idx_host);
 int32_t qlc_replay_gather_host(qlc_env* env, const uint32_t* idx_host, uint32_t n, int32_t layout,
                                void* state_host, void* next_host, float* reward_host, uint8_t* action_host, uint8_t* done_host);
+int32_t qlc_replay_sample_gather_host(qlc_env* env, uint32_t batch, uint64_t call_index, int32_t layout, uint32_t* idx_out_host,
+                                      void* state_host, void* next_host, float* reward_host, uint8_t* action_host, uint8_t* done_host);
 int32_t qlc_replay_action_counts(qlc_env* env, uint64_t counts[3]);   /* actions() histogram (learner log :242-245) */
 
 /* ---- episode statistics (replay_buffer.rs:100-124, self_driving_tf_q_learner.rs:134-139,220-223) ---- */
@@ -171,6 +206,23 @@ int32_t qlc_stats_read(qlc_env* env, qlc_episode_stats* out);         /* synchro
 /* device vector of 5 doubles {sum_return, episodes, steps, -min_return, max_return} refreshed on `stream`;
  * sum the first three and max-reduce the last two across ranks (ncclAllReduce / torch.distributed). */
 int32_t qlc_stats_export(qlc_env* env, double* out_dev, void* stream);
+/* ---- the same reduction behind the C ABI (a host without torch.distributed, e.g. the Rust `ql-cuda` crate): NCCL is bound at
+ * run time (dlopen "libnccl.so.2", QLC_NCCL_LIB overrides), one process per GPU, one communicator per env handle. Rank 0 calls
+ * qlc_comm_unique_id and hands the 128 bytes to the other ranks by whatever channel the host has (file, socket, env var);
+ * every rank then calls qlc_comm_init (collective, blocking). world == 1 with id == NULL needs no NCCL at all.
+ * qlc_stats_allreduce enqueues one reduction: nothing but an event record lands on `stream` (the caller's step stream) - the
+ * export of the shard's statistics as of the end of the last step launch (a snapshot the step kernel's last CTA takes, so later
+ * launches may already be running), ONE ncclAllGather of 5 doubles, the combine and the copy into a host mirror run on the
+ * communicator's own low-priority stream: it can be called after every step without being on the step path.
+ * qlc_stats_global returns the job-wide statistics of the last completed reduction (wait != 0: waits for the last enqueued). ---- */
+#define QLC_COMM_ID_BYTES 128
+int32_t qlc_comm_unique_id(uint8_t* id128);
+int32_t qlc_comm_init(qlc_env* env, int32_t rank, int32_t world, const uint8_t* id128);
+int32_t qlc_comm_destroy(qlc_env* env);                              /* also done by qlc_env_destroy */
+int32_t qlc_comm_info(qlc_env* env, int32_t* rank, int32_t* world, int32_t* nccl_version, int32_t* nccl_ranks);
+int32_t qlc_stats_allreduce(qlc_env* env, void* stream);
+int32_t qlc_stats_global(qlc_env* env, qlc_episode_stats* out, int32_t wait);
+
 int32_t qlc_stats_push(qlc_env* env, float episode_reward);           /* add_episode_reward */
 int32_t qlc_stats_mean(qlc_env* env, float* out);                     /* avg_episode_reward */
 int32_t qlc_stats_min(qlc_env* env, float* out);                      /* min_episode_reward */
@@ -190,7 +242,10 @@ typedef struct qlc_qnet_weights {          /* host f32 arrays in the Keras layou
 } qlc_qnet_weights;
 int32_t qlc_qnet_create(qlc_env* env, const qlc_qnet_weights* weights_host, qlc_qnet** out);
 int32_t qlc_qnet_set_weights(qlc_qnet* qnet, const qlc_qnet_weights* weights_host);
-int32_t qlc_qnet_destroy(qlc_qnet* qnet);
+int32_t qlc_qnet_destroy(qlc_qnet* qnet);   /* valid before or after qlc_env_destroy of its env; after it, every other qnet call fails */
+/* qlc_qnet_forward is asynchronous and cannot report a failed pass; this synchronises the device, returns the sticky flag
+ * (non-zero: an MMA completion barrier timed out, the outputs of that pass are undefined) and clears it. */
+int32_t qlc_qnet_error(qlc_qnet* qnet, uint32_t* flag);
 /* idx_dev NULL: the current observation of all n_envs envs (predict_action for every env); else n replay transitions by
  * logical index, which = 0 their state / 1 their state_next. Outputs (device, any may be NULL): q [n][3] f32, action [n] u8
  * (first maximum, tf.argmax), max_q [n] f32 (tf.reduce_max). Asynchronous on `stream`. */

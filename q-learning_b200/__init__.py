@@ -31,23 +31,27 @@ NUM_FRAMES = 4
 
 LAYOUT_U8_BHYX = 0
 LAYOUT_F32_BXYH = 1
+LAYOUT_U8_BXYH = 2
 
-OK, ERR_INVALID_ARG, ERR_CUDA, ERR_OUT_OF_RANGE, ERR_NO_DEVICE, ERR_NOT_ENOUGH = 0, 1, 2, 3, 4, 5
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_OUT_OF_RANGE, ERR_NO_DEVICE, ERR_NOT_ENOUGH, ERR_COMM = 0, 1, 2, 3, 4, 5, 6
+COMM_ID_BYTES = 128
 
 ENVERR_WALL_DISTANCE, ENVERR_APPROX_RANGE, ENVERR_RECURSION, ENVERR_BISECTION, ENVERR_DEGENERATE, ENVERR_ACTION, ENVERR_HANDOVER = 1, 2, 4, 8, 16, 32, 64
 
 # every symbol include/ql_cuda.h declares (checked by tests/test_abi.py against the header and the built library)
 ABI_SYMBOLS = [
-    "qlc_version", "qlc_last_error_string", "qlc_device_count", "qlc_env_create", "qlc_env_destroy", "qlc_sync",
+    "qlc_version", "qlc_build_info", "qlc_last_error_string", "qlc_device_count", "qlc_env_create", "qlc_env_destroy", "qlc_sync",
     "qlc_host_alloc", "qlc_host_free",
     "qlc_env_reset", "qlc_env_step", "qlc_env_step_host", "qlc_env_step_host_submit", "qlc_env_step_host_wait", "qlc_env_obs", "qlc_env_obs_host", "qlc_env_state_view",
-    "qlc_env_read_state", "qlc_env_goal_mean", "qlc_env_time", "qlc_env_error_flags",
-    "qlc_replay_len", "qlc_replay_capacity", "qlc_replay_sample", "qlc_replay_gather", "qlc_replay_sample_host",
-    "qlc_replay_gather_host", "qlc_replay_action_counts",
+    "qlc_env_read_state", "qlc_env_goal_mean", "qlc_env_time", "qlc_env_lives_host", "qlc_env_error_flags",
+    "qlc_obs_gather", "qlc_obs_gather_host",
+    "qlc_replay_len", "qlc_replay_capacity", "qlc_replay_sample", "qlc_replay_gather", "qlc_replay_sample_gather", "qlc_replay_sample_host",
+    "qlc_replay_gather_host", "qlc_replay_sample_gather_host", "qlc_replay_action_counts",
+    "qlc_comm_unique_id", "qlc_comm_init", "qlc_comm_destroy", "qlc_comm_info", "qlc_stats_allreduce", "qlc_stats_global",
     "qlc_env_save", "qlc_env_load",
     "qlc_stats_read", "qlc_stats_export", "qlc_stats_push", "qlc_stats_mean", "qlc_stats_min", "qlc_stats_window",
     "qlc_debug_collision_wall", "qlc_debug_collision_rect", "qlc_debug_collision_rect_batch", "qlc_debug_gemm_bf16",
-    "qlc_qnet_create", "qlc_qnet_set_weights", "qlc_qnet_destroy", "qlc_qnet_forward", "qlc_qnet_forward_host",
+    "qlc_qnet_create", "qlc_qnet_set_weights", "qlc_qnet_destroy", "qlc_qnet_error", "qlc_qnet_forward", "qlc_qnet_forward_host",
 ]
 
 
@@ -78,6 +82,14 @@ class QlcStateView(C.Structure):
         "ball_cx", "ball_cy", "ball_dx", "ball_dy", "pad_min_x", "pad_max_x", "pad_speed",
         "bricks", "score", "episode_step", "episode", "err", "finished", "frames", "records")] + [
         ("n_envs", C.c_uint32), ("time_slots", C.c_uint32), ("time", C.c_uint64)]
+
+
+class QlcObsHandle(C.Structure):
+    """qlc_obs_handle: the observation of env `env` after `time` env-steps, `k` of them in the current episode."""
+    _fields_ = [("time", C.c_uint64), ("k", C.c_uint32), ("env", C.c_uint32)]
+
+
+OBS_HANDLE_DTYPE = np.dtype([("time", np.uint64), ("k", np.uint32), ("env", np.uint32)])
 
 
 class QlcQnetWeights(C.Structure):
@@ -115,6 +127,7 @@ def load_library(build_if_missing=True):
     vp, i32, u32, u64 = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64
     sig = {
         "qlc_version": (i32, []),
+        "qlc_build_info": (C.c_char_p, []),
         "qlc_last_error_string": (C.c_char_p, []),
         "qlc_device_count": (i32, [vp]),
         "qlc_env_create": (i32, [C.POINTER(QlcConfig), C.POINTER(vp)]),
@@ -134,6 +147,18 @@ def load_library(build_if_missing=True):
         "qlc_env_goal_mean": (C.c_float, []),
         "qlc_env_time": (i32, [vp, C.POINTER(u64)]),
         "qlc_env_error_flags": (i32, [vp, C.POINTER(u32)]),
+        "qlc_env_lives_host": (i32, [vp, vp]),
+        "qlc_obs_gather": (i32, [vp, vp, u32, i32, vp, vp]),
+        "qlc_obs_gather_host": (i32, [vp, vp, u32, i32, vp]),
+        "qlc_replay_sample_gather": (i32, [vp, u32, u32, u64, i32, vp, vp, vp, vp, vp, vp, vp]),
+        "qlc_replay_sample_gather_host": (i32, [vp, u32, u64, i32, vp, vp, vp, vp, vp, vp]),
+        "qlc_comm_unique_id": (i32, [vp]),
+        "qlc_comm_init": (i32, [vp, i32, i32, vp]),
+        "qlc_comm_destroy": (i32, [vp]),
+        "qlc_comm_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "qlc_stats_allreduce": (i32, [vp, vp]),
+        "qlc_stats_global": (i32, [vp, C.POINTER(QlcEpisodeStats), i32]),
+        "qlc_qnet_error": (i32, [vp, C.POINTER(u32)]),
         "qlc_replay_len": (i32, [vp, C.POINTER(u64)]),
         "qlc_replay_capacity": (i32, [vp, C.POINTER(u64)]),
         "qlc_replay_sample": (i32, [vp, u32, u32, u64, vp, vp]),
@@ -205,10 +230,33 @@ class PinnedArray:
             pass
 
 
+def build_info():
+    """{'src_hash': ..., 'profiling': '0' | '1'} of the loaded library (profiling = 1: an ablation build that honours QLC_DEBUG_SKIP)."""
+    text = load_library().qlc_build_info().decode()
+    return dict(kv.split("=", 1) for kv in text.strip(";").split(";"))
+
+
 def device_count():
     n = C.c_int32(0)
     rc = load_library().qlc_device_count(C.byref(n))
     return n.value if rc == OK else 0
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the C ABI: 128 bytes for rank 0 to hand to the other ranks."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    _check(load_library().qlc_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def _stack_shape(n, layout):
+    if layout == LAYOUT_U8_BHYX:
+        return (n, NUM_FRAMES, FRAME_H, FRAME_W), np.uint8
+    if layout == LAYOUT_F32_BXYH:
+        return (n, FRAME_W, FRAME_H, NUM_FRAMES), np.float32
+    if layout == LAYOUT_U8_BXYH:
+        return (n, FRAME_W, FRAME_H, NUM_FRAMES), np.uint8
+    raise QlError("unknown layout")
 
 
 class BreakoutAction(enum.IntEnum):
@@ -352,12 +400,8 @@ class BreakoutEnvironment:
         return t.value
 
     def obs(self, layout=LAYOUT_U8_BHYX):
-        if layout == LAYOUT_U8_BHYX:
-            out = np.empty((self.n_envs, NUM_FRAMES, FRAME_H, FRAME_W), dtype=np.uint8)
-        elif layout == LAYOUT_F32_BXYH:
-            out = np.empty((self.n_envs, FRAME_W, FRAME_H, NUM_FRAMES), dtype=np.float32)
-        else:
-            raise QlError("unknown layout")
+        shape, dt = _stack_shape(self.n_envs, layout)
+        out = np.empty(shape, dtype=dt)
         _check(self._L.qlc_env_obs_host(self._h, layout, _np_ptr(out)))
         return out
 
@@ -373,12 +417,52 @@ class BreakoutEnvironment:
         f["finished"] = np.empty(n, dtype=np.uint8)
         sh = QlcStateHost(*[f[name].ctypes.data for name, _ in QlcStateHost._fields_])
         _check(self._L.qlc_env_read_state(self._h, C.byref(sh)))
+        f["lives"] = (f["finished"] == 0).astype(np.uint8)      # one life per episode (mechanics.rs:131-135)
         return f
 
     def state_view(self):
         v = QlcStateView()
         _check(self._L.qlc_env_state_view(self._h, C.byref(v)))
         return v
+
+    def lives(self):
+        """u8 [n_envs]: 1 while an env's episode runs, 0 once it is over (the reference game ends with the first miss,
+        mechanics.rs:131-135: there is no lives counter to decrement)."""
+        out = np.empty(self.n_envs, dtype=np.uint8)
+        _check(self._L.qlc_env_lives_host(self._h, _np_ptr(out)))
+        return out
+
+    def obs_gather(self, handles, layout=LAYOUT_F32_BXYH):
+        """Stacks of state handles (numpy array of OBS_HANDLE_DTYPE: time, k, env) into a host array."""
+        h = np.ascontiguousarray(handles, dtype=OBS_HANDLE_DTYPE)
+        shape, dt = _stack_shape(h.size, layout)
+        out = np.empty(shape, dtype=dt)
+        _check(self._L.qlc_obs_gather_host(self._h, _np_ptr(h), h.size, layout, _np_ptr(out)))
+        return out
+
+    def obs_gather_device(self, handles_ptr, n, layout, out_ptr, stream=None):
+        _check(self._L.qlc_obs_gather(self._h, handles_ptr, n, layout, out_ptr, stream))
+
+    # -- statistics reduction over the env shards, NCCL behind the C ABI (one process per GPU)
+    def comm_init(self, rank, world, unique_id=None):
+        """unique_id: the 128 bytes rank 0 got from comm_unique_id(), handed to every rank by the host's own channel
+        (torch.distributed broadcast, a file, ...). world == 1 without an id needs no NCCL."""
+        buf = None if unique_id is None else (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        _check(self._L.qlc_comm_init(self._h, rank, world, buf))
+
+    def comm_info(self):
+        r, w, v, n = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        _check(self._L.qlc_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v), C.byref(n)))
+        return dict(rank=r.value, world=w.value, nccl_version=v.value, nccl_ranks=n.value)
+
+    def stats_allreduce(self, stream=None):
+        """Enqueue one reduction on the communicator's side stream (only an event record touches `stream`)."""
+        _check(self._L.qlc_stats_allreduce(self._h, stream))
+
+    def stats_global(self, wait=True):
+        s = QlcEpisodeStats()
+        _check(self._L.qlc_stats_global(self._h, C.byref(s), 1 if wait else 0))
+        return dict(sum_return=s.sum_return, episodes=s.episodes, steps=s.steps, min_return=s.min_return, max_return=s.max_return)
 
     def error_flags(self):
         e = C.c_uint32(0)
@@ -486,12 +570,7 @@ class ReplayBuffer:
         until the next get_many(reuse=True) of the same size) instead of fresh pageable arrays."""
         idx = np.ascontiguousarray(indices, dtype=np.uint32)
         n = idx.size
-        if layout == LAYOUT_U8_BHYX:
-            shape, dt = (n, NUM_FRAMES, FRAME_H, FRAME_W), np.uint8
-        elif layout == LAYOUT_F32_BXYH:
-            shape, dt = (n, FRAME_W, FRAME_H, NUM_FRAMES), np.float32
-        else:
-            raise QlError("unknown layout")
+        shape, dt = _stack_shape(n, layout)
         if reuse:
             key = (n, layout)
             if getattr(self, "_pinned_key", None) != key:
@@ -509,7 +588,30 @@ class ReplayBuffer:
                                               None if sn is None else _np_ptr(sn), _np_ptr(reward), _np_ptr(action), _np_ptr(done)))
         return BufferSample(s, sn, reward, action, done)
 
+    def sample(self, batch, layout=LAYOUT_F32_BXYH, call_index=None, want_state=True, want_next=True):
+        """generate_distinct_random_ids + get_many + batch_to_multi_dim_array as ONE kernel launch (the kernel draws the indices
+        itself), into host arrays: (indices u32[batch], BufferSample)."""
+        if call_index is None:
+            call_index = self._calls
+            self._calls += 1
+        shape, dt = _stack_shape(batch, layout)
+        s = np.empty(shape, dtype=dt) if want_state else None
+        sn = np.empty(shape, dtype=dt) if want_next else None
+        idx = np.empty(batch, dtype=np.uint32)
+        reward = np.empty(batch, dtype=np.float32)
+        action = np.empty(batch, dtype=np.uint8)
+        done = np.empty(batch, dtype=np.uint8)
+        _check(self._L.qlc_replay_sample_gather_host(self._env._h, batch, call_index, layout, _np_ptr(idx), None if s is None else _np_ptr(s),
+                                                     None if sn is None else _np_ptr(sn), _np_ptr(reward), _np_ptr(action), _np_ptr(done)))
+        return idx, BufferSample(s, sn, reward, action, done)
+
     # device-buffer forms
+    def sample_gather_device(self, batch, n_batches, call_index, layout, idx_out_ptr, state_ptr, next_ptr, reward_ptr=None, action_ptr=None, done_ptr=None,
+                             stream=None):
+        """sample + gather in one launch on device buffers (idx_out_ptr may be None)."""
+        _check(self._L.qlc_replay_sample_gather(self._env._h, batch, n_batches, call_index, layout, idx_out_ptr, state_ptr, next_ptr, reward_ptr, action_ptr,
+                                                done_ptr, stream))
+
     def sample_device(self, batch, n_batches, call_index, idx_ptr, stream=None):
         _check(self._L.qlc_replay_sample(self._env._h, batch, n_batches, call_index, idx_ptr, stream))
 
@@ -612,6 +714,12 @@ class QNetwork:
         m = np.empty(n, dtype=np.float32)
         _check(self._L.qlc_qnet_forward_host(self._h, None if idx is None else _np_ptr(idx), n, which, _np_ptr(q), _np_ptr(a), _np_ptr(m)))
         return q, a, m
+
+    def error(self):
+        """Synchronise and return (then clear) the sticky time-out flag of the asynchronous forward_device passes."""
+        e = C.c_uint32(0)
+        _check(self._L.qlc_qnet_error(self._h, C.byref(e)))
+        return e.value
 
     def forward_device(self, idx_ptr, n, which, q_ptr=None, action_ptr=None, max_q_ptr=None, stream=None):
         _check(self._L.qlc_qnet_forward(self._h, idx_ptr, n, which, q_ptr, action_ptr, max_q_ptr, stream))

@@ -1,0 +1,31 @@
+// comm.h — NCCL, bound at run time (dlopen) so that libqlcuda.so has no link-time dependency on it: a single-GPU host never
+// loads it, a multi-GPU host gets whichever libnccl.so.2 its process already uses (e.g. the one PyTorch ships) or the system one.
+// Only use: the episode-statistics reduction of the env shards — nothing on the step path.
+#pragma once
+#include <cstddef>
+#include <string>
+
+namespace qlc_comm {
+
+// the handful of NCCL declarations used (ABI-stable since NCCL 2.0; values from nccl.h)
+struct UniqueId { char internal[128]; };
+typedef struct ncclComm* Comm;
+enum { kFloat64 = 8 };
+enum { kSum = 0, kMax = 2 };
+
+struct Api {
+    int (*GetVersion)(int*);
+    int (*GetUniqueId)(UniqueId*);
+    int (*CommInitRank)(Comm*, int, UniqueId, int);
+    int (*CommDestroy)(Comm);
+    int (*CommCount)(Comm, int*);
+    int (*AllGather)(const void*, void*, size_t, int, Comm, void* /*cudaStream_t*/);
+    int (*AllReduce)(const void*, void*, size_t, int, int, Comm, void* /*cudaStream_t*/);
+    const char* (*GetErrorString)(int);
+    std::string path;      // what was loaded
+};
+
+// NULL + *why when libnccl cannot be loaded (QLC_NCCL_LIB overrides the name). Thread-safe, loaded once.
+const Api* api(std::string* why);
+
+}  // namespace qlc_comm

@@ -32,9 +32,16 @@ struct DeviceStats {                      // order-independent accumulators
 
 struct RasterTables;
 
+// Release builds cannot skip work: the ablation switch exists only in -DQLC_PROFILING builds (qlc_build_info() says which).
+#ifdef QLC_PROFILING
+#define QLC_DEBUG_SKIP_IS(p, v) ((p).debug_skip == (v))
+#else
+#define QLC_DEBUG_SKIP_IS(p, v) false
+#endif
+
 struct StepParams {
     uint32_t n_envs, env_id_base, time_slots, max_episode_steps, auto_reset, n_steps;
-    uint32_t debug_skip;       // profiling aid (QLC_DEBUG_SKIP): 1 = no physics, 2 = no frame stores; 0 in production
+    uint32_t debug_skip;       // ablation aid, only honoured in -DQLC_PROFILING builds (QLC_DEBUG_SKIP): 1 = no physics, 2 = no frame stores
     const RasterTables* tables;   // built once per env handle by raster_tables_kernel
     unsigned int* work_counter; uint32_t work_base;   // work hand-out: first item = blockIdx.x, then gridDim.x + atomicAdd(counter, 1) - base
     // time chunking (0 = off): an item is (chunk c, batch b) = steps [c*chunk_len, (c+1)*chunk_len) of batch b; chunk c of a
@@ -44,6 +51,9 @@ struct StepParams {
     uint32_t epc;              // envs per CTA (<= R*NE), chosen by the host so that the grid fills all SMs evenly
     uint64_t t0, seed;
     uint8_t* frames; uint32_t* records; DeviceStats* stats;
+    // statistics snapshot (NULL = off): the last CTA to finish copies the shard accumulators here, so that a reduction running on
+    // a side stream reads the state "after this launch" while later launches already mutate `stats`
+    DeviceStats* snap; unsigned int* exit_counter; uint32_t exit_base;
     const uint8_t* actions; float* reward; uint8_t* done;
 };
 
@@ -263,7 +273,7 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             if (active && s + 1 < p.n_steps) next_action = p.actions[(size_t)(s + 1) * p.n_envs + e];
             if (action >= 3u) { env.err |= ENVERR_ACTION; action = 0u; }
             const uint32_t score_before = env.score;
-            if (active && p.debug_skip != 1u) time_step(env, action, mc);
+            if (active && !QLC_DEBUG_SKIP_IS(p, 1u)) time_step(env, action, mc);
             if (seq >= (uint32_t)D) mbar_wait(&S.empty[q], ((seq / D) - 1) & 1);
             if (active) {
                 RenderRec rr;
@@ -310,6 +320,17 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             if (lane == 0) st_release_u64(&p.progress[batch], ((unsigned long long)p.launch_serial << 32) | s_end);
         }
         }   // items
+        if (p.snap) {    // every statistics atomic of this CTA is done: count it out, the last one takes the snapshot
+            __threadfence();
+            __syncwarp();
+            if (lane == 0 && atomicAdd(p.exit_counter, 1u) - p.exit_base == gridDim.x - 1u) {
+                __threadfence();
+                DeviceStats v;
+                v.sum_return = atomicAdd(&p.stats->sum_return, 0ull); v.episodes = atomicAdd(&p.stats->episodes, 0ull);
+                v.min_return = atomicMin(&p.stats->min_return, 0xFFFFFFFFu); v.max_return = atomicMax(&p.stats->max_return, 0u);
+                *p.snap = v;
+            }
+        }
     } else {
         // ------------------------------- render warps -------------------------------
         const int rw = warp - 1;
@@ -430,7 +451,7 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
                 __syncwarp();
                 // ---- the group's frames leave as one bulk group (committed even when empty, so the count stays uniform) ----
                 if (lane == 0) {
-                    if (p.debug_skip != 2u) {
+                    if (!QLC_DEBUG_SKIP_IS(p, 2u)) {
                         #pragma unroll
                         for (int f = 0; f < FPG; ++f) {
                             const int i = g * FPG + f;
@@ -465,190 +486,275 @@ __global__ void env_reset_kernel(EnvArrays st, uint32_t n_envs, uint32_t env_id_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Kernel 3: distinct uniform index sampling (generate_distinct_random_ids) — one CTA per minibatch.
-// The sequential rejection loop of the reference keeps the FIRST OCCURRENCES of the accepted draws, in stream
-// order; that set is computed in parallel: 1024 raw Philox draws per round, a shared-memory hash table keeps the
-// smallest stream position per value, an ordered block scan compacts the first occurrences.
+// Distinct uniform index sampling (generate_distinct_random_ids, self_driving_tf_q_learner.rs:276-296) as a WARP routine.
+// The reference's sequential rejection loop keeps the FIRST OCCURRENCES of the accepted draws, in stream order. Draw p of
+// minibatch `call` is word p & 3 of philox({p >> 2, call_lo, call_hi, 'SAMP'}), mapped to [0, len) by Lemire's multiply-shift
+// with rejection. The warp walks the stream 32 positions at a time: duplicates inside the 32 are resolved with
+// __match_any_sync (lowest lane = first occurrence), duplicates of earlier positions with a small shared-memory hash set
+// (atomicCAS insert); ranks come from ballots. Because the routine is cheap (one Philox block per lane and 128 positions) it
+// runs INSIDE the gather kernels — every CTA derives the index of its own item and stops as soon as it has it — so that a
+// sampled minibatch is ONE kernel launch; the index-only entry point (qlc_replay_sample) runs the same routine, one warp
+// per minibatch, storing all of them.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int SAMPLE_THREADS = 256, SAMPLE_TABLE = 4096, SAMPLE_MAX_BATCH = 1024;
+constexpr int SAMPLE_MAX_BATCH = 1024;
+constexpr uint32_t SAMPLE_EMPTY = 0xFFFFFFFFu;           // never a value: len < 2^32 - 1 is checked by the host
+constexpr uint32_t SAMPLE_MAX_BLOCKS = 1u << 19;         // x 128 stream positions: the bound of the "loop" in the reference
 
-__global__ void __launch_bounds__(SAMPLE_THREADS) replay_sample_kernel(uint32_t* out, uint32_t batch, uint32_t len, uint64_t seed, uint64_t call0) {
-    __shared__ uint32_t tval[SAMPLE_TABLE], tpos[SAMPLE_TABLE];
-    __shared__ uint32_t warp_tot[SAMPLE_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t call = call0 + blockIdx.x;
-    uint32_t* dst = out + (size_t)blockIdx.x * batch;
-    for (int i = tid; i < SAMPLE_TABLE; i += SAMPLE_THREADS) { tval[i] = 0xFFFFFFFFu; tpos[i] = 0xFFFFFFFFu; }
-    __syncthreads();
+__host__ __device__ __forceinline__ uint32_t sample_table_size(uint32_t batch) {   // power of two >= 2 * (batch + 32)
+    uint32_t n = 128;
+    while (n < 2u * (batch + 32u)) n <<= 1;
+    return n;                                                                       // <= 4096 entries = 16 KB
+}
+
+// ALL = false: returns the index of item j of the minibatch (every lane gets it).  ALL = true: stores the first `batch`
+// indices to out[0..batch) and returns 0.  `table` = sample_table_size(batch) words of shared memory, all SAMPLE_EMPTY.
+template <bool ALL>
+__device__ __forceinline__ uint32_t sample_distinct_warp(uint32_t* table, uint32_t tsize, uint32_t len, uint64_t seed, uint64_t call,
+                                                         uint32_t j, uint32_t batch, uint32_t* out, int lane) {
     const uint32_t thresh = (uint32_t)((0x100000000ull - (uint64_t)len) % (uint64_t)len);   // Lemire rejection zone
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t tmask = tsize - 1u, lt = (1u << lane) - 1u;
     uint32_t kept = 0;
-    for (uint32_t round = 0; round < 65536u && kept < batch; ++round) {
-        const uint32_t ctr = round * SAMPLE_THREADS + tid;
-        const uint4 r = philox4x32_10(make_uint4(ctr, (uint32_t)call, (uint32_t)(call >> 32), STREAM_SAMPLE), key);
-        const uint32_t raw[4] = {r.x, r.y, r.z, r.w};
-        uint32_t val[4], slot[4]; bool valid[4];
-        #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const uint64_t m = (uint64_t)raw[w] * (uint64_t)len;
-            valid[w] = !((uint32_t)m < thresh);
-            val[w] = (uint32_t)(m >> 32);
-            slot[w] = 0;
-            if (valid[w]) {
-                uint32_t h = (val[w] * 0x9E3779B1u) >> 20;          // 12-bit hash
+    for (uint32_t blk = 0; blk < SAMPLE_MAX_BLOCKS; ++blk) {
+        const uint4 r = philox4x32_10(make_uint4(blk * 32u + (uint32_t)lane, (uint32_t)call, (uint32_t)(call >> 32), STREAM_SAMPLE), key);
+        #pragma unroll 1
+        for (int sub = 0; sub < 4; ++sub) {
+            // stream position blk*128 + sub*32 + lane lives in word (lane & 3) of the block of lane sub*8 + (lane >> 2)
+            const int src = sub * 8 + (lane >> 2);
+            const uint32_t x = __shfl_sync(0xFFFFFFFFu, r.x, src), y = __shfl_sync(0xFFFFFFFFu, r.y, src);
+            const uint32_t z = __shfl_sync(0xFFFFFFFFu, r.z, src), w = __shfl_sync(0xFFFFFFFFu, r.w, src);
+            const uint32_t raw = (lane & 2) ? ((lane & 1) ? w : z) : ((lane & 1) ? y : x);
+            const uint64_t m = (uint64_t)raw * (uint64_t)len;
+            const bool valid = !((uint32_t)m < thresh);
+            const uint32_t val = (uint32_t)(m >> 32);
+            const unsigned long long mkey = valid ? ((1ull << 32) | val) : (unsigned long long)lane;   // rejected draws match nobody
+            const uint32_t same = __match_any_sync(0xFFFFFFFFu, mkey);
+            bool fresh = false;
+            if (valid && (uint32_t)lane == (uint32_t)(__ffs(same) - 1)) {                            // first occurrence among these 32
+                uint32_t h = (val * 0x9E3779B1u) >> 7 & tmask;
                 for (;;) {
-                    const uint32_t old = atomicCAS(&tval[h], 0xFFFFFFFFu, val[w]);
-                    if (old == 0xFFFFFFFFu || old == val[w]) break;
-                    h = (h + 1) & (SAMPLE_TABLE - 1);
+                    const uint32_t old = atomicCAS(&table[h], SAMPLE_EMPTY, val);
+                    if (old == SAMPLE_EMPTY) { fresh = true; break; }                                // not seen at an earlier position
+                    if (old == val) break;
+                    h = (h + 1u) & tmask;
                 }
-                slot[w] = h;
-                atomicMin(&tpos[h], ctr * 4u + (uint32_t)w);
+            }
+            const uint32_t acc = __ballot_sync(0xFFFFFFFFu, fresh);
+            const uint32_t rank = kept + __popc(acc & lt);
+            if (ALL) {
+                if (fresh && rank < batch) out[rank] = val;
+                kept += __popc(acc);
+                if (kept >= batch) return 0u;
+            } else {
+                const uint32_t hit = __ballot_sync(0xFFFFFFFFu, fresh && rank == j);
+                if (hit) return __shfl_sync(0xFFFFFFFFu, val, __ffs(hit) - 1);
+                kept += __popc(acc);
             }
         }
-        __syncthreads();
-        bool first[4]; uint32_t cnt = 0;
-        #pragma unroll
-        for (int w = 0; w < 4; ++w) { first[w] = valid[w] && tpos[slot[w]] == ctr * 4u + (uint32_t)w; cnt += first[w] ? 1u : 0u; }
-        // ordered exclusive scan of cnt over the block
-        uint32_t incl = cnt;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        uint32_t base = kept;
-        for (int w = 0; w < warp; ++w) base += warp_tot[w];
-        uint32_t total = 0;
-        for (int w = 0; w < SAMPLE_THREADS / 32; ++w) total += warp_tot[w];
-        uint32_t pos = base + incl - cnt;
-        #pragma unroll
-        for (int w = 0; w < 4; ++w) if (first[w]) { if (pos < batch) dst[pos] = val[w]; ++pos; }
-        kept += total;
-        __syncthreads();
     }
+    return 0u;   // unreachable for len >= batch (the reference would loop forever here)
+}
+
+// index-only form: one warp per minibatch
+__global__ void __launch_bounds__(32) replay_sample_kernel(uint32_t* out, uint32_t batch, uint32_t len, uint64_t seed, uint64_t call0) {
+    __shared__ uint32_t table[4096];
+    const int lane = threadIdx.x;
+    const uint32_t tsize = sample_table_size(batch);
+    for (uint32_t i = lane; i < tsize; i += 32) table[i] = SAMPLE_EMPTY;
+    __syncwarp();
+    sample_distinct_warp<true>(table, tsize, len, seed, call0 + blockIdx.x, 0u, batch, out + (size_t)blockIdx.x * batch, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Kernel 4/5: frame-stack gather (ReplayBuffer::get_many + batch_to_multi_dim_array, and Environment::state).
+// Frame-stack gather (ReplayBuffer::get_many + batch_to_multi_dim_array, and Environment::state).
 // A transition at time T of env e with k frames already in its episode uses frames F_{T-d}: state d=1..4,
 // next d=0..3, valid iff d <= k; F_{T-d} sits in ring slot (k-d) mod 4 of the reference's FrameRingBuffer.
+// Where an item comes from (GatherParams::mode):
+//   GATHER_INDICES  logical replay indices given by the caller (get_many)
+//   GATHER_CURRENT  item b = env b at the current time (Environment::state for the whole shard)
+//   GATHER_HANDLES  state handles {time, k, env} (what a cloned BreakoutState is on the host: two integers, not pixels)
+//   GATHER_SAMPLE   the kernel draws the distinct indices itself (minibatch = item / batch): sample + gather in one launch
 // ---------------------------------------------------------------------------------------------------------
+enum { GATHER_INDICES = 0, GATHER_CURRENT = 1, GATHER_HANDLES = 2, GATHER_SAMPLE = 3 };
+
+struct ObsHandle { unsigned long long time; uint32_t k, env; };   // = qlc_obs_handle
+
 struct GatherParams {
     const uint8_t* frames; const uint32_t* records; const uint32_t* episode_step;
-    const uint32_t* indices;   // NULL => observation mode: item b is env b at the current time (state only)
-    uint32_t n_items, n_envs, time_slots;
+    const uint32_t* indices; const ObsHandle* handles;
+    uint32_t mode, n_items, n_envs, time_slots;
     uint64_t t_now, t_oldest;  // replay holds transitions of times [t_oldest, t_now)
+    uint32_t sample_batch, sample_len; uint64_t seed, call0; uint32_t* idx_out;   // GATHER_SAMPLE
     void* out_state; void* out_next;
     float* reward; uint8_t* action; uint8_t* done;
 };
 
-__device__ __forceinline__ void locate(const GatherParams& g, uint32_t b, uint64_t& T, uint32_t& e, uint32_t& k, uint32_t& rec) {
-    if (g.indices) {
-        const uint32_t idx = g.indices[b];
-        T = g.t_oldest + idx / g.n_envs; e = idx % g.n_envs;
-        if (T >= g.t_now) { T = g.t_now; k = 0; rec = 0; return; }    // out of range: all-zero item
-        rec = g.records[(size_t)(T % g.time_slots) * g.n_envs + e];
-        const uint32_t kmin = (rec >> 5) & 7u, kmod = (rec >> 3) & 3u;
-        k = kmin < 4u ? kmin : 4u + kmod;    // any k' with k' mod 4 and min(k',4) preserved
-    } else {
-        T = g.t_now; e = b; rec = 0;
+// false = the item does not exist (index >= len, handle whose frames have left the ring): every slot is zero-filled
+__device__ __forceinline__ bool locate(const GatherParams& g, uint32_t b, uint32_t idx, uint64_t& T, uint32_t& e, uint32_t& k, uint32_t& rec) {
+    rec = 0; k = 0; e = 0; T = g.t_now;
+    if (g.mode == GATHER_CURRENT) {
+        e = b;
         const uint32_t ks = g.episode_step[e];
         k = ks < 4u ? ks : 4u + (ks & 3u);
+        return true;
     }
+    if (g.mode == GATHER_HANDLES) {
+        const ObsHandle h = g.handles[b];
+        const uint32_t need = h.k < 4u ? h.k : 4u;                      // frames F_{T-1} .. F_{T-need} must still be in the ring
+        if (h.env >= g.n_envs || h.time > g.t_now || h.time < need || h.time - need + g.time_slots < g.t_now) return false;
+        T = h.time; e = h.env; k = h.k < 4u ? h.k : 4u + (h.k & 3u);
+        return true;
+    }
+    T = g.t_oldest + idx / g.n_envs; e = idx % g.n_envs;
+    if (T >= g.t_now) { T = g.t_now; e = 0; return false; }
+    rec = g.records[(size_t)(T % g.time_slots) * g.n_envs + e];
+    const uint32_t kmin = (rec >> 5) & 7u, kmod = (rec >> 3) & 3u;
+    k = kmin < 4u ? kmin : 4u + kmod;    // any k' with k' mod 4 and min(k',4) preserved
+    return true;
+}
+
+// which frame of the ring (time-slot * n_envs + env) holds ring slot h of item b's stack; ~0u = zero-filled slot
+__device__ __forceinline__ uint4 slot_frames(const GatherParams& g, uint32_t b, uint32_t which) {
+    uint64_t T; uint32_t e, k, rec;
+    const bool exists = locate(g, b, g.mode == GATHER_INDICES ? g.indices[b] : 0u, T, e, k, rec);
+    uint32_t f[4];
+    #pragma unroll
+    for (uint32_t h = 0; h < 4; ++h) {
+        const uint32_t d = which ? ((k - h) & 3u) : (((k - h - 1u) & 3u) + 1u);
+        f[h] = (exists && d <= k) ? (uint32_t)((T - d) % g.time_slots) * g.n_envs + e : 0xFFFFFFFFu;
+    }
+    return make_uint4(f[0], f[1], f[2], f[3]);
+}
+
+__device__ __forceinline__ void write_scalars(const GatherParams& g, uint32_t b, uint32_t rec) {
+    if (g.reward) g.reward[b] = (float)((rec >> 8) & 0xFFu);
+    if (g.action) g.action[b] = (uint8_t)(rec & 3u);
+    if (g.done) g.done[b] = (uint8_t)((rec >> 2) & 1u);
 }
 
 // u8 [b][slot][y][x]: one warp per item; <= 5 distinct frames in, 8 frames out, all as 7,056-byte bulk copies.
 __global__ void __launch_bounds__(32) gather_u8_kernel(GatherParams g) {
-    extern __shared__ __align__(128) uint8_t sm[];     // 5 frames + 1 zero frame
+    extern __shared__ __align__(128) uint8_t sm[];     // 5 frames + 1 zero frame; the sampler's hash set borrows the first 16 KB
     __shared__ uint64_t bar;
     const int lane = threadIdx.x;
     const uint32_t b = blockIdx.x;
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // launched with programmatic stream serialization: the indices come from the sample kernel
-    uint64_t T; uint32_t e, k, rec;
-    locate(g, b, T, e, k, rec);
     uint8_t* zero = sm + 5 * FRAME_BYTES;
     for (int i = lane; i < FRAME_VEC16; i += 32) reinterpret_cast<uint4*>(zero)[i] = make_uint4(0, 0, 0, 0);
     if (lane == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0 && !g.out_state && !g.out_next) {      // scalars only (get_many without tensorisation)
-        if (g.reward) g.reward[b] = (float)((rec >> 8) & 0xFFu);
-        if (g.action) g.action[b] = (uint8_t)(rec & 3u);
-        if (g.done) g.done[b] = (uint8_t)((rec >> 2) & 1u);
-        return;
+    uint32_t idx = 0;
+    if (g.mode == GATHER_SAMPLE) {
+        uint32_t* table = reinterpret_cast<uint32_t*>(sm);
+        const uint32_t tsize = sample_table_size(g.sample_batch);
+        for (uint32_t i = lane; i < tsize; i += 32) table[i] = SAMPLE_EMPTY;
+        __syncwarp();
+        const uint32_t mb = b / g.sample_batch, j = b - mb * g.sample_batch;
+        idx = sample_distinct_warp<false>(table, tsize, g.sample_len, g.seed, g.call0 + mb, j, g.sample_batch, nullptr, lane);
     }
+    // launched with programmatic stream serialization: everything above neither reads nor writes anything an earlier kernel touches
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (g.mode == GATHER_SAMPLE && lane == 0 && g.idx_out) g.idx_out[b] = idx;
+    if (g.mode == GATHER_INDICES) idx = g.indices[b];
+    uint64_t T; uint32_t e, k, rec;
+    const bool exists = locate(g, b, idx, T, e, k, rec);
+    fence_proxy_async_smem();                            // zero frame / hash set (generic proxy) before the bulk copies (async proxy)
+    __syncwarp();
     if (lane == 0) {
+        write_scalars(g, b, rec);
+        if (!g.out_state && !g.out_next) return;         // scalars only (get_many without tensorisation)
         const int d_lo = g.out_next ? 0 : 1, d_hi = g.out_state ? 4 : 3;
         uint32_t bytes = 0;
-        for (int d = d_lo; d <= d_hi; ++d) if ((uint32_t)d <= k) bytes += FRAME_BYTES;
-        mbar_expect_tx(&bar, bytes);
-        for (int d = d_lo; d <= d_hi; ++d)
-            if ((uint32_t)d <= k) {
-                const uint64_t Tf = T - (uint64_t)d;
-                bulk_load(sm + d * FRAME_BYTES, g.frames + ((size_t)(Tf % g.time_slots) * g.n_envs + e) * FRAME_BYTES, FRAME_BYTES, &bar);
-            }
-        mbar_wait(&bar, 0);
+        for (int d = d_lo; d <= d_hi; ++d) if (exists && (uint32_t)d <= k) bytes += FRAME_BYTES;
+        if (bytes) {
+            mbar_expect_tx(&bar, bytes);
+            for (int d = d_lo; d <= d_hi; ++d)
+                if ((uint32_t)d <= k) {
+                    const uint64_t Tf = T - (uint64_t)d;
+                    bulk_load(sm + d * FRAME_BYTES, g.frames + ((size_t)(Tf % g.time_slots) * g.n_envs + e) * FRAME_BYTES, FRAME_BYTES, &bar);
+                }
+            mbar_wait(&bar, 0);
+        }
         for (int h = 0; h < 4; ++h) {
             if (g.out_state) {
                 const uint32_t d = ((k - h - 1u) & 3u) + 1u;
-                bulk_store((uint8_t*)g.out_state + ((size_t)b * 4 + h) * FRAME_BYTES, d <= k ? sm + d * FRAME_BYTES : zero, FRAME_BYTES);
+                bulk_store((uint8_t*)g.out_state + ((size_t)b * 4 + h) * FRAME_BYTES, (exists && d <= k) ? sm + d * FRAME_BYTES : zero, FRAME_BYTES);
             }
             if (g.out_next) {
                 const uint32_t d = (k - h) & 3u;
-                bulk_store((uint8_t*)g.out_next + ((size_t)b * 4 + h) * FRAME_BYTES, d <= k ? sm + d * FRAME_BYTES : zero, FRAME_BYTES);
+                bulk_store((uint8_t*)g.out_next + ((size_t)b * 4 + h) * FRAME_BYTES, (exists && d <= k) ? sm + d * FRAME_BYTES : zero, FRAME_BYTES);
             }
         }
         bulk_commit();
-        if (g.reward) g.reward[b] = (float)((rec >> 8) & 0xFFu);
-        if (g.action) g.action[b] = (uint8_t)(rec & 3u);
-        if (g.done) g.done[b] = (uint8_t)((rec >> 2) & 1u);
         bulk_wait<0>();
     }
 }
 
-// f32 [b][x][y][slot]: one CTA per (item, which); 4 frames staged in shared memory by bulk copies, then a
-// conflict-free transposing read (row stride 84 B = 21 words) and one coalesced float4 store per pixel.
-constexpr int GATHER_F32_THREADS = 256;
-__global__ void __launch_bounds__(GATHER_F32_THREADS) gather_f32_kernel(GatherParams g) {
-    extern __shared__ __align__(128) uint8_t sm[];     // 4 slot frames
+// [b][x][y][slot] (the reference's ToMultiDimArray layout), as f32 (value = u8 as f32) or as u8: one CTA per (item, which);
+// 4 slot frames staged in shared memory by bulk copies, then a conflict-free transposing read (row stride 84 B = 21 words)
+// and one coalesced 16-byte (f32) / 4-byte (u8) store per pixel.
+constexpr int GATHER_XYH_THREADS = 256;
+__device__ __forceinline__ void store_pixel(float4* o, int idx, uint8_t a, uint8_t b, uint8_t c, uint8_t d) { o[idx] = make_float4((float)a, (float)b, (float)c, (float)d); }
+__device__ __forceinline__ void store_pixel(uchar4* o, int idx, uint8_t a, uint8_t b, uint8_t c, uint8_t d) { o[idx] = make_uchar4(a, b, c, d); }
+
+template <class Px>
+__global__ void __launch_bounds__(GATHER_XYH_THREADS) gather_xyh_kernel(GatherParams g) {
+    extern __shared__ __align__(128) uint8_t sm[];     // 4 slot frames; the sampler's hash set borrows the first 16 KB
     __shared__ uint64_t bar;
+    __shared__ uint32_t s_idx;
     const int tid = threadIdx.x;
     const uint32_t b = blockIdx.x >> 1, which = blockIdx.x & 1u;   // 0 = state, 1 = next
-    float4* out = reinterpret_cast<float4*>(which ? g.out_next : g.out_state);
-    if (!out) return;
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // launched with programmatic stream serialization: the indices come from the sample kernel
-    uint64_t T; uint32_t e, k, rec;
-    locate(g, b, T, e, k, rec);
+    Px* out = reinterpret_cast<Px*>(which ? g.out_next : g.out_state);
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    uint32_t idx = 0;
+    if (g.mode == GATHER_SAMPLE) {
+        uint32_t* table = reinterpret_cast<uint32_t*>(sm);
+        const uint32_t tsize = sample_table_size(g.sample_batch);
+        for (uint32_t i = tid; i < tsize; i += GATHER_XYH_THREADS) table[i] = SAMPLE_EMPTY;
+        __syncthreads();
+        if (tid < 32) {
+            const uint32_t mb = b / g.sample_batch, j = b - mb * g.sample_batch;
+            const uint32_t v = sample_distinct_warp<false>(table, tsize, g.sample_len, g.seed, g.call0 + mb, j, g.sample_batch, nullptr, tid);
+            if (tid == 0) s_idx = v;
+        }
+        __syncthreads();
+        idx = s_idx;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic stream serialization: nothing above touches an earlier kernel's data
+    if (g.mode == GATHER_SAMPLE && tid == 0 && g.idx_out && (which == 0 || !g.out_state)) g.idx_out[b] = idx;
+    if (g.mode == GATHER_INDICES) idx = g.indices[b];
+    uint64_t T; uint32_t e, k, rec;
+    const bool exists = locate(g, b, idx, T, e, k, rec);
+    if (tid == 0 && (which == 0 || !g.out_state)) write_scalars(g, b, rec);
+    if (!out) return;
     // zero-fill the slots that have no frame yet
     uint32_t dsl[4];
     #pragma unroll
     for (int h = 0; h < 4; ++h) {
         dsl[h] = which ? ((k - h) & 3u) : (((k - h - 1u) & 3u) + 1u);
+        if (!exists) dsl[h] = 0xFFFFu;
         if (dsl[h] > k)
-            for (int i = tid; i < FRAME_VEC16; i += GATHER_F32_THREADS) reinterpret_cast<uint4*>(sm + h * FRAME_BYTES)[i] = make_uint4(0, 0, 0, 0);
+            for (int i = tid; i < FRAME_VEC16; i += GATHER_XYH_THREADS) reinterpret_cast<uint4*>(sm + h * FRAME_BYTES)[i] = make_uint4(0, 0, 0, 0);
     }
+    fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
-        uint32_t bytes = 0;
-        for (int h = 0; h < 4; ++h) if (dsl[h] <= k) bytes += FRAME_BYTES;
-        mbar_expect_tx(&bar, bytes);
-        for (int h = 0; h < 4; ++h)
-            if (dsl[h] <= k) {
-                const uint64_t Tf = T - (uint64_t)dsl[h];
-                bulk_load(sm + h * FRAME_BYTES, g.frames + ((size_t)(Tf % g.time_slots) * g.n_envs + e) * FRAME_BYTES, FRAME_BYTES, &bar);
-            }
-        if (which == 0 || !g.out_state) {
-            if (g.reward) g.reward[b] = (float)((rec >> 8) & 0xFFu);
-            if (g.action) g.action[b] = (uint8_t)(rec & 3u);
-            if (g.done) g.done[b] = (uint8_t)((rec >> 2) & 1u);
+    uint32_t bytes = 0;
+    #pragma unroll
+    for (int h = 0; h < 4; ++h) if (dsl[h] <= k) bytes += FRAME_BYTES;
+    if (bytes) {
+        if (tid == 0) {
+            mbar_expect_tx(&bar, bytes);
+            for (int h = 0; h < 4; ++h)
+                if (dsl[h] <= k) {
+                    const uint64_t Tf = T - (uint64_t)dsl[h];
+                    bulk_load(sm + h * FRAME_BYTES, g.frames + ((size_t)(Tf % g.time_slots) * g.n_envs + e) * FRAME_BYTES, FRAME_BYTES, &bar);
+                }
         }
+        mbar_wait(&bar, 0);
     }
-    mbar_wait(&bar, 0);
-    float4* o = out + (size_t)b * FRAME_BYTES;
-    for (int idx = tid; idx < FRAME_BYTES; idx += GATHER_F32_THREADS) {
-        const int x = idx / FRAME_H, y = idx - x * FRAME_H;
+    Px* o = out + (size_t)b * FRAME_BYTES;
+    for (int i = tid; i < FRAME_BYTES; i += GATHER_XYH_THREADS) {
+        const int x = i / FRAME_H, y = i - x * FRAME_H;
         const int src = y * FRAME_W + x;
-        o[idx] = make_float4((float)sm[src], (float)sm[FRAME_BYTES + src], (float)sm[2 * FRAME_BYTES + src], (float)sm[3 * FRAME_BYTES + src]);
+        store_pixel(o, i, sm[src], sm[FRAME_BYTES + src], sm[2 * FRAME_BYTES + src], sm[3 * FRAME_BYTES + src]);
     }
 }
 
@@ -668,9 +774,25 @@ __global__ void action_histogram_kernel(const uint32_t* records, uint32_t n_envs
     if ((threadIdx.x & 31) == 0) { atomicAdd(&counts[0], c0); atomicAdd(&counts[1], c1); atomicAdd(&counts[2], c2); }
 }
 
+// "lives" of the reference game: the episode ends the first time the ball passes the paddle (mechanics.rs:131-135), so an
+// env has exactly one life while it is not finished
+__global__ void lives_kernel(const uint8_t* finished, uint8_t* lives, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lives[i] = finished[i] ? 0 : 1;
+}
+
 __global__ void stats_export_kernel(const DeviceStats* s, uint64_t steps, double* out) {
     out[0] = (double)s->sum_return; out[1] = (double)s->episodes; out[2] = (double)steps;
     out[3] = s->episodes ? -(double)s->min_return : -1.0e300; out[4] = s->episodes ? (double)s->max_return : -1.0e300;
+}
+// all-gathered per-rank vectors [world][5] -> {sum, sum, sum, max, max} (one collective instead of a sum- and a max-all-reduce)
+__global__ void stats_combine_kernel(const double* gathered, int world, double* out) {
+    double a = 0.0, b = 0.0, c = 0.0, d = -1.0e300, e = -1.0e300;
+    for (int r = 0; r < world; ++r) {
+        const double* v = gathered + 5 * r;
+        a += v[0]; b += v[1]; c += v[2]; d = v[3] > d ? v[3] : d; e = v[4] > e ? v[4] : e;
+    }
+    out[0] = a; out[1] = b; out[2] = c; out[3] = d; out[4] = e;
 }
 
 __global__ void err_or_kernel(const uint32_t* err, uint32_t n, uint32_t* out) {

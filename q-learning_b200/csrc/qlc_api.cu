@@ -4,6 +4,8 @@
 #include "kernels.cuh"
 #include "qnet.cuh"
 #include "qnet_conv.cuh"
+#include "host_pool.h"
+#include "comm.h"
 
 #include <nvtx3/nvToolsExt.h>   // header-only; ranges cost a few ns unless a tool (ncu --nvtx, nsys) is attached
 
@@ -15,6 +17,17 @@
 #include <vector>
 
 using namespace qlc;
+
+#ifndef QLC_SRC_HASH
+#define QLC_SRC_HASH "unknown"
+#endif
+#ifdef QLC_PROFILING
+#define QLC_PROFILING_STR "1"
+#else
+#define QLC_PROFILING_STR "0"
+#endif
+// build.py reads this marker out of the file to tell a stale library from a current one without loading it
+extern "C" const char qlc_build_info_string[] = "QLC_BUILD_INFO:src_hash=" QLC_SRC_HASH ";profiling=" QLC_PROFILING_STR ";";
 
 static thread_local std::string g_last_error;
 
@@ -51,6 +64,7 @@ struct qlc_env {
     cudaEvent_t submit_done[8] = {};           // completion of submit k in slot k % 8 (created on first use)
     cudaStream_t copy_stream = nullptr;        // pipelined submits: the H2D of step k+1 runs beside the kernel of step k
     cudaEvent_t h2d_done[2] = {};
+    cudaEvent_t stage_ev = nullptr;            // host gathers: "the state stack has arrived" while the next stack is still in flight
     int zero_copy = 1;                         // QLC_ZERO_COPY=0: always stage page-locked outputs through a D2H copy
     uint32_t time_slots = 0;                   // frame/record ring length in time steps (= t_cap + 4)
     uint32_t t_cap = 0;                        // replay capacity in time steps
@@ -67,7 +81,23 @@ struct qlc_env {
     int debug_skip = 0;                        // QLC_DEBUG_SKIP (profiling aid)
     int persistent = 1;                        // QLC_PERSISTENT=0: one CTA per env batch
     std::vector<void*> allocs;
+    std::vector<struct qlc_qnet*> qnets;       // Q-networks created on this env: invalidated (not dangling) when the env goes first
+    // episode-statistics reduction over the env shards (qlc_comm_init / qlc_stats_allreduce): NCCL on a side stream, off the step path
+    struct Comm {
+        qlc_comm::Comm nccl = nullptr; int rank = 0, world = 1;
+        cudaStream_t stream = nullptr;
+        DeviceStats* snap = nullptr;           // 4 snapshot slots, written by the last CTA of launch k into slot k % 4
+        unsigned int* exit_counter = nullptr; uint32_t exit_base = 0;
+        cudaEvent_t step_done = nullptr;       // recorded on the caller's step stream by qlc_stats_allreduce
+        cudaEvent_t slot_read[4] = {};         // the reduction that read slot i has finished with it
+        bool slot_busy[4] = {};
+        double *mine = nullptr, *gathered = nullptr, *reduced = nullptr;   // device: [5], [world][5], [5]
+        double* host = nullptr;                // page-locked mirror of `reduced`
+        uint64_t reductions = 0;
+        uint32_t last_serial = 0; bool have_snap = false;
+    }* comm = nullptr;
 };
+static void qnet_release_device(struct qlc_qnet* q);
 
 static int32_t ensure_pin(qlc_env* env, size_t bytes) {
     if (bytes <= env->pin_bytes) return QLC_OK;
@@ -113,6 +143,7 @@ static int32_t dev_alloc(qlc_env* env, T** p, size_t count, bool zero) {
 extern "C" {
 
 int32_t qlc_version(void) { return QLC_VERSION; }
+const char* qlc_build_info(void) { return qlc_build_info_string + sizeof("QLC_BUILD_INFO:") - 1; }
 const char* qlc_last_error_string(void) { return g_last_error.c_str(); }
 
 int32_t qlc_device_count(int32_t* count) {
@@ -161,7 +192,9 @@ int32_t qlc_env_create(const qlc_config* cfg, qlc_env** out) {
     env->time_slots = env->t_cap + 4;
     if (const char* c = getenv("QLC_ADVANCE_CFG")) env->advance_cfg = atoi(c);
     if (const char* c = getenv("QLC_EPC")) env->epc_override = atoi(c);
-    if (const char* c = getenv("QLC_DEBUG_SKIP")) env->debug_skip = atoi(c);
+#ifdef QLC_PROFILING
+    if (const char* c = getenv("QLC_DEBUG_SKIP")) env->debug_skip = atoi(c);      // ablation builds only; a release build ignores the variable
+#endif
     if (const char* c = getenv("QLC_PERSISTENT")) env->persistent = atoi(c);
     if (const char* c = getenv("QLC_CHUNK")) env->chunk_override = atoi(c);
     if (const char* c = getenv("QLC_ZERO_COPY")) env->zero_copy = atoi(c);
@@ -208,11 +241,14 @@ int32_t qlc_env_destroy(qlc_env* env) {
     if (!env) return QLC_OK;
     cudaSetDevice(env->cfg.device);
     cudaDeviceSynchronize();
+    qlc_comm_destroy(env);
+    for (struct qlc_qnet* q : env->qnets) qnet_release_device(q);      // their handles stay valid for qlc_qnet_destroy, every other call fails
     for (void* p : env->allocs) cudaFree(p);
     if (env->pin) cudaFreeHost(env->pin);
     if (env->dev_stage) cudaFree(env->dev_stage);
     for (cudaEvent_t ev : env->submit_done) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : env->h2d_done) if (ev) cudaEventDestroy(ev);
+    if (env->stage_ev) cudaEventDestroy(env->stage_ev);
     if (env->copy_stream) cudaStreamDestroy(env->copy_stream);
     if (env->own_stream) cudaStreamDestroy(env->own_stream);
     delete env;
@@ -297,16 +333,14 @@ static int32_t launch_advance(qlc_env* env, StepParams& p, cudaStream_t s, uint3
     }
     CUDA_TRY(cudaGetLastError());
     if (n_batches * n_chunks > grid) env->work_base += n_batches * n_chunks;      // (n_items - grid) hand-outs + one failed grab per CTA
+    if (env->comm && p.snap) { env->comm->exit_base += grid; env->comm->last_serial = env->launch_serial; env->comm->have_snap = true; }
     return QLC_OK;
 }
 
-extern "C" {
-
-int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps, float* reward_dev, uint8_t* done_dev, void* stream) {
-    QLC_RANGE("qlc_env_step");
-    if (!env || !actions_dev) return fail(QLC_ERR_INVALID_ARG, "env/actions is null");
-    if (n_steps == 0) return QLC_OK;
-    int32_t rc = set_device(env); if (rc) return rc;
+// one launch of at most time_slots steps (a longer one would wrap the frame ring inside the launch: with time chunking two CTAs
+// could then have bulk stores to the same slot in flight, ordered by nothing)
+static int32_t step_launch(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps, float* reward_dev, uint8_t* done_dev, void* stream) {
+    int32_t rc = QLC_OK;
     StepParams p{};
     p.n_envs = env->cfg.n_envs; p.env_id_base = env->cfg.env_id_base; p.time_slots = env->time_slots;
     p.max_episode_steps = env->cfg.max_episode_steps; p.auto_reset = env->cfg.auto_reset; p.n_steps = n_steps;
@@ -314,6 +348,11 @@ int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps,
     p.actions = actions_dev; p.reward = reward_dev; p.done = done_dev;
     p.debug_skip = (uint32_t)env->debug_skip;
     cudaStream_t s = (cudaStream_t)stream;
+    if (qlc_env::Comm* c = env->comm) {
+        const uint32_t slot = (env->launch_serial + 1u) & 3u;     // launch_advance pre-increments the serial
+        if (c->slot_busy[slot]) { CUDA_TRY(cudaStreamWaitEvent(s, c->slot_read[slot], 0)); c->slot_busy[slot] = false; }   // 4 launches back: long done
+        p.snap = c->snap + slot; p.exit_counter = c->exit_counter; p.exit_base = c->exit_base;
+    }
     // Shape selection (measured, profiles/r01_notes.md). Launches that are only a few waves of work are cut into
     // (time chunk, 8-env batch) items handed out dynamically, so that every SM / GPC keeps pulling work at its own pace —
     // this removes a 10-15 % GPU-to-GPU spread seen with one static 32-env batch per SM. Big shards are balanced by their
@@ -338,6 +377,24 @@ int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps,
     }
     if (rc) return rc;
     env->t += n_steps;
+    return QLC_OK;
+}
+
+extern "C" {
+
+int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps, float* reward_dev, uint8_t* done_dev, void* stream) {
+    QLC_RANGE("qlc_env_step");
+    if (!env || !actions_dev) return fail(QLC_ERR_INVALID_ARG, "env/actions is null");
+    if (n_steps == 0) return QLC_OK;
+    int32_t rc = set_device(env); if (rc) return rc;
+    const size_t n = env->cfg.n_envs;
+    for (uint32_t at = 0; at < n_steps;) {               // launches of at most one ring length each (see step_launch)
+        const uint32_t part = n_steps - at < env->time_slots ? n_steps - at : env->time_slots;
+        rc = step_launch(env, actions_dev + (size_t)at * n, part, reward_dev ? reward_dev + (size_t)at * n : nullptr,
+                         done_dev ? done_dev + (size_t)at * n : nullptr, stream);
+        if (rc) return rc;
+        at += part;
+    }
     return QLC_OK;
 }
 
@@ -444,14 +501,24 @@ static void fill_gather(const qlc_env* env, GatherParams& g) {
     g.frames = env->frames; g.records = env->records; g.episode_step = env->st.episode_step;
     g.n_envs = env->cfg.n_envs; g.time_slots = env->time_slots;
     g.t_now = env->t; g.t_oldest = env->t > env->t_cap ? env->t - env->t_cap : 0;
+    g.mode = GATHER_INDICES;
 }
 
 static int32_t launch_gather(qlc_env* env, const GatherParams& g, int32_t layout, cudaStream_t s) {
     if (g.n_items == 0) return QLC_OK;
-    if (layout == QLC_LAYOUT_U8_BHYX) {
+    static bool configured[64] = {};
+    if (!configured[env->cfg.device & 63]) {     // the u8 kernel's 6 frames need the opt-in shared-memory size
+        CUDA_TRY(cudaFuncSetAttribute(gather_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * FRAME_BYTES));
+        configured[env->cfg.device & 63] = true;
+    }
+    // scalars only (get_many without tensorisation): the one-warp kernel has the path for it, whatever the layout
+    if (layout == QLC_LAYOUT_U8_BHYX || (!g.out_state && !g.out_next)) {
+        if (layout != QLC_LAYOUT_U8_BHYX && layout != QLC_LAYOUT_F32_BXYH && layout != QLC_LAYOUT_U8_BXYH) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
         CUDA_TRY(launch_pdl(gather_u8_kernel, dim3(g.n_items), dim3(32), 6 * FRAME_BYTES, s, g));
     } else if (layout == QLC_LAYOUT_F32_BXYH) {
-        CUDA_TRY(launch_pdl(gather_f32_kernel, dim3(g.n_items * 2), dim3(GATHER_F32_THREADS), 4 * FRAME_BYTES, s, g));
+        CUDA_TRY(launch_pdl(gather_xyh_kernel<float4>, dim3(g.n_items * 2), dim3(GATHER_XYH_THREADS), 4 * FRAME_BYTES, s, g));
+    } else if (layout == QLC_LAYOUT_U8_BXYH) {
+        CUDA_TRY(launch_pdl(gather_xyh_kernel<uchar4>, dim3(g.n_items * 2), dim3(GATHER_XYH_THREADS), 4 * FRAME_BYTES, s, g));
     } else {
         return fail(QLC_ERR_INVALID_ARG, "unknown layout");
     }
@@ -460,6 +527,7 @@ static int32_t launch_gather(qlc_env* env, const GatherParams& g, int32_t layout
 }
 
 static size_t item_bytes(int32_t layout) { return layout == QLC_LAYOUT_F32_BXYH ? (size_t)FRAME_BYTES * 4 * sizeof(float) : (size_t)FRAME_BYTES * 4; }
+static bool known_layout(int32_t layout) { return layout == QLC_LAYOUT_U8_BHYX || layout == QLC_LAYOUT_F32_BXYH || layout == QLC_LAYOUT_U8_BXYH; }
 
 int32_t qlc_env_obs(qlc_env* env, int32_t layout, void* out_dev, void* stream) {
     QLC_RANGE("qlc_env_obs");
@@ -467,21 +535,26 @@ int32_t qlc_env_obs(qlc_env* env, int32_t layout, void* out_dev, void* stream) {
     if (((uintptr_t)out_dev & 15) != 0) return fail(QLC_ERR_INVALID_ARG, "output must be 16-byte aligned");
     int32_t rc = set_device(env); if (rc) return rc;
     GatherParams g{}; fill_gather(env, g);
-    g.indices = nullptr; g.n_items = env->cfg.n_envs; g.out_state = out_dev;
+    g.mode = GATHER_CURRENT; g.n_items = env->cfg.n_envs; g.out_state = out_dev;
     return launch_gather(env, g, layout, (cudaStream_t)stream);
 }
 
-int32_t qlc_env_obs_host(qlc_env* env, int32_t layout, void* out_host) {
-    QLC_RANGE("qlc_env_obs_host");
-    if (!env || !out_host) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
-    if (layout != QLC_LAYOUT_U8_BHYX && layout != QLC_LAYOUT_F32_BXYH) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
+// ---- state handles: what a cloned BreakoutState is on the host (state_as_rc / step_as_rc, prelude.rs:36,52-58) ----
+int32_t qlc_obs_gather(qlc_env* env, const qlc_obs_handle* handles_dev, uint32_t n, int32_t layout, void* out_dev, void* stream) {
+    QLC_RANGE("qlc_obs_gather");
+    if (!env || !handles_dev || !out_dev) return fail(QLC_ERR_INVALID_ARG, "env/handles/out is null");
+    if (((uintptr_t)out_dev & 15) != 0) return fail(QLC_ERR_INVALID_ARG, "output must be 16-byte aligned");
     int32_t rc = set_device(env); if (rc) return rc;
-    const size_t bytes = item_bytes(layout) * env->cfg.n_envs;
-    rc = ensure_dev_stage(env, bytes); if (rc) return rc;
-    rc = qlc_env_obs(env, layout, env->dev_stage, env->own_stream); if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_host, env->dev_stage, bytes, cudaMemcpyDeviceToHost, env->own_stream));
-    CUDA_TRY(cudaStreamSynchronize(env->own_stream));
-    return QLC_OK;
+    static_assert(sizeof(qlc_obs_handle) == sizeof(ObsHandle), "handle layout");
+    GatherParams g{}; fill_gather(env, g);
+    g.mode = GATHER_HANDLES; g.handles = reinterpret_cast<const ObsHandle*>(handles_dev); g.n_items = n; g.out_state = out_dev;
+    return launch_gather(env, g, layout, (cudaStream_t)stream);
+}
+
+// a handle is usable while the frames it names are still in the ring (and it is not from the future)
+static bool handle_alive(const qlc_env* env, const qlc_obs_handle& h) {
+    const uint64_t need = h.k < 4u ? h.k : 4u;
+    return h.env < env->cfg.n_envs && h.time <= env->t && h.time >= need && h.time - need + env->time_slots >= env->t;
 }
 
 int32_t qlc_env_state_view(qlc_env* env, qlc_state_view* out) {
@@ -505,6 +578,20 @@ int32_t qlc_env_read_state(qlc_env* env, const qlc_state_host* o) {
     RD(bricks, bricks, uint64_t); RD(score, score, uint32_t); RD(episode_step, episode_step, uint32_t);
     RD(episode, episode, uint32_t); RD(err, err, uint32_t); RD(finished, finished, uint8_t);
 #undef RD
+    return QLC_OK;
+}
+
+// "lives" of the reference game: the episode ends the first time the ball passes the paddle (mechanics.rs:131-135), so an env
+// has exactly one life while it is not finished
+int32_t qlc_env_lives_host(qlc_env* env, uint8_t* lives_host) {
+    if (!env || !lives_host) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    int32_t rc = set_device(env); if (rc) return rc;
+    const uint32_t n = env->cfg.n_envs;
+    CUDA_TRY(cudaDeviceSynchronize());
+    rc = ensure_dev_stage(env, n); if (rc) return rc;
+    lives_kernel<<<(n + 255) / 256, 256>>>(env->st.finished, (uint8_t*)env->dev_stage, n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(lives_host, env->dev_stage, n, cudaMemcpyDeviceToHost));
     return QLC_OK;
 }
 
@@ -542,16 +629,23 @@ int32_t qlc_replay_capacity(qlc_env* env, uint64_t* cap) {
     *cap = env->cfg.replay_capacity == 0 ? 0 : (uint64_t)env->t_cap * env->cfg.n_envs; return QLC_OK;
 }
 
+static int32_t check_sample_args(qlc_env* env, uint32_t batch, uint64_t* len_out) {
+    if (batch == 0 || batch > SAMPLE_MAX_BATCH) return fail(QLC_ERR_INVALID_ARG, "batch must be in 1..1024");
+    const uint64_t len = replay_len(env);
+    if (len < batch) return fail(QLC_ERR_NOT_ENOUGH, "replay holds fewer transitions than the batch size");
+    if (len >= 0xFFFFFFFFull) return fail(QLC_ERR_INVALID_ARG, "replay longer than 2^32-2 transitions");
+    *len_out = len;
+    return QLC_OK;
+}
+
 int32_t qlc_replay_sample(qlc_env* env, uint32_t batch, uint32_t n_batches, uint64_t call_index, uint32_t* idx_dev, void* stream) {
     QLC_RANGE("qlc_replay_sample");
     if (!env || !idx_dev) return fail(QLC_ERR_INVALID_ARG, "env/idx is null");
-    if (batch == 0 || batch > SAMPLE_MAX_BATCH) return fail(QLC_ERR_INVALID_ARG, "batch must be in 1..1024");
+    uint64_t len = 0;
+    int32_t rc = check_sample_args(env, batch, &len); if (rc) return rc;
     if (n_batches == 0) return QLC_OK;
-    const uint64_t len = replay_len(env);
-    if (len < batch) return fail(QLC_ERR_NOT_ENOUGH, "replay holds fewer transitions than the batch size");
-    if (len >= 0xFFFFFFFFull) return fail(QLC_ERR_INVALID_ARG, "replay longer than 2^32-1 transitions");
-    int32_t rc = set_device(env); if (rc) return rc;
-    replay_sample_kernel<<<n_batches, SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(idx_dev, batch, (uint32_t)len, env->cfg.seed, call_index);
+    rc = set_device(env); if (rc) return rc;
+    replay_sample_kernel<<<n_batches, 32, 0, (cudaStream_t)stream>>>(idx_dev, batch, (uint32_t)len, env->cfg.seed, call_index);
     CUDA_TRY(cudaGetLastError());
     return QLC_OK;
 }
@@ -568,6 +662,24 @@ int32_t qlc_replay_gather(qlc_env* env, const uint32_t* idx_dev, uint32_t n, int
     return launch_gather(env, g, layout, (cudaStream_t)stream);
 }
 
+// sample + gather in ONE launch: every CTA of the gather kernel derives the index of its own item from the Philox stream
+int32_t qlc_replay_sample_gather(qlc_env* env, uint32_t batch, uint32_t n_batches, uint64_t call_index, int32_t layout, uint32_t* idx_out_dev,
+                                 void* state_dev, void* next_dev, float* reward_dev, uint8_t* action_dev, uint8_t* done_dev, void* stream) {
+    QLC_RANGE("qlc_replay_sample_gather");
+    if (!env) return fail(QLC_ERR_INVALID_ARG, "env is null");
+    if ((((uintptr_t)state_dev) | ((uintptr_t)next_dev)) & 15) return fail(QLC_ERR_INVALID_ARG, "outputs must be 16-byte aligned");
+    uint64_t len = 0;
+    int32_t rc = check_sample_args(env, batch, &len); if (rc) return rc;
+    if (n_batches == 0) return QLC_OK;
+    if ((uint64_t)batch * n_batches > 0x3FFFFFFFull) return fail(QLC_ERR_INVALID_ARG, "too many items for one call");
+    rc = set_device(env); if (rc) return rc;
+    GatherParams g{}; fill_gather(env, g);
+    g.mode = GATHER_SAMPLE; g.sample_batch = batch; g.sample_len = (uint32_t)len; g.seed = env->cfg.seed; g.call0 = call_index; g.idx_out = idx_out_dev;
+    g.n_items = batch * n_batches; g.out_state = state_dev; g.out_next = next_dev;
+    g.reward = reward_dev; g.action = action_dev; g.done = done_dev;
+    return launch_gather(env, g, layout, (cudaStream_t)stream);
+}
+
 int32_t qlc_replay_sample_host(qlc_env* env, uint32_t batch, uint64_t call_index, uint32_t* idx_host) {
     QLC_RANGE("qlc_replay_sample_host");
     if (!env || !idx_host) return fail(QLC_ERR_INVALID_ARG, "env/idx is null");
@@ -579,40 +691,121 @@ int32_t qlc_replay_sample_host(qlc_env* env, uint32_t batch, uint64_t call_index
     return QLC_OK;
 }
 
+// Host-buffer gathers. An f32 [b][x][y][slot] request is gathered as u8 in the same order on the device, crosses PCIe as u8 (1/4
+// of the bytes) and is widened into the caller's buffer by the host pool (value = u8 as f32: bit-identical to widening on the
+// device). QLC_HOST_WIDEN=0 keeps the f32 tensors on the device side of the copy (A/B measurements).
+struct HostGather {
+    GatherParams g; int32_t layout; uint32_t n;
+    const void* h2d_src; size_t h2d_bytes;                 // indices or handles
+    void* state_host; void* next_host; float* reward_host; uint8_t* action_host; uint8_t* done_host; uint32_t* idx_out_host;
+};
+
+static int32_t run_host_gather(qlc_env* env, HostGather& hg) {
+    static const bool widen_on_host = getenv("QLC_HOST_WIDEN") ? atoi(getenv("QLC_HOST_WIDEN")) != 0 : true;
+    const uint32_t n = hg.n;
+    const bool widen = hg.layout == QLC_LAYOUT_F32_BXYH && widen_on_host;
+    const int32_t dev_layout = widen ? QLC_LAYOUT_U8_BXYH : hg.layout;
+    const size_t ib = item_bytes(dev_layout);
+    // device staging: in (idx / handles) | state | next | reward | action | done | idx_out
+    const size_t o_in = 0, o_s = (hg.h2d_bytes + 255) & ~(size_t)255, o_n = o_s + ib * n, o_r = o_n + ib * n, o_a = o_r + (size_t)n * 4, o_d = o_a + n;
+    const size_t o_i = (o_d + n + 15) & ~(size_t)15, total = o_i + (size_t)n * 4;
+    int32_t rc = ensure_dev_stage(env, total); if (rc) return rc;
+    rc = ensure_pin(env, total); if (rc) return rc;
+    uint8_t* dev = (uint8_t*)env->dev_stage; uint8_t* pin = (uint8_t*)env->pin;
+    cudaStream_t s = env->own_stream;
+    if (hg.h2d_bytes) {
+        memcpy(pin + o_in, hg.h2d_src, hg.h2d_bytes);
+        CUDA_TRY(cudaMemcpyAsync(dev + o_in, pin + o_in, hg.h2d_bytes, cudaMemcpyHostToDevice, s));
+    }
+    GatherParams& g = hg.g;
+    if (g.mode == GATHER_INDICES) g.indices = (const uint32_t*)(dev + o_in);
+    if (g.mode == GATHER_HANDLES) g.handles = (const ObsHandle*)(dev + o_in);
+    if (g.mode == GATHER_SAMPLE) g.idx_out = hg.idx_out_host ? (uint32_t*)(dev + o_i) : nullptr;
+    g.n_items = n;
+    g.out_state = hg.state_host ? dev + o_s : nullptr; g.out_next = hg.next_host ? dev + o_n : nullptr;
+    const bool scalars = g.mode == GATHER_INDICES || g.mode == GATHER_SAMPLE;
+    g.reward = scalars ? (float*)(dev + o_r) : nullptr; g.action = scalars ? dev + o_a : nullptr; g.done = scalars ? dev + o_d : nullptr;
+    rc = launch_gather(env, g, dev_layout, s); if (rc) return rc;
+    // u8 stacks go straight into page-locked caller buffers (qlc_host_alloc); pageable ones, and everything that is widened, through
+    // the page-locked staging
+    const bool direct_s = hg.state_host && !widen && is_pinned(hg.state_host), direct_n = hg.next_host && !widen && is_pinned(hg.next_host);
+    if (!env->stage_ev) CUDA_TRY(cudaEventCreateWithFlags(&env->stage_ev, cudaEventDisableTiming));
+    if (hg.state_host) CUDA_TRY(cudaMemcpyAsync(direct_s ? hg.state_host : (void*)(pin + o_s), dev + o_s, ib * n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(env->stage_ev, s));
+    if (hg.next_host) CUDA_TRY(cudaMemcpyAsync(direct_n ? hg.next_host : (void*)(pin + o_n), dev + o_n, ib * n, cudaMemcpyDeviceToHost, s));
+    if (scalars || hg.idx_out_host) CUDA_TRY(cudaMemcpyAsync(pin + o_r, dev + o_r, total - o_r, cudaMemcpyDeviceToHost, s));
+    if (hg.state_host && !direct_s) {            // the state stack is widened / copied while the next stack is still in flight
+        CUDA_TRY(cudaEventSynchronize(env->stage_ev));
+        if (widen) qlc_host::widen_u8_f32(pin + o_s, (float*)hg.state_host, ib * n);
+        else memcpy(hg.state_host, pin + o_s, ib * n);
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (hg.next_host && !direct_n) {
+        if (widen) qlc_host::widen_u8_f32(pin + o_n, (float*)hg.next_host, ib * n);
+        else memcpy(hg.next_host, pin + o_n, ib * n);
+    }
+    if (hg.reward_host) memcpy(hg.reward_host, pin + o_r, (size_t)n * 4);
+    if (hg.action_host) memcpy(hg.action_host, pin + o_a, n);
+    if (hg.done_host) memcpy(hg.done_host, pin + o_d, n);
+    if (hg.idx_out_host) memcpy(hg.idx_out_host, pin + o_i, (size_t)n * 4);
+    return QLC_OK;
+}
+
 int32_t qlc_replay_gather_host(qlc_env* env, const uint32_t* idx_host, uint32_t n, int32_t layout, void* state_host, void* next_host,
                                float* reward_host, uint8_t* action_host, uint8_t* done_host) {
     QLC_RANGE("qlc_replay_gather_host");
     if (!env || !idx_host) return fail(QLC_ERR_INVALID_ARG, "env/idx is null");
-    if (layout != QLC_LAYOUT_U8_BHYX && layout != QLC_LAYOUT_F32_BXYH) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
+    if (!known_layout(layout)) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
     if (n == 0) return QLC_OK;
     const uint64_t len = replay_len(env);
     for (uint32_t i = 0; i < n; ++i) if (idx_host[i] >= len) return fail(QLC_ERR_OUT_OF_RANGE, "replay index out of range");
     int32_t rc = set_device(env); if (rc) return rc;
-    const size_t ib = item_bytes(layout);
-    // device staging: idx | state | next | reward | action | done
-    const size_t o_idx = 0, o_s = ((size_t)n * 4 + 255) & ~(size_t)255, o_n = o_s + ib * n, o_r = o_n + ib * n, o_a = o_r + (size_t)n * 4, o_d = o_a + n;
-    const size_t total = o_d + n;
-    rc = ensure_dev_stage(env, total); if (rc) return rc;
-    rc = ensure_pin(env, total); if (rc) return rc;
-    uint8_t* dev = (uint8_t*)env->dev_stage; uint8_t* pin = (uint8_t*)env->pin;
-    cudaStream_t s = env->own_stream;
-    memcpy(pin + o_idx, idx_host, (size_t)n * 4);
-    CUDA_TRY(cudaMemcpyAsync(dev + o_idx, pin + o_idx, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    rc = qlc_replay_gather(env, (const uint32_t*)(dev + o_idx), n, layout, state_host ? dev + o_s : nullptr, next_host ? dev + o_n : nullptr,
-                           (float*)(dev + o_r), dev + o_a, dev + o_d, s);
-    if (rc) return rc;
-    // the big outputs go straight into page-locked caller buffers (qlc_host_alloc); pageable ones through the pinned staging
-    const bool pin_s = state_host && is_pinned(state_host), pin_n = next_host && is_pinned(next_host);
-    if (state_host) CUDA_TRY(cudaMemcpyAsync(pin_s ? state_host : (void*)(pin + o_s), dev + o_s, ib * n, cudaMemcpyDeviceToHost, s));
-    if (next_host) CUDA_TRY(cudaMemcpyAsync(pin_n ? next_host : (void*)(pin + o_n), dev + o_n, ib * n, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(pin + o_r, dev + o_r, total - o_r, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    if (state_host && !pin_s) memcpy(state_host, pin + o_s, ib * n);
-    if (next_host && !pin_n) memcpy(next_host, pin + o_n, ib * n);
-    if (reward_host) memcpy(reward_host, pin + o_r, (size_t)n * 4);
-    if (action_host) memcpy(action_host, pin + o_a, n);
-    if (done_host) memcpy(done_host, pin + o_d, n);
-    return QLC_OK;
+    HostGather hg{}; fill_gather(env, hg.g);
+    hg.layout = layout; hg.n = n; hg.h2d_src = idx_host; hg.h2d_bytes = (size_t)n * 4;
+    hg.state_host = state_host; hg.next_host = next_host; hg.reward_host = reward_host; hg.action_host = action_host; hg.done_host = done_host;
+    return run_host_gather(env, hg);
+}
+
+int32_t qlc_replay_sample_gather_host(qlc_env* env, uint32_t batch, uint64_t call_index, int32_t layout, uint32_t* idx_out_host,
+                                      void* state_host, void* next_host, float* reward_host, uint8_t* action_host, uint8_t* done_host) {
+    QLC_RANGE("qlc_replay_sample_gather_host");
+    if (!env) return fail(QLC_ERR_INVALID_ARG, "env is null");
+    if (!known_layout(layout)) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
+    uint64_t len = 0;
+    int32_t rc = check_sample_args(env, batch, &len); if (rc) return rc;
+    rc = set_device(env); if (rc) return rc;
+    HostGather hg{}; fill_gather(env, hg.g);
+    hg.g.mode = GATHER_SAMPLE; hg.g.sample_batch = batch; hg.g.sample_len = (uint32_t)len; hg.g.seed = env->cfg.seed; hg.g.call0 = call_index;
+    hg.layout = layout; hg.n = batch; hg.idx_out_host = idx_out_host;
+    hg.state_host = state_host; hg.next_host = next_host; hg.reward_host = reward_host; hg.action_host = action_host; hg.done_host = done_host;
+    return run_host_gather(env, hg);
+}
+
+int32_t qlc_env_obs_host(qlc_env* env, int32_t layout, void* out_host) {
+    QLC_RANGE("qlc_env_obs_host");
+    if (!env || !out_host) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    if (!known_layout(layout)) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
+    int32_t rc = set_device(env); if (rc) return rc;
+    HostGather hg{}; fill_gather(env, hg.g);
+    hg.g.mode = GATHER_CURRENT;
+    hg.layout = layout; hg.n = env->cfg.n_envs; hg.state_host = out_host;
+    return run_host_gather(env, hg);
+}
+
+// batch_to_multi_dim_array for host-side state handles (breakout_environment.rs:56-77): n stacks into out_host
+int32_t qlc_obs_gather_host(qlc_env* env, const qlc_obs_handle* handles_host, uint32_t n, int32_t layout, void* out_host) {
+    QLC_RANGE("qlc_obs_gather_host");
+    if (!env || !handles_host || !out_host) return fail(QLC_ERR_INVALID_ARG, "env/handles/out is null");
+    if (!known_layout(layout)) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
+    if (n == 0) return QLC_OK;
+    for (uint32_t i = 0; i < n; ++i)
+        if (!handle_alive(env, handles_host[i])) return fail(QLC_ERR_OUT_OF_RANGE, "stale state handle: its frames have left the frame ring (or it belongs to another env)");
+    int32_t rc = set_device(env); if (rc) return rc;
+    HostGather hg{}; fill_gather(env, hg.g);
+    hg.g.mode = GATHER_HANDLES;
+    hg.layout = layout; hg.n = n; hg.h2d_src = handles_host; hg.h2d_bytes = (size_t)n * sizeof(qlc_obs_handle);
+    hg.state_host = out_host;
+    return run_host_gather(env, hg);
 }
 
 int32_t qlc_replay_action_counts(qlc_env* env, uint64_t counts[3]) {
@@ -649,6 +842,134 @@ int32_t qlc_stats_export(qlc_env* env, double* out_dev, void* stream) {
     CUDA_TRY(cudaGetLastError());
     return QLC_OK;
 }
+// ---------------- statistics reduction over the env shards: NCCL behind the C ABI, on a side stream ----------------
+int32_t qlc_comm_unique_id(uint8_t* id128) {
+    if (!id128) return fail(QLC_ERR_INVALID_ARG, "id is null");
+    std::string why;
+    const qlc_comm::Api* nccl = qlc_comm::api(&why);
+    if (!nccl) return fail(QLC_ERR_COMM, why);
+    qlc_comm::UniqueId id;
+    const int r = nccl->GetUniqueId(&id);
+    if (r != 0) return fail(QLC_ERR_COMM, std::string("ncclGetUniqueId: ") + nccl->GetErrorString(r));
+    memcpy(id128, id.internal, QLC_COMM_ID_BYTES);
+    return QLC_OK;
+}
+
+int32_t qlc_comm_destroy(qlc_env* env) {
+    if (!env || !env->comm) return QLC_OK;
+    qlc_env::Comm* c = env->comm;
+    cudaSetDevice(env->cfg.device);
+    cudaDeviceSynchronize();
+    if (c->nccl) { std::string why; if (const qlc_comm::Api* nccl = qlc_comm::api(&why)) nccl->CommDestroy(c->nccl); }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->step_done) cudaEventDestroy(c->step_done);
+    for (cudaEvent_t ev : c->slot_read) if (ev) cudaEventDestroy(ev);
+    cudaFree(c->snap); cudaFree(c->exit_counter); cudaFree(c->mine); cudaFree(c->gathered); cudaFree(c->reduced);
+    if (c->host) cudaFreeHost(c->host);
+    delete c;
+    env->comm = nullptr;
+    return QLC_OK;
+}
+
+int32_t qlc_comm_init(qlc_env* env, int32_t rank, int32_t world, const uint8_t* id128) {
+    QLC_RANGE("qlc_comm_init");
+    if (!env) return fail(QLC_ERR_INVALID_ARG, "env is null");
+    if (world < 1 || rank < 0 || rank >= world) return fail(QLC_ERR_INVALID_ARG, "need 0 <= rank < world");
+    if (world > 1 && !id128) return fail(QLC_ERR_INVALID_ARG, "a communicator of more than one rank needs the id from qlc_comm_unique_id on rank 0");
+    if (env->comm) return fail(QLC_ERR_INVALID_ARG, "this env already has a communicator");
+    int32_t rc = set_device(env); if (rc) return rc;
+    qlc_env::Comm* c = new qlc_env::Comm();
+    c->rank = rank; c->world = world;
+    env->comm = c;
+    auto bail = [&](int32_t code, const std::string& msg) { qlc_comm_destroy(env); return fail(code, msg); };
+    if (id128) {        // world == 1 without an id: no NCCL at all (the reduction is the identity)
+        std::string why;
+        const qlc_comm::Api* nccl = qlc_comm::api(&why);
+        if (!nccl) return bail(QLC_ERR_COMM, why);
+        qlc_comm::UniqueId id; memcpy(id.internal, id128, QLC_COMM_ID_BYTES);
+        const int r = nccl->CommInitRank(&c->nccl, world, id, rank);
+        if (r != 0) { c->nccl = nullptr; return bail(QLC_ERR_COMM, std::string("ncclCommInitRank: ") + nccl->GetErrorString(r)); }
+    }
+    cudaError_t e = cudaSuccess;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);                    // lowest priority: step CTAs are scheduled first
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, lo);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->step_done, cudaEventDisableTiming);
+    for (cudaEvent_t& ev : c->slot_read) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&c->snap, 4 * sizeof(DeviceStats));
+    if (e == cudaSuccess) e = cudaMalloc(&c->exit_counter, 4);
+    if (e == cudaSuccess) e = cudaMemset(c->exit_counter, 0, 4);
+    if (e == cudaSuccess) e = cudaMalloc(&c->mine, 5 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&c->gathered, (size_t)world * 5 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&c->reduced, 5 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->host, 5 * sizeof(double));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return bail(QLC_ERR_CUDA, std::string("qlc_comm_init: ") + cudaGetErrorString(e));
+    for (int i = 0; i < 5; ++i) c->host[i] = i < 3 ? 0.0 : -1.0e300;
+    return QLC_OK;
+}
+
+int32_t qlc_comm_info(qlc_env* env, int32_t* rank, int32_t* world, int32_t* nccl_version, int32_t* nccl_ranks) {
+    if (!env || !env->comm) return fail(QLC_ERR_INVALID_ARG, "no communicator (qlc_comm_init)");
+    if (rank) *rank = env->comm->rank;
+    if (world) *world = env->comm->world;
+    if (nccl_version) *nccl_version = 0;
+    if (nccl_ranks) *nccl_ranks = 0;
+    if (env->comm->nccl) {
+        std::string why;
+        const qlc_comm::Api* nccl = qlc_comm::api(&why);
+        int v = 0, n = 0;
+        if (nccl && nccl->GetVersion(&v) == 0 && nccl_version) *nccl_version = v;
+        if (nccl && nccl->CommCount(env->comm->nccl, &n) == 0 && nccl_ranks) *nccl_ranks = n;
+    }
+    return QLC_OK;
+}
+
+// Enqueues one reduction of {sum_return, episodes, steps, min, max} over all ranks. Nothing but an event record lands on
+// `stream` (the caller's step stream): the export, ONE ncclAllGather of 5 doubles, the combine and the copy to the host mirror
+// run on the communicator's own low-priority stream, behind the work `stream` holds now, next to whatever it is given later.
+int32_t qlc_stats_allreduce(qlc_env* env, void* stream) {
+    QLC_RANGE("qlc_stats_allreduce");
+    if (!env || !env->comm) return fail(QLC_ERR_INVALID_ARG, "no communicator (qlc_comm_init)");
+    int32_t rc = set_device(env); if (rc) return rc;
+    qlc_env::Comm* c = env->comm;
+    CUDA_TRY(cudaEventRecord(c->step_done, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->step_done, 0));
+    const uint64_t steps = env->t * env->cfg.n_envs;
+    const uint32_t slot = c->last_serial & 3u;
+    // the snapshot the last launch left (launches after it may already be running); before the first launch: the accumulators
+    stats_export_kernel<<<1, 1, 0, c->stream>>>(c->have_snap ? c->snap + slot : env->stats, steps, c->mine);
+    CUDA_TRY(cudaGetLastError());
+    if (c->have_snap) { CUDA_TRY(cudaEventRecord(c->slot_read[slot], c->stream)); c->slot_busy[slot] = true; }
+    const double* result = c->mine;
+    if (c->nccl) {
+        std::string why;
+        const qlc_comm::Api* nccl = qlc_comm::api(&why);
+        if (!nccl) return fail(QLC_ERR_COMM, why);
+        const int r = nccl->AllGather(c->mine, c->gathered, 5, qlc_comm::kFloat64, c->nccl, (void*)c->stream);
+        if (r != 0) return fail(QLC_ERR_COMM, std::string("ncclAllGather: ") + nccl->GetErrorString(r));
+        stats_combine_kernel<<<1, 1, 0, c->stream>>>(c->gathered, c->world, c->reduced);
+        CUDA_TRY(cudaGetLastError());
+        result = c->reduced;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->host, result, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    c->reductions += 1;
+    return QLC_OK;
+}
+
+// The job-wide statistics of the last reduction that has completed (wait != 0: of the last one enqueued).
+int32_t qlc_stats_global(qlc_env* env, qlc_episode_stats* out, int32_t wait) {
+    if (!env || !out) return fail(QLC_ERR_INVALID_ARG, "env/out is null");
+    if (!env->comm) return fail(QLC_ERR_INVALID_ARG, "no communicator (qlc_comm_init)");
+    int32_t rc = set_device(env); if (rc) return rc;
+    if (wait) CUDA_TRY(cudaStreamSynchronize(env->comm->stream));
+    const volatile double* h = env->comm->host;
+    out->sum_return = (uint64_t)h[0]; out->episodes = (uint64_t)h[1]; out->steps = (uint64_t)h[2];
+    const bool any = out->episodes != 0;
+    out->min_return = any ? (uint32_t)(-h[3]) : 0xFFFFFFFFu; out->max_return = any ? (uint32_t)h[4] : 0u;
+    return QLC_OK;
+}
+
 int32_t qlc_stats_push(qlc_env* env, float r) {                      // Buffer::add (replay_buffer.rs:21-29)
     if (!env) return fail(QLC_ERR_INVALID_ARG, "env is null");
     if (env->window.size() >= env->cfg.episode_window) env->window.pop_front();
@@ -760,6 +1081,7 @@ int32_t qlc_env_load(qlc_env* env, const char* path) {
     if (ok) ok = cudaMemcpy(env->stats, &h.stats, sizeof h.stats, cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) return fail(QLC_ERR_CUDA, std::string("reading checkpoint failed (the env state is now undefined): ") + path);
     env->t = h.t; env->window = window;
+    if (env->comm) env->comm->have_snap = false;     // the snapshots belong to the run that was replaced
     return QLC_OK;
 }
 
@@ -848,7 +1170,8 @@ extern "C" {
 
 // ---------------- Q-network forward on the tensor cores ----------------
 struct qlc_qnet {
-    qlc_env* env = nullptr;
+    qlc_env* env = nullptr;                                                 // NULL once the env has been destroyed: every call but destroy fails
+    int device = 0;
     __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr; float* w5 = nullptr;
     float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *b4 = nullptr, *b5 = nullptr;
     __nv_bfloat16 *w1p = nullptr, *w2p = nullptr, *w3p = nullptr, *w4p = nullptr, *w4p256 = nullptr;   // operand-layout weights (dense: N tiles of 128 and of 256): planes [K/8][N][8]
@@ -866,19 +1189,55 @@ static void qnet_free_acts(qlc_qnet* q) {
     q->a1 = q->a2 = q->a3 = q->a4 = q->a1p = q->a2p = q->a3p = nullptr; q->head_partial = nullptr; q->head_count = nullptr; q->slot_frame = nullptr; q->cap_items = 0;
 }
 
-int32_t qlc_qnet_destroy(qlc_qnet* q) {
-    if (!q) return QLC_OK;
-    cudaSetDevice(q->env->cfg.device);
+}  // extern "C"
+
+// frees everything the network holds on the device and cuts its tie to the env (called by qlc_qnet_destroy, and by
+// qlc_env_destroy for networks that outlive their env: their handle stays valid, but only for qlc_qnet_destroy)
+static void qnet_release_device(qlc_qnet* q) {
+    if (!q->env) return;
+    cudaSetDevice(q->device);
     cudaDeviceSynchronize();
     qnet_free_acts(q);
     cudaFree(q->w1); cudaFree(q->w2); cudaFree(q->w3); cudaFree(q->w4); cudaFree(q->w5); cudaFree(q->w1p); cudaFree(q->w2p); cudaFree(q->w3p); cudaFree(q->w4p); cudaFree(q->w4p256);
     cudaFree(q->b1); cudaFree(q->b2); cudaFree(q->b3); cudaFree(q->b4); cudaFree(q->b5); cudaFree(q->err); cudaFree(q->stage); cudaFree(q->prof);
+    q->w1 = q->w2 = q->w3 = q->w4 = q->w1p = q->w2p = q->w3p = q->w4p = q->w4p256 = nullptr; q->w5 = nullptr;
+    q->b1 = q->b2 = q->b3 = q->b4 = q->b5 = nullptr; q->err = nullptr; q->stage = nullptr; q->stage_bytes = 0; q->prof = nullptr;
+    q->env = nullptr;
+}
+
+extern "C" {
+
+int32_t qlc_qnet_destroy(qlc_qnet* q) {
+    if (!q) return QLC_OK;
+    if (qlc_env* env = q->env) {
+        for (size_t i = 0; i < env->qnets.size(); ++i)
+            if (env->qnets[i] == q) { env->qnets.erase(env->qnets.begin() + i); break; }
+        qnet_release_device(q);
+    }
     delete q;
+    return QLC_OK;
+}
+
+// MMA completion time-out flag of the device-path forward (qlc_qnet_forward never synchronises): read and clear
+int32_t qlc_qnet_error(qlc_qnet* q, uint32_t* flag) {
+    if (!q || !flag) return fail(QLC_ERR_INVALID_ARG, "qnet/out is null");
+    if (!q->env) return fail(QLC_ERR_INVALID_ARG, "the environment of this Q-network has been destroyed");
+    int32_t rc = set_device(q->env); if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned int herr = 0;
+    CUDA_TRY(cudaMemcpy(&herr, q->err, 4, cudaMemcpyDeviceToHost));
+    *flag = herr;
+    if (herr) {
+        // a pass that gave up may have left per-row tickets of the fused head behind: start the next one clean
+        if (q->head_count) CUDA_TRY(cudaMemset(q->head_count, 0, (size_t)((q->cap_items + 127u) / 128u) * 128u * 4));
+        CUDA_TRY(cudaMemset(q->err, 0, 4));
+    }
     return QLC_OK;
 }
 
 int32_t qlc_qnet_set_weights(qlc_qnet* q, const qlc_qnet_weights* w) {
     if (!q || !w) return fail(QLC_ERR_INVALID_ARG, "qnet/weights is null");
+    if (!q->env) return fail(QLC_ERR_INVALID_ARG, "the environment of this Q-network has been destroyed");
     const float* srcs[10] = {w->conv1_kernel, w->conv1_bias, w->conv2_kernel, w->conv2_bias, w->conv3_kernel, w->conv3_bias, w->dense1_kernel, w->dense1_bias, w->dense2_kernel, w->dense2_bias};
     const size_t counts[10] = {8 * 8 * 4 * 32, 32, 4 * 4 * 32 * 64, 64, 3 * 3 * 64 * 64, 64, 3136 * 512, 512, 512 * 3, 3};
     for (int i = 0; i < 10; ++i) if (!srcs[i]) return fail(QLC_ERR_INVALID_ARG, "a weight pointer is null");
@@ -913,7 +1272,8 @@ int32_t qlc_qnet_create(qlc_env* env, const qlc_qnet_weights* w, qlc_qnet** out)
     *out = nullptr;
     int32_t rc = set_device(env); if (rc) return rc;
     qlc_qnet* q = new qlc_qnet();
-    q->env = env;
+    q->env = env; q->device = env->cfg.device;
+    env->qnets.push_back(q);
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     A((void**)&q->w1, 32 * 256 * 2); A((void**)&q->w2, 64 * 512 * 2); A((void**)&q->w3, 64 * 576 * 2); A((void**)&q->w4, (size_t)512 * 3136 * 2); A((void**)&q->w5, 3 * 512 * 4);
@@ -933,6 +1293,7 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
     QLC_RANGE("qlc_qnet_forward");
     if (!q) return fail(QLC_ERR_INVALID_ARG, "qnet is null");
     qlc_env* env = q->env;
+    if (!env) return fail(QLC_ERR_INVALID_ARG, "the environment of this Q-network has been destroyed");
     int32_t rc = set_device(env); if (rc) return rc;
     if (!idx_dev) { n = env->cfg.n_envs; which = 0; }
     if (n == 0) return QLC_OK;
@@ -955,7 +1316,7 @@ int32_t qlc_qnet_forward(qlc_qnet* q, const uint32_t* idx_dev, uint32_t n, int32
         q->cap_items = n;
     }
     GatherParams g{}; fill_gather(env, g);
-    g.indices = idx_dev; g.n_items = n;
+    g.indices = idx_dev; g.n_items = n; g.mode = idx_dev ? GATHER_INDICES : GATHER_CURRENT;
     cudaError_t e;
     const int impl = q->impl;
     if (impl >= 1) {
@@ -1025,6 +1386,7 @@ int32_t qlc_qnet_forward_host(qlc_qnet* q, const uint32_t* idx_host, uint32_t n,
     QLC_RANGE("qlc_qnet_forward_host");
     if (!q) return fail(QLC_ERR_INVALID_ARG, "qnet is null");
     qlc_env* env = q->env;
+    if (!env) return fail(QLC_ERR_INVALID_ARG, "the environment of this Q-network has been destroyed");
     int32_t rc = set_device(env); if (rc) return rc;
     if (!idx_host) n = env->cfg.n_envs;
     if (n == 0) return QLC_OK;
@@ -1039,14 +1401,9 @@ int32_t qlc_qnet_forward_host(qlc_qnet* q, const uint32_t* idx_host, uint32_t n,
     if (max_q_host) CUDA_TRY(cudaMemcpyAsync(max_q_host, dev + o_m, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     if (action_host) CUDA_TRY(cudaMemcpyAsync(action_host, dev + o_a, n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    unsigned int herr = 0;
-    CUDA_TRY(cudaMemcpy(&herr, q->err, 4, cudaMemcpyDeviceToHost));
-    if (herr) {
-        // a pass that gave up may have left per-row tickets of the fused head behind: start the next one clean
-        if (q->head_count) cudaMemset(q->head_count, 0, (size_t)((q->cap_items + 127u) / 128u) * 128u * 4);
-        cudaMemset(q->err, 0, 4);
-        return fail(QLC_ERR_CUDA, "qnet: an MMA completion barrier timed out");
-    }
+    uint32_t herr = 0;
+    rc = qlc_qnet_error(q, &herr); if (rc) return rc;
+    if (herr) return fail(QLC_ERR_CUDA, "qnet: an MMA completion barrier timed out");
     return QLC_OK;
 }
 

@@ -129,13 +129,7 @@ __global__ void qnet_locate_kernel(GatherParams g, uint32_t which, uint32_t* slo
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= g.n_items) return;
-    uint64_t T; uint32_t e, k, rec;
-    locate(g, b, T, e, k, rec);
-    #pragma unroll
-    for (uint32_t h = 0; h < 4; ++h) {
-        const uint32_t d = which ? ((k - h) & 3u) : (((k - h - 1u) & 3u) + 1u);
-        slot_frame[b * 4u + h] = d <= k ? (uint32_t)((T - d) % g.time_slots) * g.n_envs + e : 0xFFFFFFFFu;
-    }
+    reinterpret_cast<uint4*>(slot_frame)[b] = slot_frames(g, b, which);
 }
 
 // weight preparation: Keras layouts (f32) -> bf16 [N][K] K-major in the K order each loader uses

@@ -278,17 +278,7 @@ __global__ void __launch_bounds__(G::THREADS, 1) conv_sw_kernel(ConvArgs args, O
         if (lane == 0) {
             // which frame of the ring holds ring slot h of an item's stack (~0u: not written yet in this episode, all zero) - the
             // rules of the gather kernels (locate(), kernels.cuh); one or two global loads per item, issued ahead of the wait below
-            auto slot_table = [&](uint32_t item) -> uint4 {
-                uint64_t T; uint32_t e, k, rec;
-                locate(args.g, item, T, e, k, rec);
-                uint32_t f[4];
-                #pragma unroll
-                for (uint32_t h = 0; h < 4; ++h) {
-                    const uint32_t d = args.which ? ((k - h) & 3u) : (((k - h - 1u) & 3u) + 1u);
-                    f[h] = d <= k ? (uint32_t)((T - d) % args.g.time_slots) * args.g.n_envs + e : 0xFFFFFFFFu;
-                }
-                return make_uint4(f[0], f[1], f[2], f[3]);
-            };
+            auto slot_table = [&](uint32_t item) -> uint4 { return slot_frames(args.g, item, args.which); };
             uint4 cur = make_uint4(0u, 0u, 0u, 0u);
             if constexpr (G::FROM_RING) { if (blockIdx.x < n_batches) cur = slot_table(blockIdx.x); }
             for (uint32_t it = 0, bi = blockIdx.x; bi < n_batches && !*abort_flag; ++it, bi += gridDim.x) {

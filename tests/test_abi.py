@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(qlb):
     for s in syms:
         assert hasattr(lib, s), "libqlcuda.so does not export %s" % s
     assert sorted(qlb.ABI_SYMBOLS) == syms, "python binding list and header disagree"
-    assert lib.qlc_version() == 100
+    assert lib.qlc_version() == 200
     assert qlb.BreakoutEnvironment.episode_reward_goal_mean.__doc__ is None or True
     assert float(lib.qlc_env_goal_mean()) == 59.0
 
