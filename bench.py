@@ -534,7 +534,7 @@ def _host_threads():
     if n and int(n) > 0:
         return int(n)
     ranks = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-    return max(1, min(8, (os.cpu_count() or 2) // (2 * max(ranks, 1))))
+    return max(1, min(16, (os.cpu_count() or 2) // max(ranks, 1)))
 
 
 def measure_extras(q, torch, env, rb, dev, stream, peak, replay, cpu_baseline=True):

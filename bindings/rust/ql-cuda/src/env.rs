@@ -8,7 +8,11 @@ use ql::prelude::{Action, DebugVisualizer, Environment, ModelActionType, QlError
 
 use crate::{check, ffi};
 
-/// Owns the `qlc_env` (N = 1 env + frame ring + replay shard in HBM). Shared by the environment, its states and the replay buffer.
+/// `Parameter::default().history_buffer_len` (self_driving_tf_q_learner.rs:59): how many steps a state handle must stay alive
+/// for the learner's replay FIFO. 1 M frames of 84 x 84 u8 = 7 GB of the 180 GB of HBM.
+pub const DEFAULT_HISTORY_BUFFER_LEN: usize = 1_000_000;
+
+/// Owns the `qlc_env` (one env + its frame ring in HBM). Shared by the environment and every state handle.
 pub(crate) struct Handle(pub(crate) *mut ffi::qlc_env);
 
 impl Handle {
@@ -57,75 +61,53 @@ impl Display for BreakoutAction {
     fn fmt(&self, f: &mut Formatter<'_>) -> std::fmt::Result { write!(f, "{:?}", self) }
 }
 
-#[derive(Clone, Copy, Debug, PartialEq, Eq)]
-pub enum StateKind {
-    /// the environment's observation at `time`
-    Live,
-    /// `state` / `state_next` of replay row `index`, valid until the env steps again
-    ReplayState(u32),
-    ReplayNext(u32),
-}
-
-/// BreakoutState as a cheap handle: `Clone` copies indices, the pixels stay in the HBM frame ring until tensorised.
+/// BreakoutState (breakout_environment.rs:24-28) as a handle: the observation of the env after `time` steps, `k` of them in
+/// the current episode. `Clone` copies the handle; the four frames it names stay in the HBM frame ring and remain readable
+/// for `history_buffer_len` further steps — as long as the reference's replay FIFO can still hold the `Rc` around it.
 #[derive(Clone)]
 pub struct CudaBreakoutState {
     pub(crate) env: Rc<Handle>,
-    pub(crate) kind: StateKind,
     pub(crate) time: u64,
+    pub(crate) k: u32,
     model_dims: [u64; 3],
 }
 
 impl CudaBreakoutState {
-    pub(crate) fn new(env: Rc<Handle>, kind: StateKind, time: u64) -> Self {
-        Self { env, kind, time, model_dims: [ffi::QLC_FRAME_W as u64, ffi::QLC_FRAME_H as u64, ffi::QLC_NUM_FRAMES as u64] }
-    }
-    pub fn dims(&self) -> &[u64] { &self.model_dims }
+    pub(crate) fn new(env: Rc<Handle>, time: u64, k: u32, model_dims: [u64; 3]) -> Self { Self { env, time, k, model_dims } }
 
-    /// `[b][x][y][slot]` f32, value = u8 as f32 (breakout_environment.rs:56-77) — one gather kernel for the whole batch.
-    pub fn batch_to_f32<const N: usize>(batch: &[&Rc<Self>; N]) -> Result<Vec<f32>> {
-        let per = ffi::QLC_FRAME_W * ffi::QLC_FRAME_H * ffi::QLC_NUM_FRAMES;
-        let mut out = vec![0f32; N * per];
-        let first = batch[0];
-        match first.kind {
-            StateKind::Live => {
-                if first.time != first.env.time() {
-                    Err(QlError("stale state handle".to_string()))?
-                }
-                let mut one = vec![0f32; per];
-                check(unsafe { ffi::qlc_env_obs_host(first.env.0, ffi::QLC_LAYOUT_F32_BXYH, one.as_mut_ptr() as *mut _) })?;
-                for b in 0..N {
-                    out[b * per..(b + 1) * per].copy_from_slice(&one);
-                }
-            }
-            StateKind::ReplayState(_) | StateKind::ReplayNext(_) => {
-                let next = matches!(first.kind, StateKind::ReplayNext(_));
-                let mut idx = [0u32; N];
-                for (b, s) in batch.iter().enumerate() {
-                    idx[b] = match (s.kind, next) {
-                        (StateKind::ReplayState(i), false) | (StateKind::ReplayNext(i), true) => i,
-                        _ => Err(QlError("mixed state kinds in one batch".to_string()))?,
-                    };
-                    if s.time != s.env.time() {
-                        Err(QlError("stale replay sample".to_string()))?
-                    }
-                }
-                let p = out.as_mut_ptr() as *mut std::os::raw::c_void;
-                let (sp, np) = if next { (std::ptr::null_mut(), p) } else { (p, std::ptr::null_mut()) };
-                check(unsafe {
-                    ffi::qlc_replay_gather_host(first.env.0, idx.as_ptr(), N as u32, ffi::QLC_LAYOUT_F32_BXYH, sp, np,
-                                                std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut())
-                })?;
-            }
+    pub fn model_dims(&self) -> &[u64] { &self.model_dims }
+
+    pub(crate) fn raw(&self) -> ffi::qlc_obs_handle { ffi::qlc_obs_handle { time: self.time, k: self.k, env: 0 } }
+
+    /// `[b][x][y][hist]` f32, value = u8 as f32 (breakout_environment.rs:56-77) for any mix of handles of ONE environment:
+    /// one gather kernel, the stacks cross PCIe as u8 and are widened into the returned vector by the library.
+    pub fn gather_f32(batch: &[&CudaBreakoutState]) -> Result<Vec<f32>> {
+        if batch.is_empty() {
+            return Ok(Vec::new());
         }
+        let first = batch[0];
+        let per = (first.model_dims[0] * first.model_dims[1] * first.model_dims[2]) as usize;
+        let mut handles = Vec::with_capacity(batch.len());
+        for s in batch {
+            if !Rc::ptr_eq(&s.env, &first.env) {
+                Err(QlError("states of different environments in one batch".to_string()))?
+            }
+            handles.push(s.raw());
+        }
+        let mut out = vec![0f32; batch.len() * per];
+        check(unsafe {
+            ffi::qlc_obs_gather_host(first.env.0, handles.as_ptr(), handles.len() as u32, ffi::QLC_LAYOUT_F32_BXYH, out.as_mut_ptr() as *mut _)
+        })?;
         Ok(out)
     }
 }
 
 impl Debug for CudaBreakoutState {
-    fn fmt(&self, f: &mut Formatter<'_>) -> std::fmt::Result { write!(f, "CudaBreakoutState {{ {:?} @ t={} }}", self.kind, self.time) }
+    fn fmt(&self, f: &mut Formatter<'_>) -> std::fmt::Result { write!(f, "CudaBreakoutState {{ t={}, k={} }}", self.time, self.k) }
 }
 
 impl DebugVisualizer for CudaBreakoutState {
+    /// describes the environment's *current* mechanics (a handle names frames, not ball coordinates)
     fn one_line_info(&self) -> String {
         let (mut cx, mut cy, mut pmin, mut pmax, mut bricks) = (0f32, 0f32, 0f32, 0f32, 0u64);
         let sh = ffi::qlc_state_host {
@@ -140,21 +122,25 @@ impl DebugVisualizer for CudaBreakoutState {
     fn render_to_console(&self) -> Screen { todo!() } // as in the reference (breakout_environment.rs:91)
 }
 
-// `ToMultiDimArray<Tensor<f32>>` (ql-with-tensorflow/src/ml_model/model.rs:12-26) is implemented for
-// `CudaBreakoutState` inside ql-with-tensorflow (the trait's home crate), see INTEGRATION.md section 3:
-//   dims()                      -> self.dims()
-//   to_multi_dim_array()        -> Tensor::new(&[84, 84, 4]).with_values(&CudaBreakoutState::batch_to_f32(&[&Rc::new(self.clone())])?)
-//   batch_to_multi_dim_array()  -> Tensor::new(&[N, 84, 84, 4]).with_values(&CudaBreakoutState::batch_to_f32(batch)?)
+/// shard statistics (qlc_episode_stats)
+pub type EpisodeStats = ffi::qlc_episode_stats;
 
 /// One Breakout env on the GPU behind `ql::prelude::Environment` (breakout_environment.rs:131-207).
 pub struct CudaBreakoutEnvironment {
     env: Rc<Handle>,
     state: CudaBreakoutState,
+    model_dims: [u64; 3],
 }
 
 impl CudaBreakoutEnvironment {
-    /// `BreakoutEnvironment::new(frame_size_x, frame_size_y)` plus the replay ring length (`Parameter::history_buffer_len`).
-    pub fn new(frame_size_x: usize, frame_size_y: usize, history_buffer_len: usize, seed: u64, device: i32) -> Result<Self> {
+    /// `BreakoutEnvironment::new(frame_size_x, frame_size_y)` (:139-153), on device 0, seed 0, with a frame ring long enough
+    /// for `Parameter::default().history_buffer_len`. Panics like the reference constructor cannot fail: see `with_options`.
+    pub fn new(frame_size_x: usize, frame_size_y: usize) -> Self {
+        Self::with_options(frame_size_x, frame_size_y, DEFAULT_HISTORY_BUFFER_LEN, 0, 0).expect("qlc_env_create")
+    }
+
+    /// `history_buffer_len` = `Parameter::history_buffer_len` of the learner that will hold the handles (must be >= it).
+    pub fn with_options(frame_size_x: usize, frame_size_y: usize, history_buffer_len: usize, seed: u64, device: i32) -> Result<Self> {
         let cfg = ffi::qlc_config {
             struct_size: std::mem::size_of::<ffi::qlc_config>() as u32,
             device,
@@ -164,7 +150,7 @@ impl CudaBreakoutEnvironment {
             frame_h: frame_size_y as u32,
             seed,
             replay_capacity: history_buffer_len as u64,
-            max_episode_steps: 0,
+            max_episode_steps: 0, // the learner counts the steps of an episode itself (:149)
             episode_window: 100,
             auto_reset: 0, // the learner resets: learn_episode :142
             reserved: 0,
@@ -172,9 +158,25 @@ impl CudaBreakoutEnvironment {
         let mut h: *mut ffi::qlc_env = std::ptr::null_mut();
         check(unsafe { ffi::qlc_env_create(&cfg, &mut h) })?;
         let env = Rc::new(Handle(h));
-        let state = CudaBreakoutState::new(Rc::clone(&env), StateKind::Live, 0);
-        Ok(Self { env, state })
+        let model_dims = [frame_size_x as u64, frame_size_y as u64, ffi::QLC_NUM_FRAMES as u64];
+        let state = CudaBreakoutState::new(Rc::clone(&env), 0, 0, model_dims);
+        Ok(Self { env, state, model_dims })
     }
+
+    /// 1 while the episode runs, 0 once it is over: the reference game ends with the first miss (mechanics.rs:131-135).
+    pub fn lives(&self) -> u8 {
+        let mut l = 0u8;
+        check(unsafe { ffi::qlc_env_lives_host(self.env.0, &mut l) }).expect("qlc_env_lives_host");
+        l
+    }
+
+    /// OR of the sticky error flags (conditions on which the reference panics: mechanics.rs:145,265,284,303,511)
+    pub fn error_flags(&self) -> u32 {
+        let mut e = 0u32;
+        check(unsafe { ffi::qlc_env_error_flags(self.env.0, &mut e) }).expect("qlc_env_error_flags");
+        e
+    }
+
     pub(crate) fn handle(&self) -> Rc<Handle> { Rc::clone(&self.env) }
 }
 
@@ -184,7 +186,7 @@ impl Environment for CudaBreakoutEnvironment {
 
     fn reset(&mut self) {
         check(unsafe { ffi::qlc_env_reset(self.env.0, std::ptr::null(), std::ptr::null()) }).expect("qlc_env_reset");
-        self.state = CudaBreakoutState::new(Rc::clone(&self.env), StateKind::Live, self.env.time());
+        self.state = CudaBreakoutState::new(Rc::clone(&self.env), self.env.time(), 0, self.model_dims);
     }
 
     fn state(&self) -> &Self::S { &self.state }
@@ -193,7 +195,7 @@ impl Environment for CudaBreakoutEnvironment {
         let a = action.numeric();
         let (mut reward, mut done) = (0f32, 0u8);
         check(unsafe { ffi::qlc_env_step_host(self.env.0, &a, 1, &mut reward, &mut done) }).expect("qlc_env_step_host");
-        self.state = CudaBreakoutState::new(Rc::clone(&self.env), StateKind::Live, self.env.time());
+        self.state = CudaBreakoutState::new(Rc::clone(&self.env), self.state.time + 1, self.state.k + 1, self.model_dims);
         (&self.state, reward, done != 0)
     }
 

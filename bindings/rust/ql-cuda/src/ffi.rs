@@ -125,6 +125,7 @@ extern "C" {
     pub fn qlc_host_free(p: *mut c_void) -> i32;
     pub fn qlc_env_reset(env: *mut qlc_env, mask_host: *const u8, dir_x_host: *const f32) -> i32;
     pub fn qlc_env_step(env: *mut qlc_env, actions_dev: *const u8, n_steps: u32, reward_dev: *mut f32, done_dev: *mut u8, stream: *mut c_void) -> i32;
+    pub fn qlc_env_step_random(env: *mut qlc_env, n_steps: u32, actions_out_dev: *mut u8, reward_dev: *mut f32, done_dev: *mut u8, stream: *mut c_void) -> i32;
     pub fn qlc_env_step_host(env: *mut qlc_env, actions_host: *const u8, n_steps: u32, reward_host: *mut f32, done_host: *mut u8) -> i32;
     pub fn qlc_env_step_host_submit(env: *mut qlc_env, actions_host: *const u8, n_steps: u32, reward_host: *mut f32, done_host: *mut u8) -> i32;
     pub fn qlc_env_step_host_wait(env: *mut qlc_env, max_pending: u32) -> i32;

@@ -149,6 +149,11 @@ int32_t qlc_env_reset(qlc_env* env, const uint8_t* mask_host, const float* dir_x
  * Each step also renders the 84x84 u8 frame into the frame ring and writes the replay transition record
  * (ReplayBuffer::add). Asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
 int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps, float* reward_dev, uint8_t* done_dev, void* stream);
+/* The learner's pure-random phase (self_driving_tf_q_learner.rs:153-157: rng.gen_range(0..ACTION_SPACE) while step_count <
+ * epsilon_pure_random_steps) without an action buffer: the step kernel draws the uniform action of env e at time t itself
+ * (word 0 of philox({env_id_base + e, t, 0, 'ACTI'}, seed) * 3 >> 32) and writes it to actions_out_dev [n_steps][n_envs] if
+ * that is not NULL (the replay record keeps it either way). */
+int32_t qlc_env_step_random(qlc_env* env, uint32_t n_steps, uint8_t* actions_out_dev, float* reward_dev, uint8_t* done_dev, void* stream);
 /* same with HOST buffers: validates actions (QLC_ERR_OUT_OF_RANGE), H2D, step, D2H, synchronises. */
 int32_t qlc_env_step_host(qlc_env* env, const uint8_t* actions_host, uint32_t n_steps, float* reward_host, uint8_t* done_host);
 /* Pipelined form for action streams that do not depend on the previous result (the learner's random-policy phase

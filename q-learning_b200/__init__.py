@@ -42,7 +42,7 @@ ENVERR_WALL_DISTANCE, ENVERR_APPROX_RANGE, ENVERR_RECURSION, ENVERR_BISECTION, E
 ABI_SYMBOLS = [
     "qlc_version", "qlc_build_info", "qlc_last_error_string", "qlc_device_count", "qlc_env_create", "qlc_env_destroy", "qlc_sync",
     "qlc_host_alloc", "qlc_host_free",
-    "qlc_env_reset", "qlc_env_step", "qlc_env_step_host", "qlc_env_step_host_submit", "qlc_env_step_host_wait", "qlc_env_obs", "qlc_env_obs_host", "qlc_env_state_view",
+    "qlc_env_reset", "qlc_env_step", "qlc_env_step_random", "qlc_env_step_host", "qlc_env_step_host_submit", "qlc_env_step_host_wait", "qlc_env_obs", "qlc_env_obs_host", "qlc_env_state_view",
     "qlc_env_read_state", "qlc_env_goal_mean", "qlc_env_time", "qlc_env_lives_host", "qlc_env_error_flags",
     "qlc_obs_gather", "qlc_obs_gather_host",
     "qlc_replay_len", "qlc_replay_capacity", "qlc_replay_sample", "qlc_replay_gather", "qlc_replay_sample_gather", "qlc_replay_sample_host",
@@ -137,6 +137,7 @@ def load_library(build_if_missing=True):
         "qlc_host_free": (i32, [vp]),
         "qlc_env_reset": (i32, [vp, vp, vp]),
         "qlc_env_step": (i32, [vp, vp, u32, vp, vp, vp]),
+        "qlc_env_step_random": (i32, [vp, u32, vp, vp, vp, vp]),
         "qlc_env_step_host": (i32, [vp, vp, u32, vp, vp]),
         "qlc_env_step_host_submit": (i32, [vp, vp, u32, vp, vp]),
         "qlc_env_step_host_wait": (i32, [vp, u32]),
@@ -389,6 +390,11 @@ class BreakoutEnvironment:
     def step_device(self, actions_ptr, n_steps, reward_ptr=None, done_ptr=None, stream=None):
         """Asynchronous step on device buffers (raw device pointers, e.g. torch tensor .data_ptr())."""
         _check(self._L.qlc_env_step(self._h, actions_ptr, n_steps, reward_ptr, done_ptr, stream))
+
+    def step_random_device(self, n_steps, actions_out_ptr=None, reward_ptr=None, done_ptr=None, stream=None):
+        """The learner's pure-random phase: the step kernel draws the uniform action of every env and step itself (Philox 'ACTI'
+        stream); no action buffer, no policy kernel. Asynchronous, device pointers."""
+        _check(self._L.qlc_env_step_random(self._h, n_steps, actions_out_ptr, reward_ptr, done_ptr, stream))
 
     def episode_reward_goal_mean(self):
         return float(self._L.qlc_env_goal_mean())

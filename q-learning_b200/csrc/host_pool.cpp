@@ -69,8 +69,8 @@ struct Pool {
             // one process per GPU shares the host: LOCAL_WORLD_SIZE (torchrun) ranks split the cores
             int ranks = 1;
             if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
-            want = (int)(hw ? hw : 2) / (2 * ranks);     // half the hardware threads: the caller's own threads (and SMT siblings) need the rest
-            if (want > 8) want = 8;
+            want = ((int)(hw ? hw : 2) - 1) / ranks;     // (one hardware thread is left to the driver's own threads) measured on the 16-thread GPU box (tools/microbench/widen_rate.cpp): 26 / 51 / 68 /
+            if (want > 16) want = 16;                    // 106 / 183 GB/s with 1 / 2 / 4 / 8 / 16 threads - it keeps scaling to every hardware thread
         }
         if (want < 1) want = 1;
         n_threads = want;

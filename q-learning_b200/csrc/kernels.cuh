@@ -54,7 +54,9 @@ struct StepParams {
     // statistics snapshot (NULL = off): the last CTA to finish copies the shard accumulators here, so that a reduction running on
     // a side stream reads the state "after this launch" while later launches already mutate `stats`
     DeviceStats* snap; unsigned int* exit_counter; uint32_t exit_base;
-    const uint8_t* actions; float* reward; uint8_t* done;
+    const uint8_t* actions;    // [n_steps][n_envs]; NULL = uniform random policy drawn here (policy_action), written to actions_out if given
+    uint8_t* actions_out;
+    float* reward; uint8_t* done;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -266,11 +268,13 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             env_init(env, -0.25f); env.err = 0;
         }
         MoveCache mc; move_cache_update(mc, env);
-        uint32_t action = active ? p.actions[(size_t)s_begin * p.n_envs + e] : 0u;
+        uint32_t action = 0u;
+        if (active) action = p.actions ? p.actions[(size_t)s_begin * p.n_envs + e] : policy_action(p.seed, p.env_id_base + e, (uint32_t)(p.t0 + s_begin));
         for (uint32_t s = s_begin; s < s_end; ++s, ++seq) {
             const int q = seq % D;
             uint32_t next_action = 0u;
-            if (active && s + 1 < p.n_steps) next_action = p.actions[(size_t)(s + 1) * p.n_envs + e];
+            if (active && s + 1 < p.n_steps) next_action = p.actions ? p.actions[(size_t)(s + 1) * p.n_envs + e] : policy_action(p.seed, p.env_id_base + e, (uint32_t)(p.t0 + s + 1));
+            if (active && p.actions_out) p.actions_out[(size_t)s * p.n_envs + e] = (uint8_t)action;
             if (action >= 3u) { env.err |= ENVERR_ACTION; action = 0u; }
             const uint32_t score_before = env.score;
             if (active && !QLC_DEBUG_SKIP_IS(p, 1u)) time_step(env, action, mc);
@@ -320,6 +324,12 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             if (lane == 0) st_release_u64(&p.progress[batch], ((unsigned long long)p.launch_serial << 32) | s_end);
         }
         }   // items
+        // Programmatic dependent launch, triggered LATE: the physics of every item of this CTA is done, what is left is the
+        // render warps' last frames and the store drain. Once every CTA has got here the next kernel of the stream may start
+        // its prologue (barriers, zeroed frames, index sampling) on the SMs that free up; it blocks in its own
+        // griddepcontrol.wait until this grid has completed and flushed. (Triggering at the top of the kernel would let a small
+        // dependent grid — a minibatch gather — pile onto the few SMs this grid leaves free.)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         if (p.snap) {    // every statistics atomic of this CTA is done: count it out, the last one takes the snapshot
             __threadfence();
             __syncwarp();
@@ -489,78 +499,125 @@ __global__ void env_reset_kernel(EnvArrays st, uint32_t n_envs, uint32_t env_id_
 // Distinct uniform index sampling (generate_distinct_random_ids, self_driving_tf_q_learner.rs:276-296) as a WARP routine.
 // The reference's sequential rejection loop keeps the FIRST OCCURRENCES of the accepted draws, in stream order. Draw p of
 // minibatch `call` is word p & 3 of philox({p >> 2, call_lo, call_hi, 'SAMP'}), mapped to [0, len) by Lemire's multiply-shift
-// with rejection. The warp walks the stream 32 positions at a time: duplicates inside the 32 are resolved with
-// __match_any_sync (lowest lane = first occurrence), duplicates of earlier positions with a small shared-memory hash set
-// (atomicCAS insert); ranks come from ballots. Because the routine is cheap (one Philox block per lane and 128 positions) it
-// runs INSIDE the gather kernels — every CTA derives the index of its own item and stops as soon as it has it — so that a
-// sampled minibatch is ONE kernel launch; the index-only entry point (qlc_replay_sample) runs the same routine, one warp
-// per minibatch, storing all of them.
+// with rejection. The warp walks the stream 128 positions per round — lane L owns positions 4L..4L+3 of the round, the four
+// words of ONE Philox block — and keeps the values seen so far in a shared-memory hash table (value, stream position), open
+// addressing. Inserts use NO atomics (shared-memory atomics turned out to be the bottleneck once several sampler warps share
+// an SM): every draw looks at its slot, the ones that found it empty store their value, a __syncwarp later whoever reads its
+// own value back owns the slot, the others probe on. Draws with equal values walk the same probe sequence in lockstep and
+// therefore always meet in the same slot in the same pass — they notice it because only one of their stream positions
+// survives in the position word; that (rare: two equal values among 128 draws) case is settled with atomicMin on the
+// positions. A draw is a first occurrence iff no earlier round holds its value and it has the smallest position of its round.
+// Ranks come from a warp prefix sum of the per-lane counts. Because the routine is cheap it runs INSIDE the gather kernels —
+// every CTA derives the index of its own item and stops as soon as it has it — so that a sampled minibatch is ONE kernel
+// launch; the index-only entry point (qlc_replay_sample) runs the same routine, one warp per minibatch, storing all of them.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SAMPLE_MAX_BATCH = 1024;
 constexpr uint32_t SAMPLE_EMPTY = 0xFFFFFFFFu;           // never a value: len < 2^32 - 1 is checked by the host
-constexpr uint32_t SAMPLE_MAX_BLOCKS = 1u << 19;         // x 128 stream positions: the bound of the "loop" in the reference
+constexpr uint32_t SAMPLE_MAX_ROUNDS = 1u << 19;         // x 128 stream positions: the bound of the "loop" in the reference
 
-__host__ __device__ __forceinline__ uint32_t sample_table_size(uint32_t batch) {   // power of two >= 2 * (batch + 32)
-    uint32_t n = 128;
-    while (n < 2u * (batch + 32u)) n <<= 1;
-    return n;                                                                       // <= 4096 entries = 16 KB
+__host__ __device__ __forceinline__ uint32_t sample_table_size(uint32_t batch) {   // slots: power of two >= 2 * (batch + 128)
+    uint32_t n = 512;
+    while (n < 2u * (batch + 128u)) n <<= 1;
+    return n;                                                                       // <= 4096 slots x (value, position) = 32 KB
+}
+
+__device__ __forceinline__ void sample_table_clear(uint32_t* table, uint32_t tsize, int tid, int nthreads) {
+    for (uint32_t i = tid; i < 2u * tsize / 4u; i += nthreads) reinterpret_cast<uint4*>(table)[i] = make_uint4(SAMPLE_EMPTY, SAMPLE_EMPTY, SAMPLE_EMPTY, SAMPLE_EMPTY);
 }
 
 // ALL = false: returns the index of item j of the minibatch (every lane gets it).  ALL = true: stores the first `batch`
-// indices to out[0..batch) and returns 0.  `table` = sample_table_size(batch) words of shared memory, all SAMPLE_EMPTY.
+// indices to out[0..batch) and returns 0.  `table` = 2 * sample_table_size(batch) words of shared memory, all SAMPLE_EMPTY
+// (values in the first half, stream positions in the second).
 template <bool ALL>
 __device__ __forceinline__ uint32_t sample_distinct_warp(uint32_t* table, uint32_t tsize, uint32_t len, uint64_t seed, uint64_t call,
                                                          uint32_t j, uint32_t batch, uint32_t* out, int lane) {
     const uint32_t thresh = (uint32_t)((0x100000000ull - (uint64_t)len) % (uint64_t)len);   // Lemire rejection zone
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    const uint32_t tmask = tsize - 1u, lt = (1u << lane) - 1u;
+    const uint32_t tmask = tsize - 1u;
+    volatile uint32_t* tval = table; volatile uint32_t* tpos = table + tsize;
     uint32_t kept = 0;
-    for (uint32_t blk = 0; blk < SAMPLE_MAX_BLOCKS; ++blk) {
-        const uint4 r = philox4x32_10(make_uint4(blk * 32u + (uint32_t)lane, (uint32_t)call, (uint32_t)(call >> 32), STREAM_SAMPLE), key);
-        #pragma unroll 1
-        for (int sub = 0; sub < 4; ++sub) {
-            // stream position blk*128 + sub*32 + lane lives in word (lane & 3) of the block of lane sub*8 + (lane >> 2)
-            const int src = sub * 8 + (lane >> 2);
-            const uint32_t x = __shfl_sync(0xFFFFFFFFu, r.x, src), y = __shfl_sync(0xFFFFFFFFu, r.y, src);
-            const uint32_t z = __shfl_sync(0xFFFFFFFFu, r.z, src), w = __shfl_sync(0xFFFFFFFFu, r.w, src);
-            const uint32_t raw = (lane & 2) ? ((lane & 1) ? w : z) : ((lane & 1) ? y : x);
-            const uint64_t m = (uint64_t)raw * (uint64_t)len;
-            const bool valid = !((uint32_t)m < thresh);
-            const uint32_t val = (uint32_t)(m >> 32);
-            const unsigned long long mkey = valid ? ((1ull << 32) | val) : (unsigned long long)lane;   // rejected draws match nobody
-            const uint32_t same = __match_any_sync(0xFFFFFFFFu, mkey);
-            bool fresh = false;
-            if (valid && (uint32_t)lane == (uint32_t)(__ffs(same) - 1)) {                            // first occurrence among these 32
-                uint32_t h = (val * 0x9E3779B1u) >> 7 & tmask;
-                for (;;) {
-                    const uint32_t old = atomicCAS(&table[h], SAMPLE_EMPTY, val);
-                    if (old == SAMPLE_EMPTY) { fresh = true; break; }                                // not seen at an earlier position
-                    if (old == val) break;
-                    h = (h + 1u) & tmask;
+    for (uint32_t round = 0; round < SAMPLE_MAX_ROUNDS; ++round) {
+        const uint32_t ctr = round * 32u + (uint32_t)lane;
+        const uint32_t round_base = round * 128u;
+        const uint4 r = philox4x32_10(make_uint4(ctr, (uint32_t)call, (uint32_t)(call >> 32), STREAM_SAMPLE), key);
+        const uint32_t raw[4] = {r.x, r.y, r.z, r.w};
+        uint32_t val[4], slot[4];
+        bool pending[4], cand[4];                        // cand: accepted draw whose value no earlier round holds
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint64_t m = (uint64_t)raw[w] * (uint64_t)len;
+            pending[w] = !((uint32_t)m < thresh);
+            val[w] = (uint32_t)(m >> 32);
+            slot[w] = ((val[w] * 0x9E3779B1u) >> 12) & tmask;
+            cand[w] = false;
+        }
+        bool conflict = false;                           // two draws of THIS round share a value
+        while (__any_sync(0xFFFFFFFFu, pending[0] || pending[1] || pending[2] || pending[3])) {
+            bool attempt[4];
+            #pragma unroll
+            for (int w = 0; w < 4; ++w) {                // look
+                attempt[w] = false;
+                if (pending[w]) {
+                    const uint32_t cur = tval[slot[w]];
+                    if (cur == SAMPLE_EMPTY) attempt[w] = true;
+                    else if (cur == val[w]) { pending[w] = false; if (tpos[slot[w]] >= round_base) { cand[w] = true; conflict = true; } }   // same value: earlier round = duplicate
+                    else slot[w] = (slot[w] + 1u) & tmask;
                 }
             }
-            const uint32_t acc = __ballot_sync(0xFFFFFFFFu, fresh);
-            const uint32_t rank = kept + __popc(acc & lt);
-            if (ALL) {
-                if (fresh && rank < batch) out[rank] = val;
-                kept += __popc(acc);
-                if (kept >= batch) return 0u;
-            } else {
-                const uint32_t hit = __ballot_sync(0xFFFFFFFFu, fresh && rank == j);
-                if (hit) return __shfl_sync(0xFFFFFFFFu, val, __ffs(hit) - 1);
-                kept += __popc(acc);
-            }
+            __syncwarp();
+            #pragma unroll
+            for (int w = 0; w < 4; ++w) if (attempt[w]) tval[slot[w]] = val[w];     // claim: one of the writers survives
+            __syncwarp();
+            #pragma unroll
+            for (int w = 0; w < 4; ++w)
+                if (attempt[w]) {
+                    if (tval[slot[w]] == val[w]) { pending[w] = false; cand[w] = true; tpos[slot[w]] = ctr * 4u + (uint32_t)w; }   // mine, or an equal value's
+                    else slot[w] = (slot[w] + 1u) & tmask;
+                }
+            __syncwarp();
+            #pragma unroll
+            for (int w = 0; w < 4; ++w) if (attempt[w] && cand[w] && tpos[slot[w]] != ctr * 4u + (uint32_t)w) conflict = true;   // an equal value claimed with me
+            __syncwarp();
         }
+        if (__any_sync(0xFFFFFFFFu, conflict)) {         // rare: settle equal values of this round by their stream positions
+            #pragma unroll
+            for (int w = 0; w < 4; ++w) if (cand[w]) atomicMin(table + tsize + slot[w], ctr * 4u + (uint32_t)w);
+            __syncwarp();
+            #pragma unroll
+            for (int w = 0; w < 4; ++w) cand[w] = cand[w] && tpos[slot[w]] == ctr * 4u + (uint32_t)w;
+        }
+        uint32_t cnt = 0;
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) cnt += cand[w] ? 1u : 0u;
+        uint32_t incl = cnt;                              // ordered prefix sum over the lanes (= over the stream positions)
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t rank = kept + incl - cnt;
+        if (ALL) {
+            #pragma unroll
+            for (int w = 0; w < 4; ++w) if (cand[w]) { if (rank < batch) out[rank] = val[w]; ++rank; }
+            kept += total;
+            if (kept >= batch) return 0u;
+        } else {
+            uint32_t mine = SAMPLE_EMPTY;
+            #pragma unroll
+            for (int w = 0; w < 4; ++w) if (cand[w]) { if (rank == j) mine = val[w]; ++rank; }
+            const uint32_t hit = __ballot_sync(0xFFFFFFFFu, mine != SAMPLE_EMPTY);
+            if (hit) return __shfl_sync(0xFFFFFFFFu, mine, __ffs(hit) - 1);
+            kept += total;
+        }
+        __syncwarp();
     }
     return 0u;   // unreachable for len >= batch (the reference would loop forever here)
 }
 
 // index-only form: one warp per minibatch
 __global__ void __launch_bounds__(32) replay_sample_kernel(uint32_t* out, uint32_t batch, uint32_t len, uint64_t seed, uint64_t call0) {
-    __shared__ uint32_t table[4096];
+    __shared__ uint32_t table[2 * 4096];
     const int lane = threadIdx.x;
     const uint32_t tsize = sample_table_size(batch);
-    for (uint32_t i = lane; i < tsize; i += 32) table[i] = SAMPLE_EMPTY;
+    for (uint32_t i = lane; i < 2u * tsize; i += 32) table[i] = SAMPLE_EMPTY;
     __syncwarp();
     sample_distinct_warp<true>(table, tsize, len, seed, call0 + blockIdx.x, 0u, batch, out + (size_t)blockIdx.x * batch, lane);
 }
@@ -585,6 +642,7 @@ struct GatherParams {
     uint32_t mode, n_items, n_envs, time_slots;
     uint64_t t_now, t_oldest;  // replay holds transitions of times [t_oldest, t_now)
     uint32_t sample_batch, sample_len; uint64_t seed, call0; uint32_t* idx_out;   // GATHER_SAMPLE
+    uint32_t slices;           // [b][x][y][slot] kernel: CTAs per (item, state | next), each writes 1/slices of the pixels
     void* out_state; void* out_next;
     float* reward; uint8_t* action; uint8_t* done;
 };
@@ -634,21 +692,21 @@ __device__ __forceinline__ void write_scalars(const GatherParams& g, uint32_t b,
 
 // u8 [b][slot][y][x]: one warp per item; <= 5 distinct frames in, 8 frames out, all as 7,056-byte bulk copies.
 __global__ void __launch_bounds__(32) gather_u8_kernel(GatherParams g) {
-    extern __shared__ __align__(128) uint8_t sm[];     // 5 frames + 1 zero frame; the sampler's hash set borrows the first 16 KB
+    extern __shared__ __align__(128) uint8_t sm[];     // 5 frames + 1 zero frame; the sampler's hash table borrows the first <= 32 KB
     __shared__ uint64_t bar;
     const int lane = threadIdx.x;
     const uint32_t b = blockIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's prologue may overlap this grid (see env_advance_kernel)
     uint8_t* zero = sm + 5 * FRAME_BYTES;
     for (int i = lane; i < FRAME_VEC16; i += 32) reinterpret_cast<uint4*>(zero)[i] = make_uint4(0, 0, 0, 0);
     if (lane == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     uint32_t idx = 0;
+    uint32_t* table = reinterpret_cast<uint32_t*>(sm);
     if (g.mode == GATHER_SAMPLE) {
-        uint32_t* table = reinterpret_cast<uint32_t*>(sm);
-        const uint32_t tsize = sample_table_size(g.sample_batch);
-        for (uint32_t i = lane; i < tsize; i += 32) table[i] = SAMPLE_EMPTY;
+        sample_table_clear(table, sample_table_size(g.sample_batch), lane, 32);
         __syncwarp();
         const uint32_t mb = b / g.sample_batch, j = b - mb * g.sample_batch;
-        idx = sample_distinct_warp<false>(table, tsize, g.sample_len, g.seed, g.call0 + mb, j, g.sample_batch, nullptr, lane);
+        idx = sample_distinct_warp<false>(table, sample_table_size(g.sample_batch), g.sample_len, g.seed, g.call0 + mb, j, g.sample_batch, nullptr, lane);
     }
     // launched with programmatic stream serialization: everything above neither reads nor writes anything an earlier kernel touches
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -656,7 +714,7 @@ __global__ void __launch_bounds__(32) gather_u8_kernel(GatherParams g) {
     if (g.mode == GATHER_INDICES) idx = g.indices[b];
     uint64_t T; uint32_t e, k, rec;
     const bool exists = locate(g, b, idx, T, e, k, rec);
-    fence_proxy_async_smem();                            // zero frame / hash set (generic proxy) before the bulk copies (async proxy)
+    fence_proxy_async_smem();                            // zero frame / hash table (generic proxy) before the bulk copies (async proxy)
     __syncwarp();
     if (lane == 0) {
         write_scalars(g, b, rec);
@@ -688,42 +746,47 @@ __global__ void __launch_bounds__(32) gather_u8_kernel(GatherParams g) {
     }
 }
 
-// [b][x][y][slot] (the reference's ToMultiDimArray layout), as f32 (value = u8 as f32) or as u8: one CTA per (item, which);
-// 4 slot frames staged in shared memory by bulk copies, then a conflict-free transposing read (row stride 84 B = 21 words)
-// and one coalesced 16-byte (f32) / 4-byte (u8) store per pixel.
+// [b][x][y][slot] (the reference's ToMultiDimArray layout), as f32 (value = u8 as f32) or as u8: `slices` CTAs per (item, state |
+// next); 4 slot frames staged in shared memory by bulk copies, then a conflict-free transposing read (row stride 84 B = 21
+// words) and one coalesced 16-byte (f32) / 4-byte (u8) store per pixel of the CTA's slice. More slices = more, smaller CTAs: a
+// single minibatch of 32 spreads over every SM, and a big call is balanced by the block scheduler (the SMs' store pipes are the
+// limit: 6 instead of 7 resident CTAs on an SM would leave it idle for the last seventh of the kernel).
 constexpr int GATHER_XYH_THREADS = 256;
 __device__ __forceinline__ void store_pixel(float4* o, int idx, uint8_t a, uint8_t b, uint8_t c, uint8_t d) { o[idx] = make_float4((float)a, (float)b, (float)c, (float)d); }
 __device__ __forceinline__ void store_pixel(uchar4* o, int idx, uint8_t a, uint8_t b, uint8_t c, uint8_t d) { o[idx] = make_uchar4(a, b, c, d); }
 
 template <class Px>
 __global__ void __launch_bounds__(GATHER_XYH_THREADS) gather_xyh_kernel(GatherParams g) {
-    extern __shared__ __align__(128) uint8_t sm[];     // 4 slot frames; the sampler's hash set borrows the first 16 KB
+    extern __shared__ __align__(128) uint8_t sm[];     // 4 slot frames; the sampler's hash table borrows the first <= 32 KB
     __shared__ uint64_t bar;
     __shared__ uint32_t s_idx;
     const int tid = threadIdx.x;
-    const uint32_t b = blockIdx.x >> 1, which = blockIdx.x & 1u;   // 0 = state, 1 = next
+    const uint32_t unit = blockIdx.x / g.slices, slice = blockIdx.x - unit * g.slices;
+    const uint32_t b = unit >> 1, which = unit & 1u;   // 0 = state, 1 = next
     Px* out = reinterpret_cast<Px*>(which ? g.out_next : g.out_state);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's prologue may overlap this grid (see env_advance_kernel)
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     uint32_t idx = 0;
+    uint32_t* table = reinterpret_cast<uint32_t*>(sm);
     if (g.mode == GATHER_SAMPLE) {
-        uint32_t* table = reinterpret_cast<uint32_t*>(sm);
-        const uint32_t tsize = sample_table_size(g.sample_batch);
-        for (uint32_t i = tid; i < tsize; i += GATHER_XYH_THREADS) table[i] = SAMPLE_EMPTY;
+        sample_table_clear(table, sample_table_size(g.sample_batch), tid, GATHER_XYH_THREADS);
         __syncthreads();
         if (tid < 32) {
             const uint32_t mb = b / g.sample_batch, j = b - mb * g.sample_batch;
-            const uint32_t v = sample_distinct_warp<false>(table, tsize, g.sample_len, g.seed, g.call0 + mb, j, g.sample_batch, nullptr, tid);
+            const uint32_t v = sample_distinct_warp<false>(table, sample_table_size(g.sample_batch), g.sample_len, g.seed, g.call0 + mb, j, g.sample_batch, nullptr, tid);
             if (tid == 0) s_idx = v;
         }
-        __syncthreads();
-        idx = s_idx;
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic stream serialization: nothing above touches an earlier kernel's data
-    if (g.mode == GATHER_SAMPLE && tid == 0 && g.idx_out && (which == 0 || !g.out_state)) g.idx_out[b] = idx;
+    if (g.mode == GATHER_SAMPLE) {
+        __syncthreads();
+        idx = s_idx;
+        if (tid == 0 && slice == 0 && g.idx_out && (which == 0 || !g.out_state)) g.idx_out[b] = idx;
+    }
     if (g.mode == GATHER_INDICES) idx = g.indices[b];
     uint64_t T; uint32_t e, k, rec;
     const bool exists = locate(g, b, idx, T, e, k, rec);
-    if (tid == 0 && (which == 0 || !g.out_state)) write_scalars(g, b, rec);
+    if (tid == 0 && slice == 0 && (which == 0 || !g.out_state)) write_scalars(g, b, rec);
     if (!out) return;
     // zero-fill the slots that have no frame yet
     uint32_t dsl[4];
@@ -751,7 +814,8 @@ __global__ void __launch_bounds__(GATHER_XYH_THREADS) gather_xyh_kernel(GatherPa
         mbar_wait(&bar, 0);
     }
     Px* o = out + (size_t)b * FRAME_BYTES;
-    for (int i = tid; i < FRAME_BYTES; i += GATHER_XYH_THREADS) {
+    const int per_slice = FRAME_BYTES / (int)g.slices;     // slices in {1, 2, 4}: 7,056 = 4 * 1,764
+    for (int i = (int)slice * per_slice + tid; i < ((int)slice + 1) * per_slice; i += GATHER_XYH_THREADS) {
         const int x = i / FRAME_H, y = i - x * FRAME_H;
         const int src = y * FRAME_W + x;
         store_pixel(o, i, sm[src], sm[FRAME_BYTES + src], sm[2 * FRAME_BYTES + src], sm[3 * FRAME_BYTES + src]);

@@ -342,6 +342,13 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     }
     return c;
 }
+// The learner's pure-random phase (self_driving_tf_q_learner.rs:153-157: rng.gen_range(0..ACTION_SPACE) while
+// step_count < epsilon_pure_random_steps) with the draw made on the device: uniform in {0, 1, 2} from word 0 of
+// philox({env_global_id, t, 0, 'ACTI'}) by multiply-shift (the synthetic action stream of bench.py and the oracle).
+__device__ __forceinline__ uint32_t policy_action(uint64_t seed, uint32_t env_global_id, uint32_t t) {
+    const uint4 r = philox4x32_10(make_uint4(env_global_id, t, 0u, STREAM_ACTION), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    return (uint32_t)(((uint64_t)r.x * 3ull) >> 32);
+}
 // rand 0.8.5 gen_range(-0.35f32..-0.15) from 32 random bits (mechanics.rs:103)
 __device__ __forceinline__ float reset_dir_x(uint64_t seed, uint32_t env_global_id, uint32_t episode) {
     const uint4 r = philox4x32_10(make_uint4(env_global_id, episode, 0u, STREAM_RESET), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));

@@ -64,7 +64,7 @@ struct qlc_env {
     cudaEvent_t submit_done[8] = {};           // completion of submit k in slot k % 8 (created on first use)
     cudaStream_t copy_stream = nullptr;        // pipelined submits: the H2D of step k+1 runs beside the kernel of step k
     cudaEvent_t h2d_done[2] = {};
-    cudaEvent_t stage_ev = nullptr;            // host gathers: "the state stack has arrived" while the next stack is still in flight
+    cudaEvent_t piece_ev[16] = {};             // host gathers: "piece i of the stacks has arrived" while the next ones are still in flight
     int zero_copy = 1;                         // QLC_ZERO_COPY=0: always stage page-locked outputs through a D2H copy
     uint32_t time_slots = 0;                   // frame/record ring length in time steps (= t_cap + 4)
     uint32_t t_cap = 0;                        // replay capacity in time steps
@@ -94,6 +94,7 @@ struct qlc_env {
         double *mine = nullptr, *gathered = nullptr, *reduced = nullptr;   // device: [5], [world][5], [5]
         double* host = nullptr;                // page-locked mirror of `reduced`
         uint64_t reductions = 0;
+        bool armed = false;                    // a reduction followed the previous launch: this one takes a snapshot too
         uint32_t last_serial = 0; bool have_snap = false;
     }* comm = nullptr;
 };
@@ -248,7 +249,7 @@ int32_t qlc_env_destroy(qlc_env* env) {
     if (env->dev_stage) cudaFree(env->dev_stage);
     for (cudaEvent_t ev : env->submit_done) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : env->h2d_done) if (ev) cudaEventDestroy(ev);
-    if (env->stage_ev) cudaEventDestroy(env->stage_ev);
+    for (cudaEvent_t ev : env->piece_ev) if (ev) cudaEventDestroy(ev);
     if (env->copy_stream) cudaStreamDestroy(env->copy_stream);
     if (env->own_stream) cudaStreamDestroy(env->own_stream);
     delete env;
@@ -333,22 +334,26 @@ static int32_t launch_advance(qlc_env* env, StepParams& p, cudaStream_t s, uint3
     }
     CUDA_TRY(cudaGetLastError());
     if (n_batches * n_chunks > grid) env->work_base += n_batches * n_chunks;      // (n_items - grid) hand-outs + one failed grab per CTA
-    if (env->comm && p.snap) { env->comm->exit_base += grid; env->comm->last_serial = env->launch_serial; env->comm->have_snap = true; }
+    if (env->comm) {
+        if (p.snap) { env->comm->exit_base += grid; env->comm->last_serial = env->launch_serial; }
+        env->comm->have_snap = p.snap != nullptr;      // a launch without a snapshot makes the older ones stale
+        env->comm->armed = false;
+    }
     return QLC_OK;
 }
 
 // one launch of at most time_slots steps (a longer one would wrap the frame ring inside the launch: with time chunking two CTAs
 // could then have bulk stores to the same slot in flight, ordered by nothing)
-static int32_t step_launch(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps, float* reward_dev, uint8_t* done_dev, void* stream) {
+static int32_t step_launch(qlc_env* env, const uint8_t* actions_dev, uint8_t* actions_out_dev, uint32_t n_steps, float* reward_dev, uint8_t* done_dev, void* stream) {
     int32_t rc = QLC_OK;
     StepParams p{};
     p.n_envs = env->cfg.n_envs; p.env_id_base = env->cfg.env_id_base; p.time_slots = env->time_slots;
     p.max_episode_steps = env->cfg.max_episode_steps; p.auto_reset = env->cfg.auto_reset; p.n_steps = n_steps;
     p.t0 = env->t; p.seed = env->cfg.seed; p.frames = env->frames; p.records = env->records; p.stats = env->stats;
-    p.actions = actions_dev; p.reward = reward_dev; p.done = done_dev;
+    p.actions = actions_dev; p.actions_out = actions_out_dev; p.reward = reward_dev; p.done = done_dev;
     p.debug_skip = (uint32_t)env->debug_skip;
     cudaStream_t s = (cudaStream_t)stream;
-    if (qlc_env::Comm* c = env->comm) {
+    if (qlc_env::Comm* c = env->comm; c && c->armed) {           // snapshots only while the caller keeps reducing (an atomic per CTA otherwise saved)
         const uint32_t slot = (env->launch_serial + 1u) & 3u;     // launch_advance pre-increments the serial
         if (c->slot_busy[slot]) { CUDA_TRY(cudaStreamWaitEvent(s, c->slot_read[slot], 0)); c->slot_busy[slot] = false; }   // 4 launches back: long done
         p.snap = c->snap + slot; p.exit_counter = c->exit_counter; p.exit_base = c->exit_base;
@@ -382,20 +387,31 @@ static int32_t step_launch(qlc_env* env, const uint8_t* actions_dev, uint32_t n_
 
 extern "C" {
 
-int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps, float* reward_dev, uint8_t* done_dev, void* stream) {
-    QLC_RANGE("qlc_env_step");
-    if (!env || !actions_dev) return fail(QLC_ERR_INVALID_ARG, "env/actions is null");
+static int32_t step_split(qlc_env* env, const uint8_t* actions_dev, uint8_t* actions_out_dev, uint32_t n_steps, float* reward_dev, uint8_t* done_dev, void* stream) {
     if (n_steps == 0) return QLC_OK;
     int32_t rc = set_device(env); if (rc) return rc;
     const size_t n = env->cfg.n_envs;
     for (uint32_t at = 0; at < n_steps;) {               // launches of at most one ring length each (see step_launch)
         const uint32_t part = n_steps - at < env->time_slots ? n_steps - at : env->time_slots;
-        rc = step_launch(env, actions_dev + (size_t)at * n, part, reward_dev ? reward_dev + (size_t)at * n : nullptr,
-                         done_dev ? done_dev + (size_t)at * n : nullptr, stream);
+        rc = step_launch(env, actions_dev ? actions_dev + (size_t)at * n : nullptr, actions_out_dev ? actions_out_dev + (size_t)at * n : nullptr, part,
+                         reward_dev ? reward_dev + (size_t)at * n : nullptr, done_dev ? done_dev + (size_t)at * n : nullptr, stream);
         if (rc) return rc;
         at += part;
     }
     return QLC_OK;
+}
+
+int32_t qlc_env_step(qlc_env* env, const uint8_t* actions_dev, uint32_t n_steps, float* reward_dev, uint8_t* done_dev, void* stream) {
+    QLC_RANGE("qlc_env_step");
+    if (!env || !actions_dev) return fail(QLC_ERR_INVALID_ARG, "env/actions is null");
+    return step_split(env, actions_dev, nullptr, n_steps, reward_dev, done_dev, stream);
+}
+
+// the learner's pure-random phase: the uniform action of every env and step is drawn inside the step kernel
+int32_t qlc_env_step_random(qlc_env* env, uint32_t n_steps, uint8_t* actions_out_dev, float* reward_dev, uint8_t* done_dev, void* stream) {
+    QLC_RANGE("qlc_env_step_random");
+    if (!env) return fail(QLC_ERR_INVALID_ARG, "env is null");
+    return step_split(env, nullptr, actions_out_dev, n_steps, reward_dev, done_dev, stream);
 }
 
 static bool is_pinned(const void* p) {
@@ -504,21 +520,51 @@ static void fill_gather(const qlc_env* env, GatherParams& g) {
     g.mode = GATHER_INDICES;
 }
 
-static int32_t launch_gather(qlc_env* env, const GatherParams& g, int32_t layout, cudaStream_t s) {
-    if (g.n_items == 0) return QLC_OK;
+static bool known_layout(int32_t layout) { return layout == QLC_LAYOUT_U8_BHYX || layout == QLC_LAYOUT_F32_BXYH || layout == QLC_LAYOUT_U8_BXYH; }
+
+// Dynamic shared memory request that caps the resident CTAs per SM at `cap` (228 KB per SM, 1 KB reserved per CTA). Small grids
+// launched with programmatic stream serialization start while their predecessor still holds most SMs; without a cap the block
+// scheduler packs them 5-8 deep onto the few SMs that are free, and a minibatch gather then runs on a tenth of the machine.
+static size_t smem_for_cap(size_t needed, uint32_t cap) {
+    if (cap == 0 || cap >= 8) return needed;
+    const size_t want = (size_t)228 * 1024 / (cap + 1) + 16;     // cap + 1 CTAs of this size do not fit
+    const size_t most = (size_t)227 * 1024;
+    return needed > want ? needed : (want > most ? most : want);
+}
+
+static int32_t launch_gather(qlc_env* env, const GatherParams& g_in, int32_t layout, cudaStream_t s) {
+    if (g_in.n_items == 0) return QLC_OK;
+    GatherParams g = g_in;
     static bool configured[64] = {};
-    if (!configured[env->cfg.device & 63]) {     // the u8 kernel's 6 frames need the opt-in shared-memory size
-        CUDA_TRY(cudaFuncSetAttribute(gather_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * FRAME_BYTES));
+    if (!configured[env->cfg.device & 63]) {     // opt in to large dynamic shared memory (6 frames; occupancy caps)
+        CUDA_TRY(cudaFuncSetAttribute(gather_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(gather_xyh_kernel<float4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(gather_xyh_kernel<uchar4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured[env->cfg.device & 63] = true;
     }
+    static const int slices_force = getenv("QLC_GATHER_SLICES") ? atoi(getenv("QLC_GATHER_SLICES")) : 0;
+    static const int cap_force = getenv("QLC_GATHER_CAP") ? atoi(getenv("QLC_GATHER_CAP")) : -1;
+    const uint32_t sms = (uint32_t)env->sm_count;
+    g.slices = 1;
     // scalars only (get_many without tensorisation): the one-warp kernel has the path for it, whatever the layout
     if (layout == QLC_LAYOUT_U8_BHYX || (!g.out_state && !g.out_next)) {
-        if (layout != QLC_LAYOUT_U8_BHYX && layout != QLC_LAYOUT_F32_BXYH && layout != QLC_LAYOUT_U8_BXYH) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
-        CUDA_TRY(launch_pdl(gather_u8_kernel, dim3(g.n_items), dim3(32), 6 * FRAME_BYTES, s, g));
-    } else if (layout == QLC_LAYOUT_F32_BXYH) {
-        CUDA_TRY(launch_pdl(gather_xyh_kernel<float4>, dim3(g.n_items * 2), dim3(GATHER_XYH_THREADS), 4 * FRAME_BYTES, s, g));
-    } else if (layout == QLC_LAYOUT_U8_BXYH) {
-        CUDA_TRY(launch_pdl(gather_xyh_kernel<uchar4>, dim3(g.n_items * 2), dim3(GATHER_XYH_THREADS), 4 * FRAME_BYTES, s, g));
+        if (!known_layout(layout)) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
+        uint32_t cap = (g.n_items + sms - 1) / sms;                  // spread a small grid over the SMs
+        if (cap_force >= 0) cap = (uint32_t)cap_force;
+        CUDA_TRY(launch_pdl(gather_u8_kernel, dim3(g.n_items), dim3(32), smem_for_cap(6 * FRAME_BYTES, cap), s, g));
+    } else if (layout == QLC_LAYOUT_F32_BXYH || layout == QLC_LAYOUT_U8_BXYH) {
+        // slices: enough CTAs to put a single small minibatch on every SM (each CTA stages the 4 frames again, from L2)
+        const uint32_t units = g.n_items * 2u;
+        g.slices = units * 4u <= 2u * sms ? 4u : (units * 2u <= 2u * sms ? 2u : 1u);
+        if (slices_force == 1 || slices_force == 2 || slices_force == 4) g.slices = (uint32_t)slices_force;
+        const uint32_t ctas = units * g.slices;
+        size_t smem = 4 * FRAME_BYTES;           // 4 slot frames; the in-kernel sampler's table (batch > 896: 32 KB) borrows the same bytes
+        if (g.mode == GATHER_SAMPLE && 8u * (size_t)sample_table_size(g.sample_batch) > smem) smem = 8u * (size_t)sample_table_size(g.sample_batch);
+        uint32_t cap = (ctas + sms - 1) / sms;
+        if (cap_force >= 0) cap = (uint32_t)cap_force;
+        smem = smem_for_cap(smem, cap);
+        if (layout == QLC_LAYOUT_F32_BXYH) CUDA_TRY(launch_pdl(gather_xyh_kernel<float4>, dim3(ctas), dim3(GATHER_XYH_THREADS), smem, s, g));
+        else CUDA_TRY(launch_pdl(gather_xyh_kernel<uchar4>, dim3(ctas), dim3(GATHER_XYH_THREADS), smem, s, g));
     } else {
         return fail(QLC_ERR_INVALID_ARG, "unknown layout");
     }
@@ -527,7 +573,6 @@ static int32_t launch_gather(qlc_env* env, const GatherParams& g, int32_t layout
 }
 
 static size_t item_bytes(int32_t layout) { return layout == QLC_LAYOUT_F32_BXYH ? (size_t)FRAME_BYTES * 4 * sizeof(float) : (size_t)FRAME_BYTES * 4; }
-static bool known_layout(int32_t layout) { return layout == QLC_LAYOUT_U8_BHYX || layout == QLC_LAYOUT_F32_BXYH || layout == QLC_LAYOUT_U8_BXYH; }
 
 int32_t qlc_env_obs(qlc_env* env, int32_t layout, void* out_dev, void* stream) {
     QLC_RANGE("qlc_env_obs");
@@ -706,44 +751,55 @@ static int32_t run_host_gather(qlc_env* env, HostGather& hg) {
     const bool widen = hg.layout == QLC_LAYOUT_F32_BXYH && widen_on_host;
     const int32_t dev_layout = widen ? QLC_LAYOUT_U8_BXYH : hg.layout;
     const size_t ib = item_bytes(dev_layout);
-    // device staging: in (idx / handles) | state | next | reward | action | done | idx_out
-    const size_t o_in = 0, o_s = (hg.h2d_bytes + 255) & ~(size_t)255, o_n = o_s + ib * n, o_r = o_n + ib * n, o_a = o_r + (size_t)n * 4, o_d = o_a + n;
-    const size_t o_i = (o_d + n + 15) & ~(size_t)15, total = o_i + (size_t)n * 4;
-    int32_t rc = ensure_dev_stage(env, total); if (rc) return rc;
+    // page-locked staging (device-visible: the kernel reads the indices / handles from it and writes the scalars into it — a few
+    // hundred bytes over PCIe instead of two more copy launches): in | reward | action | done | idx_out | state | next
+    const size_t o_in = 0, o_r = (hg.h2d_bytes + 255) & ~(size_t)255, o_a = o_r + (size_t)n * 4, o_d = o_a + n, o_i = (o_d + n + 15) & ~(size_t)15;
+    const size_t o_s = (o_i + (size_t)n * 4 + 255) & ~(size_t)255, o_n = o_s + ib * n, total = o_n + ib * n;
+    int32_t rc = ensure_dev_stage(env, 2 * ib * n); if (rc) return rc;
     rc = ensure_pin(env, total); if (rc) return rc;
     uint8_t* dev = (uint8_t*)env->dev_stage; uint8_t* pin = (uint8_t*)env->pin;
+    uint8_t* dev_s = dev; uint8_t* dev_n = dev + ib * n;
     cudaStream_t s = env->own_stream;
-    if (hg.h2d_bytes) {
-        memcpy(pin + o_in, hg.h2d_src, hg.h2d_bytes);
-        CUDA_TRY(cudaMemcpyAsync(dev + o_in, pin + o_in, hg.h2d_bytes, cudaMemcpyHostToDevice, s));
-    }
+    if (hg.h2d_bytes) memcpy(pin + o_in, hg.h2d_src, hg.h2d_bytes);
     GatherParams& g = hg.g;
-    if (g.mode == GATHER_INDICES) g.indices = (const uint32_t*)(dev + o_in);
-    if (g.mode == GATHER_HANDLES) g.handles = (const ObsHandle*)(dev + o_in);
-    if (g.mode == GATHER_SAMPLE) g.idx_out = hg.idx_out_host ? (uint32_t*)(dev + o_i) : nullptr;
+    if (g.mode == GATHER_INDICES) g.indices = (const uint32_t*)(pin + o_in);
+    if (g.mode == GATHER_HANDLES) g.handles = (const ObsHandle*)(pin + o_in);
+    if (g.mode == GATHER_SAMPLE) g.idx_out = hg.idx_out_host ? (uint32_t*)(pin + o_i) : nullptr;
     g.n_items = n;
-    g.out_state = hg.state_host ? dev + o_s : nullptr; g.out_next = hg.next_host ? dev + o_n : nullptr;
+    g.out_state = hg.state_host ? dev_s : nullptr; g.out_next = hg.next_host ? dev_n : nullptr;
     const bool scalars = g.mode == GATHER_INDICES || g.mode == GATHER_SAMPLE;
-    g.reward = scalars ? (float*)(dev + o_r) : nullptr; g.action = scalars ? dev + o_a : nullptr; g.done = scalars ? dev + o_d : nullptr;
+    g.reward = scalars ? (float*)(pin + o_r) : nullptr; g.action = scalars ? pin + o_a : nullptr; g.done = scalars ? pin + o_d : nullptr;
     rc = launch_gather(env, g, dev_layout, s); if (rc) return rc;
-    // u8 stacks go straight into page-locked caller buffers (qlc_host_alloc); pageable ones, and everything that is widened, through
-    // the page-locked staging
-    const bool direct_s = hg.state_host && !widen && is_pinned(hg.state_host), direct_n = hg.next_host && !widen && is_pinned(hg.next_host);
-    if (!env->stage_ev) CUDA_TRY(cudaEventCreateWithFlags(&env->stage_ev, cudaEventDisableTiming));
-    if (hg.state_host) CUDA_TRY(cudaMemcpyAsync(direct_s ? hg.state_host : (void*)(pin + o_s), dev + o_s, ib * n, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaEventRecord(env->stage_ev, s));
-    if (hg.next_host) CUDA_TRY(cudaMemcpyAsync(direct_n ? hg.next_host : (void*)(pin + o_n), dev + o_n, ib * n, cudaMemcpyDeviceToHost, s));
-    if (scalars || hg.idx_out_host) CUDA_TRY(cudaMemcpyAsync(pin + o_r, dev + o_r, total - o_r, cudaMemcpyDeviceToHost, s));
-    if (hg.state_host && !direct_s) {            // the state stack is widened / copied while the next stack is still in flight
-        CUDA_TRY(cudaEventSynchronize(env->stage_ev));
-        if (widen) qlc_host::widen_u8_f32(pin + o_s, (float*)hg.state_host, ib * n);
-        else memcpy(hg.state_host, pin + o_s, ib * n);
+    // The stacks cross PCIe in pieces: piece i is widened (f32 requests) or copied (pageable u8 targets) on the host while piece
+    // i+1 is still in flight. u8 stacks for page-locked caller buffers (qlc_host_alloc) are copied straight into them.
+    struct Piece { uint8_t* src; uint8_t* dst; size_t off, bytes; };
+    Piece pieces[2 * 8]; int n_pieces = 0;
+    for (int w = 0; w < 2; ++w) {
+        uint8_t* host = (uint8_t*)(w ? hg.next_host : hg.state_host);
+        if (!host) continue;
+        const size_t stack = ib * n;
+        uint8_t* devp = w ? dev_n : dev_s;
+        if (!widen && is_pinned(host)) { CUDA_TRY(cudaMemcpyAsync(host, devp, stack, cudaMemcpyDeviceToHost, s)); continue; }
+        size_t parts = stack / ((size_t)384 << 10);           // pieces of >= 384 KB: a 32-minibatch stack (882 KB) goes in two
+        parts = parts < 1 ? 1 : (parts > 8 ? 8 : parts);
+        const size_t step = ((stack / parts) + 4095) & ~(size_t)4095;
+        for (size_t off = 0; off < stack; off += step) {
+            const size_t m = stack - off < step ? stack - off : step;
+            cudaEvent_t& ev = env->piece_ev[n_pieces];
+            if (!ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            uint8_t* stage = pin + (w ? o_n : o_s) + off;
+            CUDA_TRY(cudaMemcpyAsync(stage, devp + off, m, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaEventRecord(ev, s));
+            pieces[n_pieces++] = Piece{stage, host, off, m};
+        }
+    }
+    for (int i = 0; i < n_pieces; ++i) {
+        CUDA_TRY(cudaEventSynchronize(env->piece_ev[i]));
+        const Piece& p = pieces[i];
+        if (widen) qlc_host::widen_u8_f32(p.src, (float*)p.dst + p.off, p.bytes);
+        else memcpy(p.dst + p.off, p.src, p.bytes);
     }
     CUDA_TRY(cudaStreamSynchronize(s));
-    if (hg.next_host && !direct_n) {
-        if (widen) qlc_host::widen_u8_f32(pin + o_n, (float*)hg.next_host, ib * n);
-        else memcpy(hg.next_host, pin + o_n, ib * n);
-    }
     if (hg.reward_host) memcpy(hg.reward_host, pin + o_r, (size_t)n * 4);
     if (hg.action_host) memcpy(hg.action_host, pin + o_a, n);
     if (hg.done_host) memcpy(hg.done_host, pin + o_d, n);
@@ -954,6 +1010,7 @@ int32_t qlc_stats_allreduce(qlc_env* env, void* stream) {
     }
     CUDA_TRY(cudaMemcpyAsync(c->host, result, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     c->reductions += 1;
+    c->armed = true;
     return QLC_OK;
 }
 

@@ -225,6 +225,39 @@ def test_debug_skip_variable_is_ignored_by_the_release_build(qlb, O, monkeypatch
 
 
 @pytest.mark.gpu
+def test_random_policy_drawn_inside_the_step_kernel(qlb, O):
+    """qlc_env_step_random: the uniform action stream of the pure-random phase is drawn by the step kernel; it equals the
+    oracle's synthetic stream, and so do the trajectories, for single steps and long launches."""
+    torch = pytest.importorskip("torch")
+    n, seed = 300, 8
+    env = qlb.BreakoutEnvironment(n_envs=n, seed=seed, env_id_base=1000, replay_capacity=n * 16)
+    ora = O.VecEnv(n, seed=seed, env_id_base=1000, replay_capacity=n * 16)
+    t = 0
+    for steps in (1, 1, 3, 40, 1, 64):
+        acts = torch.full((steps, n), 9, dtype=torch.uint8, device="cuda")
+        rew = torch.empty((steps, n), dtype=torch.float32, device="cuda"); done = torch.empty((steps, n), dtype=torch.uint8, device="cuda")
+        env.step_random_device(steps, acts.data_ptr(), rew.data_ptr(), done.data_ptr())
+        torch.cuda.synchronize()
+        want = O.synthetic_actions(seed, 1000, n, t, steps)
+        assert np.array_equal(acts.cpu().numpy(), want)
+        for s in range(steps):
+            r, d = ora.step(want[s])
+            assert np.array_equal(r, rew[s].cpu().numpy()) and np.array_equal(d, done[s].cpu().numpy())
+        t += steps
+    env.step_random_device(5)                              # no outputs at all
+    for s in range(5):
+        ora.step(O.synthetic_actions(seed, 1000, n, t + s, 1)[0])
+    gs, os_ = env.read_state(), ora.state()
+    for k in ("ball_cx", "ball_cy", "pad_min_x", "bricks", "score", "episode_step"):
+        assert np.array_equal(gs[k], os_[k]), k
+    rb = qlb.ReplayBuffer(env)
+    idx = np.arange(0, rb.len(), 11, dtype=np.uint32)
+    g, o = rb.get_many(idx, qlb.LAYOUT_U8_BHYX), ora.get_many(idx, "u8")
+    assert np.array_equal(g.action, o["action"]) and np.array_equal(g.state_next, o["state_next"])
+    env.close(); ora.close()
+
+
+@pytest.mark.gpu
 def test_lives(qlb):
     """lives = 1 while not finished, 0 after the miss (mechanics.rs:131-135: the first miss ends the game)."""
     n = 64
@@ -357,11 +390,11 @@ def test_unchanged_learner_loop_on_the_drop_in_types(qlb, O):
     tensorised states), same training batches bit for bit, same TD targets, same episode log, same lives."""
     D = importlib.import_module("q-learning_b200.dropin")
     seed, batch = 21, 8
-    param = dict(gamma=0.99, epsilon_max=1.0, epsilon_min=0.1, max_steps_per_episode=150, epsilon_pure_random_steps=60, epsilon_greedy_steps=300.0,
-                 history_buffer_len=256, update_after_actions=4, episode_reward_history_buffer_len=3)
+    param = dict(gamma=0.99, epsilon_max=1.0, epsilon_min=0.1, max_steps_per_episode=230, epsilon_pure_random_steps=60, epsilon_greedy_steps=300.0,
+                 history_buffer_len=256, update_after_actions=4, episode_reward_history_buffer_len=3)      # a miss takes ~200 steps: some episodes end, some are cut
     rng = np.random.default_rng(8)
-    n_episodes = 9
-    draws = [(float(rng.random()), int(rng.integers(0, 3))) for _ in range(n_episodes * 150)]
+    n_episodes = 7
+    draws = [(float(rng.random()), int(rng.integers(0, 3))) for _ in range(n_episodes * 230)]
     dirs = [float(np.float32(-0.35 + 0.2 * rng.random())) for _ in range(n_episodes)]
     ref = learn_episodes(OracleEnvironment(O, seed), D.ReplayBuffer(256, 3), OraclePixels, param, batch, draws, dirs, D)
     env = D.CudaBreakoutEnvironment(84, 84, history_buffer_len=256, seed=seed)
@@ -384,7 +417,7 @@ def test_unchanged_learner_loop_on_the_drop_in_types(qlb, O):
 @pytest.mark.gpu
 def test_state_handles_vector_env(qlb, O):
     """qlc_obs_gather(_host) for handles of many envs and times equals the oracle's observation at those times (all layouts)."""
-    n, seed, cap = 24, 12, 24 * 40
+    n, seed, cap = 24, 12, 24 * 64
     env = qlb.BreakoutEnvironment(n_envs=n, seed=seed, replay_capacity=cap, max_episode_steps=25)
     ora = O.VecEnv(n, seed=seed, max_episode_steps=25, replay_capacity=cap)
     snaps = {}
