@@ -127,16 +127,23 @@ def run_reference(args, rank, world):
     from oracle import oracle as O
     O.build()
     cores = os.cpu_count() or 1
-    sample_envs, sample_steps = args.envs, max(1, args.steps_per_launch // 8)   # bounded sample of one bench step: every env, 1/8 of its env-steps
+    # one step = one whole bench step on the CPU (every env, every env-step) whenever K of them fit in about two minutes on this
+    # box's cores; a longer run takes a bounded sample of each step: every env, fewer of its env-steps
+    sample_envs = args.envs
+    O.bench_env_steps(sample_envs, 2, SEED, cores)                              # spin the thread pool up once, outside the timed steps
+    probe = O.bench_env_steps(sample_envs, 4, SEED, cores)
+    rate = sample_envs * 4 / max(probe, 1e-9)
+    sample_steps = int(max(1, min(args.steps_per_launch, 120.0 * rate / (max(args.steps, 1) * sample_envs))))
     for _ in range(args.warmup):
-        O.bench_env_steps(sample_envs, 2, SEED, cores)
+        O.bench_env_steps(sample_envs, max(1, sample_steps // 8), SEED, cores)
     t = 0.0
     for _ in range(args.steps):
         t += O.bench_env_steps(sample_envs, sample_steps, SEED, cores)
     units = sample_envs * sample_steps * args.steps
     value = units / t
-    sample = ("each step = %d envs x %d env-steps of the same workload (1/8 of a GPU bench step: step+render+grayscale+4-frame ring+"
-              "per-step state clone, the reference's CPU path restated in C), %d OpenMP threads" % (sample_envs, sample_steps, cores))
+    sample = ("each step = %d envs x %d env-steps (%s bench step of the same workload: step+render+grayscale+4-frame ring+per-step state clone, "
+              "the reference's CPU path restated in C), %d OpenMP threads" % (sample_envs, sample_steps,
+                                                                               "ONE whole" if sample_steps == args.steps_per_launch else "%d/%d of a" % (sample_steps, args.steps_per_launch), cores))
     line = {
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
@@ -276,6 +283,8 @@ def run_b200(args, rank, local_rank, world):
     stats_every_step = None if args.no_extra else measure_stats_reduce_every_step(q, torch, dist if distributed else None, env, launch, stream, rank, world, dev, barrier, args.steps)
     replay = None if args.no_extra else measure_replay_sampling(q, torch, dist if distributed else None, rb, dev, stream, world, barrier)
     loops = {} if args.no_extra else measure_actor_loops(q, torch, dist if distributed else None, env, rb, dev, stream, world, barrier)
+    if not args.no_extra:
+        loops.update(measure_actor_loop_learner(torch, dist if distributed else None, rank, local_rank, world, dev, barrier, n_envs))
     extra = {}
     cpu_baseline = None
     if rank == 0:
@@ -439,6 +448,41 @@ def measure_actor_loops(q, torch, dist, env, rb, dev, stream, world, barrier):
                             "qnet_tflops_per_gpu": QNET_FLOP_PER_OBS * n / (res[1] * 1e-3) / 1e12,
                             "note": "closed loop on the GPU: Q-network forward (greedy action for all envs) -> 1 env-step launch -> sample+gather B=32 f32 every 4th step; no learner; " + scope},
     }
+
+
+def measure_actor_loop_learner(torch, dist, rank, local_rank, world, dev, barrier, n_envs):
+    """BASELINE configs[4] WITH a learner attached, on every rank: the vectorised DQN loop of examples/dqn_breakout_torch.py — env
+    shard + replay shard on the GPU (this repo), zero-copy one-launch sample+gather into the tensors of a device-resident torch
+    Q-network of the reference architecture (library code, the stand-in for the reference's TensorFlow model: forward for the
+    greedy actions and the TD target, forward + backward + Adam for every minibatch), one minibatch of 32 per 4 env-steps like
+    the reference (self_driving_tf_q_learner.rs:181). Run twice: with the model, and with the model calls skipped (the data path
+    alone), which attributes the iteration time. No collective on the path (each rank trains its own replica here; a real
+    multi-GPU learner would all-reduce gradients - the learner is outside this repo's scope)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("dqn_breakout_torch", os.path.join(ROOT, "examples", "dqn_breakout_torch.py"))
+    ex = importlib.util.module_from_spec(spec); spec.loader.exec_module(ex)
+    iters = 12
+    res = []
+    for skip in (False, True):
+        ex.run(n_envs, 2, quiet=True, device=local_rank, env_id_base=rank * n_envs, seed=SEED, skip_model=skip, random_phase_steps=0)   # warm-up (cudnn autotune, allocator)
+        barrier()
+        t0 = time.perf_counter()
+        out = ex.run(n_envs, iters, quiet=True, device=local_rank, env_id_base=rank * n_envs, seed=SEED, skip_model=skip, random_phase_steps=0)
+        torch.cuda.synchronize()
+        res.append(out["seconds"])
+    secs_full, secs_data = res
+    if dist is not None:
+        t = torch.tensor([secs_full, secs_data], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs_full, secs_data = float(t[0].item()), float(t[1].item())
+    steps = n_envs * iters
+    return {"actor_loop_learner": {
+        "env_steps_per_sec": world * steps / secs_full, "minibatches_per_sec": world * (steps // 4) / secs_full, "ms_per_iteration": 1e3 * secs_full / iters,
+        "data_path_only_ms_per_iteration": 1e3 * secs_data / iters, "learner_share_of_iteration": 1.0 - secs_data / secs_full, "n_gpus": world,
+        "bound_by": "the torch model (forward + backward + Adam on %d samples and two forwards per iteration); the env step, replay insert and the one-launch "
+                    "sample+gather of an iteration are the data_path_only time" % (n_envs // 4 * 32),
+        "note": "%d envs per GPU, %d iterations, greedy actions from the model on every iteration (no pure-random phase), wall clock incl. env creation "
+                "excluded; slowest rank; compare actor_loop_cpu_baseline (the restated reference data path, 1 env, 1 thread, no model)" % (n_envs, iters)}}
 
 
 def measure_replay_sampling(q, torch, dist, rb, dev, stream, world, barrier):

@@ -69,13 +69,17 @@ class TorchDQNModel:
         self.net.load_state_dict(other.net.state_dict())
 
 
-def run(n_envs=1024, iterations=200, batch=32, minibatches_per_call=None, seed=0, device=0, quiet=False, tensor_core_actor=False, actor_sync_every=10):
-    """Device-resident variant of learner.SelfDrivingQLearner.learn_iteration: same rules, tensors never leave the GPU."""
+def run(n_envs=1024, iterations=200, batch=32, minibatches_per_call=None, seed=0, device=0, quiet=False, tensor_core_actor=False, actor_sync_every=10,
+        env_id_base=0, skip_model=False, random_phase_steps=None):
+    """Device-resident variant of learner.SelfDrivingQLearner.learn_iteration: same rules, tensors never leave the GPU.
+    skip_model: run the data path only (step, replay insert, sample + gather, TD-target inputs) without the network calls —
+    what is left of an iteration when the learner costs nothing (bench.py uses it to attribute the iteration time)."""
     dev = torch.device("cuda", device)
     torch.cuda.set_device(dev)
-    p = L.Parameter(history_buffer_len=n_envs * 128, epsilon_pure_random_steps=n_envs * 20, epsilon_greedy_steps=float(n_envs * 400),
-                    max_steps_per_episode=10_000)
-    env = q.BreakoutEnvironment(n_envs=n_envs, seed=seed, replay_capacity=p.history_buffer_len, max_episode_steps=p.max_steps_per_episode, device=device)
+    p = L.Parameter(history_buffer_len=n_envs * 128, epsilon_pure_random_steps=n_envs * 20 if random_phase_steps is None else random_phase_steps,
+                    epsilon_greedy_steps=float(n_envs * 400), max_steps_per_episode=10_000)
+    env = q.BreakoutEnvironment(n_envs=n_envs, seed=seed, env_id_base=env_id_base, replay_capacity=p.history_buffer_len,
+                                max_episode_steps=p.max_steps_per_episode, device=device)
     rb = q.ReplayBuffer(env)
     model, target = TorchDQNModel(dev), TorchDQNModel(dev)
     target.load_from(model)
@@ -97,7 +101,7 @@ def run(n_envs=1024, iterations=200, batch=32, minibatches_per_call=None, seed=0
         eps = torch.clamp(epsilon - torch.arange(n_envs, device=dev) * delta, min=p.epsilon_min)
         random_mask = (eps > u) | (step_count + 1 + torch.arange(n_envs, device=dev) < p.epsilon_pure_random_steps)
         actions = a_rand
-        if not bool(random_mask.all()):
+        if not skip_model and not bool(random_mask.all()):
             if actor is not None:
                 if it % actor_sync_every == 0:
                     actor.sync(model.net)
@@ -114,6 +118,8 @@ def run(n_envs=1024, iterations=200, batch=32, minibatches_per_call=None, seed=0
             for _ in range(max(1, due_per_iter // nb)):
                 s = sampler.sample(calls); calls += nb
                 st, nx = s.state.view(nb * batch, 84, 84, 4), s.state_next.view(nb * batch, 84, 84, 4)
+                if skip_model:
+                    continue
                 max_future = target.batch_predict_max_future_reward(nx)
                 rwd, dn = s.reward.view(-1), s.done.view(-1)
                 updated_q = torch.where(dn != 0, rwd, rwd + p.gamma.item() * max_future)      # TD target (:192-199)
@@ -128,7 +134,7 @@ def run(n_envs=1024, iterations=200, batch=32, minibatches_per_call=None, seed=0
                 len(finished_returns), float(np.mean(finished_returns[-500:])) if finished_returns else float("nan"), step_count / (time.time() - t0)), flush=True)
     torch.cuda.synchronize()
     stats = env.stats()
-    out = {"env_steps": step_count, "seconds": time.time() - t0, "episodes": int(stats["episodes"]), "train_calls": len(model.losses),
+    out = {"env_steps": step_count, "seconds": time.time() - t0, "episodes": int(stats["episodes"]), "train_calls": len(model.losses), "minibatches": calls,
            "last_loss": float(model.losses[-1]) if model.losses else None, "epsilon": epsilon, "error_flags": env.error_flags()}
     if actor is not None:
         actor.close()

@@ -56,8 +56,14 @@ class SelfDrivingQLearner:
         self.batch_size = batch_size
         self.checkpoint_file = checkpoint_file
         self.replay_buffer = ReplayBuffer(environment)
-        if self.replay_buffer.capacity() < min(param.history_buffer_len, 1):
-            raise QlError("the environment has no replay ring")
+        # Parameter::history_buffer_len is the FIFO length the learner trains from (:32-34,:100); the ring holds whole time steps
+        # of all envs, so the effective length is history_buffer_len rounded down to a multiple of n_envs (at least one step)
+        want = max(param.history_buffer_len // environment.n_envs, 1) * environment.n_envs
+        if self.replay_buffer.capacity() != want:
+            raise QlError("the environment's replay ring holds %d transitions but Parameter.history_buffer_len asks for %d (%d rounded down to whole "
+                          "time steps of %d envs): create the BreakoutEnvironment with replay_capacity=param.history_buffer_len"
+                          % (self.replay_buffer.capacity(), want, param.history_buffer_len, environment.n_envs))
+        self.effective_history_buffer_len = want
         self.rng = np.random.default_rng(seed)
         self.step_count = 0
         self.episode_count = 0

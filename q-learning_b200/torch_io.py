@@ -11,8 +11,9 @@ def _stream():
 
 
 class DeviceSampler:
-    """Reusable device buffers for `n_batches` minibatches of `batch` transitions; `sample()` = one
-    `qlc_replay_sample` + one `qlc_replay_gather` on torch's current stream, returns views on the buffers."""
+    """Reusable device buffers for `n_batches` minibatches of `batch` transitions; `sample()` = ONE kernel launch
+    (`qlc_replay_sample_gather`: the gather kernel draws the distinct indices itself) on torch's current stream, returns views
+    on the buffers."""
 
     def __init__(self, replay, batch, n_batches=1, layout=LAYOUT_F32_BXYH, device=None):
         self.replay, self.batch, self.n_batches, self.layout = replay, batch, n_batches, layout
@@ -32,10 +33,8 @@ class DeviceSampler:
         self.done = torch.empty((n_batches, batch), dtype=torch.uint8, device=dev)
 
     def sample(self, call_index):
-        s = _stream()
-        self.replay.sample_device(self.batch, self.n_batches, call_index, self.indices.data_ptr(), s)
-        self.replay.gather_device(self.indices.data_ptr(), self.batch * self.n_batches, self.layout, self.state.data_ptr(),
-                                  self.state_next.data_ptr(), self.reward.data_ptr(), self.action.data_ptr(), self.done.data_ptr(), s)
+        self.replay.sample_gather_device(self.batch, self.n_batches, call_index, self.layout, self.indices.data_ptr(), self.state.data_ptr(),
+                                         self.state_next.data_ptr(), self.reward.data_ptr(), self.action.data_ptr(), self.done.data_ptr(), _stream())
         return self
 
 

@@ -1,7 +1,10 @@
 """Compares a trace printed by bindings/rust/trace-dumper (the REAL reference mechanics, run wherever cargo exists) with
 the CPU oracle on the same explicit inputs. Reports the first differing step, or that the oracle is pinned on this trace.
-Usage: python tools/compare_rust_trace.py rust_trace.txt <dir_x> actions.txt
-Also: python tools/compare_rust_trace.py --emit <dir_x> actions.txt   prints the oracle's trace in the same format."""
+Usage: python tests/compare_rust_trace.py rust_trace.txt <dir_x> actions.txt
+Also: python tests/compare_rust_trace.py --emit <dir_x> actions.txt   prints the oracle's trace in the same format.
+      python tests/compare_rust_trace.py --contacts rust_contacts.txt tests/golden/contact_inputs_v1.txt
+          compares parry2d's ball / cuboid contact query (trace-dumper --contacts) with the oracle's restatement, bit for bit
+      python tests/compare_rust_trace.py --emit-contacts tests/golden/contact_inputs_v1.txt   prints the oracle's answers."""
 import os
 import sys
 
@@ -28,7 +31,29 @@ def oracle_trace(dir_x, actions):
     return lines
 
 
+def contact_lines(inputs_path):
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_contact_inputs as M
+    return M.oracle_lines(M.read_inputs(inputs_path))
+
+
 def main():
+    if sys.argv[1] == "--emit-contacts":
+        print("\n".join(contact_lines(sys.argv[2])))
+        return
+    if sys.argv[1] == "--contacts":
+        rust = [l.strip() for l in open(sys.argv[2]) if l.strip()]
+        mine = contact_lines(sys.argv[3])
+        bad = [i for i, (r, m) in enumerate(zip(rust, mine)) if r != m]
+        if len(rust) != len(mine):
+            print("line counts differ: reference %d, oracle %d" % (len(rust), len(mine)))
+            sys.exit(1)
+        if bad:
+            i = bad[0]
+            print("%d of %d contact queries differ; first at input line %d:\n  reference: %s\n  oracle:    %s" % (len(bad), len(mine), i + 1, rust[i], mine[i]))
+            sys.exit(1)
+        print("oracle == parry2d on all %d contact queries (bit for bit)" % len(mine))
+        return
     if sys.argv[1] == "--emit":
         acts = [int(t) for t in open(sys.argv[3]).read().split()]
         print("\n".join(oracle_trace(float(sys.argv[2]), acts)))

@@ -196,3 +196,34 @@ def test_sharded_vec_env_equals_one_vec_env(O):
         assert np.array_equal(a[k], b[k]), k
     assert np.array_equal(one.obs_u8(), many.obs_u8()) and d2.sum() > 0
     one.close(); many.close()
+
+
+def test_contact_query_golden(O):
+    """The restated parry2d contact query answers the committed input list (tests/golden/contact_inputs_v1.txt, the list a
+    `cargo run -p trace-dumper -- --contacts` run of the real reference is compared against) exactly as recorded, and the
+    answers make geometric sense: dist = distance(ball centre, box) - radius within float tolerance when the centre is outside,
+    normals are opposite unit vectors."""
+    import os
+    import sys
+    import numpy as np
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import make_contact_inputs as M
+    cs = M.read_inputs(os.path.join(here, "contact_inputs_v1.txt"))
+    lines = M.oracle_lines(cs)
+    want = [l.strip() for l in open(os.path.join(here, "contact_oracle_v1.txt")) if l.strip()]
+    assert len(cs) == len(want) > 1000 and lines == want
+    n_some = 0
+    for (cx, cy, r, x0, y0, x1, y1), line in zip(cs, lines):
+        dx = max(x0 - cx, 0.0, cx - x1); dy = max(y0 - cy, 0.0, cy - y1)
+        gap = float(np.hypot(np.float64(dx), np.float64(dy))) - float(r)
+        t = line.split()
+        if t[0] == "0":
+            assert gap > 0.8 - 1e-4
+            continue
+        n_some += 1
+        dist, n1x, n1y, n2x, n2y = [float(np.uint32(int(v, 16)).view(np.float32)) for v in t[1:]]
+        assert dist <= 0.8 and abs(np.hypot(n1x, n1y) - 1.0) < 1e-5 and n1x == -n2x and n1y == -n2y
+        if dx > 1e-3 or dy > 1e-3:                       # centre outside the box: the plain closest-point distance
+            assert abs(dist - gap) < 1e-4
+    assert n_some > 800

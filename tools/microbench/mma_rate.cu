@@ -7,7 +7,7 @@
 using namespace qlc;
 using namespace qlc::qnet;
 
-template <int N, int STYLE>
+template <int N, int STYLE, int M = 128>
 __global__ void __launch_bounds__(128, 1) rate_kernel(uint32_t lbo_a, uint32_t shift_rows, int iters, long long* out) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(uint32_t lbo_a, uint32_t s
     const uint32_t tmem_base = tmem_slot;
     if (warp == 0) {
         const uint32_t tmem_u = __reduce_max_sync(0xFFFFFFFFu, tmem_base);
-        constexpr uint32_t IDESC = instr_desc_bf16(128, N);
+        constexpr uint32_t IDESC = instr_desc_bf16(M, N);
         const uint32_t a_lo0 = (smem_u32(smem) >> 4) | ((lbo_a >> 4) << 16);
         const uint32_t b_lo0 = ((smem_u32(smem) + 96 * 1024) >> 4) | ((uint32_t)(N * 16 >> 4) << 16);
         const long long t0 = clock64();
@@ -51,16 +51,16 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(uint32_t lbo_a, uint32_t s
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
-template <int N, int STYLE>
+template <int N, int STYLE, int M = 128>
 static void run(uint32_t lbo, uint32_t shift, const char* what) {
     long long* d; cudaMalloc(&d, 16);
-    auto k = rate_kernel<N, STYLE>;
+    auto k = rate_kernel<N, STYLE, M>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     const int iters = 200;
     for (int rep = 0; rep < 2; ++rep) k<<<148, 128, 160 * 1024>>>(lbo, shift, iters, d);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[2] = {0, 0}; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-    printf("N=%3d style=%d lbo=%5u shift=%2u : issue %6.1f cyc/MMA, complete %6.1f cyc/MMA  %s %s\n", N, STYLE, lbo, shift, (double)h[0] / (iters * 16), (double)h[1] / (iters * 16), what,
+    printf("M=%3d N=%3d style=%d lbo=%5u shift=%2u : issue %6.1f cyc/MMA, complete %6.1f cyc/MMA  %s %s\n", M, N, STYLE, lbo, shift, (double)h[0] / (iters * 16), (double)h[1] / (iters * 16), what,
            e == cudaSuccess ? "" : cudaGetErrorString(e));
     cudaFree(d);
 }
@@ -109,5 +109,7 @@ int main() {
     run<64, 0>(3200, 1, "conv2-like"); run<64, 0>(3200, 0, "aligned"); run<64, 0>(3888, 1, "conv3-like"); run<64, 1>(3200, 1, "single thread");
     run<128, 0>(3200, 1, ""); run<128, 0>(3200, 0, "aligned"); run<256, 0>(3200, 1, ""); run<256, 0>(3200, 0, "aligned");
     run<16, 0>(3200, 1, ""); run<8, 0>(3200, 0, "aligned");
+    // role swap (weights as A with M = cout = 64, pixels as B with N = 256 / 128): does an M = 64 MMA cost half an M = 128 one?
+    run<256, 0, 64>(1024, 0, "M=64: weights as A, 256 pixels as B"); run<128, 0, 64>(1024, 0, "M=64, N=128"); run<64, 0, 64>(1024, 0, "M=64, N=64");
     return 0;
 }
