@@ -283,7 +283,7 @@ def run_b200(args, rank, local_rank, world):
     stats_every_step = None if args.no_extra else measure_stats_reduce_every_step(q, torch, dist if distributed else None, env, launch, stream, rank, world, dev, barrier, args.steps)
     replay = None if args.no_extra else measure_replay_sampling(q, torch, dist if distributed else None, rb, dev, stream, world, barrier)
     loops = {} if args.no_extra else measure_actor_loops(q, torch, dist if distributed else None, env, rb, dev, stream, world, barrier)
-    if not args.no_extra:
+    if not args.no_extra and not args.no_learner:
         loops.update(measure_actor_loop_learner(torch, dist if distributed else None, rank, local_rank, world, dev, barrier, n_envs))
     extra = {}
     cpu_baseline = None
@@ -413,7 +413,11 @@ def measure_actor_loops(q, torch, dist, env, rb, dev, stream, world, barrier):
         if rb.should_sample(i, rb.len(), 32):              # ONE launch: the gather kernel draws the distinct indices itself
             rb.sample_gather_device(32, 1, i, q.LAYOUT_F32_BXYH, idx.data_ptr(), st.data_ptr(), nx.data_ptr(), r.data_ptr(), a.data_ptr(), d.data_ptr(), stream)
 
-    def iter_random(i):
+    def iter_random(i):                       # the learner's pure-random phase: the step kernel draws the actions itself (qlc_env_step_random)
+        env.step_random_device(1, acts.data_ptr(), rew1.data_ptr(), done1.data_ptr(), stream)
+        sample_every_4th(i)
+
+    def iter_torch_policy(i):                 # a policy stand-in outside the library: one more kernel (and its host dispatch) per iteration
         ra = torch.randint(0, 3, (1, n), dtype=torch.uint8, device=dev)
         env.step_device(ra.data_ptr(), 1, rew1.data_ptr(), done1.data_ptr(), stream)
         sample_every_4th(i)
@@ -424,7 +428,7 @@ def measure_actor_loops(q, torch, dist, env, rb, dev, stream, world, barrier):
         sample_every_4th(i)
 
     res = []
-    for fn, iters in ((iter_random, 400), (iter_qnet, 200)):
+    for fn, iters in ((iter_random, 400), (iter_qnet, 200), (iter_torch_policy, 400)):
         for i in range(8):
             fn(i)
         barrier()
@@ -443,7 +447,11 @@ def measure_actor_loops(q, torch, dist, env, rb, dev, stream, world, barrier):
     scope = "%d GPU(s), %d envs each, slowest rank" % (world, n)
     return {
         "actor_loop": {"env_steps_per_sec": world * n / (res[0] * 1e-3), "minibatches_per_sec": world * 0.25 / (res[0] * 1e-3), "us_per_iteration": res[0] * 1e3, "n_gpus": world,
-                       "note": "1 step launch per iteration (actions from a device-side random policy), one-launch sample+gather B=32 f32 every 4th step; no learner; " + scope},
+                       "kernels_per_iteration": 1.25,
+                       "note": "1 step launch per iteration with the uniform random policy of the learner's pure-random phase drawn inside the step kernel "
+                               "(qlc_env_step_random; actions, reward, done written out), one-launch sample+gather B=32 f32 every 4th step; no learner; " + scope},
+        "actor_loop_torch_policy": {"env_steps_per_sec": world * n / (res[2] * 1e-3), "us_per_iteration": res[2] * 1e3, "kernels_per_iteration": 2.25,
+                                    "note": "same with the actions from torch.randint (r01's actor_loop): the extra kernel's host dispatch (~7 us) bounds the iteration"},
         "actor_loop_qnet": {"env_steps_per_sec": world * n / (res[1] * 1e-3), "minibatches_per_sec": world * 0.25 / (res[1] * 1e-3), "us_per_iteration": res[1] * 1e3, "n_gpus": world,
                             "qnet_tflops_per_gpu": QNET_FLOP_PER_OBS * n / (res[1] * 1e-3) / 1e12,
                             "note": "closed loop on the GPU: Q-network forward (greedy action for all envs) -> 1 env-step launch -> sample+gather B=32 f32 every 4th step; no learner; " + scope},
@@ -726,6 +734,7 @@ def main():
     ap.add_argument("--replay-capacity", type=int, default=REPLAY_CAPACITY)
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-learner", action="store_true", help="skip the learner-in-the-loop section (profiling runs: it is thousands of library kernels)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -500,24 +500,24 @@ __global__ void env_reset_kernel(EnvArrays st, uint32_t n_envs, uint32_t env_id_
 // The reference's sequential rejection loop keeps the FIRST OCCURRENCES of the accepted draws, in stream order. Draw p of
 // minibatch `call` is word p & 3 of philox({p >> 2, call_lo, call_hi, 'SAMP'}), mapped to [0, len) by Lemire's multiply-shift
 // with rejection. The warp walks the stream 128 positions per round — lane L owns positions 4L..4L+3 of the round, the four
-// words of ONE Philox block — and keeps the values seen so far in a shared-memory hash table (value, stream position), open
-// addressing. Inserts use NO atomics (shared-memory atomics turned out to be the bottleneck once several sampler warps share
-// an SM): every draw looks at its slot, the ones that found it empty store their value, a __syncwarp later whoever reads its
-// own value back owns the slot, the others probe on. Draws with equal values walk the same probe sequence in lockstep and
-// therefore always meet in the same slot in the same pass — they notice it because only one of their stream positions
-// survives in the position word; that (rare: two equal values among 128 draws) case is settled with atomicMin on the
-// positions. A draw is a first occurrence iff no earlier round holds its value and it has the smallest position of its round.
-// Ranks come from a warp prefix sum of the per-lane counts. Because the routine is cheap it runs INSIDE the gather kernels —
-// every CTA derives the index of its own item and stops as soon as it has it — so that a sampled minibatch is ONE kernel
-// launch; the index-only entry point (qlc_replay_sample) runs the same routine, one warp per minibatch, storing all of them.
+// words of ONE Philox block — and finds first occurrences with a shared-memory hash table (value, stream position): every
+// accepted draw claims the slot of its value with ONE atomicCAS (the four claims of a lane are issued back to back); the claim
+// that creates the entry is a first occurrence and records its position with a plain store, a claim that finds the value
+// there is a duplicate — of an earlier round (dropped) or, rarely, of a draw of the same round, in which case the two settle
+// by atomicMin on the position which of them comes first in the stream. Ranks come from a warp prefix sum of the per-lane
+// counts. The routine runs INSIDE the gather kernels, so that a sampled minibatch is ONE kernel launch: every CTA derives the
+// index of its own item and stops as soon as it has it. (Tried and dropped, profiles/r02_notes.md: one sampler per
+// thread-block cluster of 8 handing indices out through distributed shared memory, a producer CTA publishing through global
+// memory, an atomic-free insert - all slower than every CTA drawing for itself.) The index-only entry point
+// (qlc_replay_sample) runs the same routine, one warp per minibatch, storing all of them.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SAMPLE_MAX_BATCH = 1024;
 constexpr uint32_t SAMPLE_EMPTY = 0xFFFFFFFFu;           // never a value: len < 2^32 - 1 is checked by the host
 constexpr uint32_t SAMPLE_MAX_ROUNDS = 1u << 19;         // x 128 stream positions: the bound of the "loop" in the reference
 
-__host__ __device__ __forceinline__ uint32_t sample_table_size(uint32_t batch) {   // slots: power of two >= 2 * (batch + 128)
-    uint32_t n = 512;
-    while (n < 2u * (batch + 128u)) n <<= 1;
+__host__ __device__ __forceinline__ uint32_t sample_table_size(uint32_t batch) {   // slots: power of two >= 4 * (batch + 128)
+    uint32_t n = 1024;
+    while (n < 4u * (batch + 128u) && n < 4096u) n <<= 1;
     return n;                                                                       // <= 4096 slots x (value, position) = 32 KB
 }
 
@@ -525,101 +525,91 @@ __device__ __forceinline__ void sample_table_clear(uint32_t* table, uint32_t tsi
     for (uint32_t i = tid; i < 2u * tsize / 4u; i += nthreads) reinterpret_cast<uint4*>(table)[i] = make_uint4(SAMPLE_EMPTY, SAMPLE_EMPTY, SAMPLE_EMPTY, SAMPLE_EMPTY);
 }
 
-// ALL = false: returns the index of item j of the minibatch (every lane gets it).  ALL = true: stores the first `batch`
-// indices to out[0..batch) and returns 0.  `table` = 2 * sample_table_size(batch) words of shared memory, all SAMPLE_EMPTY
-// (values in the first half, stream positions in the second).
-template <bool ALL>
-__device__ __forceinline__ uint32_t sample_distinct_warp(uint32_t* table, uint32_t tsize, uint32_t len, uint64_t seed, uint64_t call,
-                                                         uint32_t j, uint32_t batch, uint32_t* out, int lane) {
+// Walks the stream of minibatch `call` and hands every first occurrence of rank in [j_lo, j_hi] to deliver(rank, value) (called
+// by the lane that owns the draw); returns once rank j_hi has been delivered. `table` = 2 * tsize words of shared memory, all
+// SAMPLE_EMPTY (values in the first half, stream positions in the second).
+template <class Deliver>
+__device__ __forceinline__ void sample_distinct_warp(uint32_t* table, uint32_t tsize, uint32_t len, uint64_t seed, uint64_t call,
+                                                     uint32_t j_lo, uint32_t j_hi, int lane, Deliver deliver) {
     const uint32_t thresh = (uint32_t)((0x100000000ull - (uint64_t)len) % (uint64_t)len);   // Lemire rejection zone
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const uint32_t tmask = tsize - 1u;
-    volatile uint32_t* tval = table; volatile uint32_t* tpos = table + tsize;
+    uint32_t* tval = table; uint32_t* tpos = table + tsize;
     uint32_t kept = 0;
     for (uint32_t round = 0; round < SAMPLE_MAX_ROUNDS; ++round) {
         const uint32_t ctr = round * 32u + (uint32_t)lane;
-        const uint32_t round_base = round * 128u;
         const uint4 r = philox4x32_10(make_uint4(ctr, (uint32_t)call, (uint32_t)(call >> 32), STREAM_SAMPLE), key);
         const uint32_t raw[4] = {r.x, r.y, r.z, r.w};
-        uint32_t val[4], slot[4];
-        bool pending[4], cand[4];                        // cand: accepted draw whose value no earlier round holds
+        uint32_t val[4], slot[4], old[4]; bool valid[4];
         #pragma unroll
         for (int w = 0; w < 4; ++w) {
             const uint64_t m = (uint64_t)raw[w] * (uint64_t)len;
-            pending[w] = !((uint32_t)m < thresh);
+            valid[w] = !((uint32_t)m < thresh);
             val[w] = (uint32_t)(m >> 32);
             slot[w] = ((val[w] * 0x9E3779B1u) >> 12) & tmask;
-            cand[w] = false;
         }
-        bool conflict = false;                           // two draws of THIS round share a value
-        while (__any_sync(0xFFFFFFFFu, pending[0] || pending[1] || pending[2] || pending[3])) {
-            bool attempt[4];
-            #pragma unroll
-            for (int w = 0; w < 4; ++w) {                // look
-                attempt[w] = false;
-                if (pending[w]) {
-                    const uint32_t cur = tval[slot[w]];
-                    if (cur == SAMPLE_EMPTY) attempt[w] = true;
-                    else if (cur == val[w]) { pending[w] = false; if (tpos[slot[w]] >= round_base) { cand[w] = true; conflict = true; } }   // same value: earlier round = duplicate
-                    else slot[w] = (slot[w] + 1u) & tmask;
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) old[w] = valid[w] ? atomicCAS(&tval[slot[w]], SAMPLE_EMPTY, val[w]) : SAMPLE_EMPTY;   // four claims in flight
+        bool first[4], again[4];                          // first: my claim created the entry; again: the value was there already
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            first[w] = false; again[w] = false;
+            if (valid[w]) {
+                while (old[w] != SAMPLE_EMPTY && old[w] != val[w]) {       // the slot belongs to another value: probe on
+                    slot[w] = (slot[w] + 1u) & tmask;
+                    old[w] = atomicCAS(&tval[slot[w]], SAMPLE_EMPTY, val[w]);
                 }
+                if (old[w] == SAMPLE_EMPTY) { first[w] = true; tpos[slot[w]] = ctr * 4u + (uint32_t)w; }   // only the creator writes the position
+                else again[w] = true;
             }
-            __syncwarp();
-            #pragma unroll
-            for (int w = 0; w < 4; ++w) if (attempt[w]) tval[slot[w]] = val[w];     // claim: one of the writers survives
-            __syncwarp();
-            #pragma unroll
-            for (int w = 0; w < 4; ++w)
-                if (attempt[w]) {
-                    if (tval[slot[w]] == val[w]) { pending[w] = false; cand[w] = true; tpos[slot[w]] = ctr * 4u + (uint32_t)w; }   // mine, or an equal value's
-                    else slot[w] = (slot[w] + 1u) & tmask;
-                }
-            __syncwarp();
-            #pragma unroll
-            for (int w = 0; w < 4; ++w) if (attempt[w] && cand[w] && tpos[slot[w]] != ctr * 4u + (uint32_t)w) conflict = true;   // an equal value claimed with me
-            __syncwarp();
         }
-        if (__any_sync(0xFFFFFFFFu, conflict)) {         // rare: settle equal values of this round by their stream positions
+        __syncwarp();
+        // a value that was there already is a duplicate of an earlier ROUND (the usual case: drop it) or of a draw of THIS round,
+        // whose creator is whichever claim won the race, not necessarily the earlier stream position: settle those (rare: two
+        // equal values among 128 draws) by atomicMin on the position
+        bool clash = false;
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) if (again[w] && tpos[slot[w]] >= round * 128u) clash = true;
+        if (__any_sync(0xFFFFFFFFu, clash)) {
             #pragma unroll
-            for (int w = 0; w < 4; ++w) if (cand[w]) atomicMin(table + tsize + slot[w], ctr * 4u + (uint32_t)w);
+            for (int w = 0; w < 4; ++w) if ((first[w] || again[w]) && tpos[slot[w]] >= round * 128u) atomicMin(&tpos[slot[w]], ctr * 4u + (uint32_t)w);
             __syncwarp();
             #pragma unroll
-            for (int w = 0; w < 4; ++w) cand[w] = cand[w] && tpos[slot[w]] == ctr * 4u + (uint32_t)w;
+            for (int w = 0; w < 4; ++w) first[w] = (first[w] || again[w]) && tpos[slot[w]] == ctr * 4u + (uint32_t)w;
         }
         uint32_t cnt = 0;
         #pragma unroll
-        for (int w = 0; w < 4; ++w) cnt += cand[w] ? 1u : 0u;
+        for (int w = 0; w < 4; ++w) cnt += first[w] ? 1u : 0u;
         uint32_t incl = cnt;                              // ordered prefix sum over the lanes (= over the stream positions)
         #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         uint32_t rank = kept + incl - cnt;
-        if (ALL) {
-            #pragma unroll
-            for (int w = 0; w < 4; ++w) if (cand[w]) { if (rank < batch) out[rank] = val[w]; ++rank; }
-            kept += total;
-            if (kept >= batch) return 0u;
-        } else {
-            uint32_t mine = SAMPLE_EMPTY;
-            #pragma unroll
-            for (int w = 0; w < 4; ++w) if (cand[w]) { if (rank == j) mine = val[w]; ++rank; }
-            const uint32_t hit = __ballot_sync(0xFFFFFFFFu, mine != SAMPLE_EMPTY);
-            if (hit) return __shfl_sync(0xFFFFFFFFu, mine, __ffs(hit) - 1);
-            kept += total;
-        }
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) if (first[w]) { if (rank >= j_lo && rank <= j_hi) deliver(rank, val[w]); ++rank; }
+        kept += total;
+        if (kept > j_hi) return;
         __syncwarp();
     }
-    return 0u;   // unreachable for len >= batch (the reference would loop forever here)
+}
+
+// the index of item j of the minibatch (every lane gets it)
+__device__ __forceinline__ uint32_t sample_one(uint32_t* table, uint32_t tsize, uint32_t len, uint64_t seed, uint64_t call, uint32_t j, int lane) {
+    uint32_t mine = SAMPLE_EMPTY;
+    sample_distinct_warp(table, tsize, len, seed, call, j, j, lane, [&](uint32_t, uint32_t v) { mine = v; });
+    const uint32_t hit = __ballot_sync(0xFFFFFFFFu, mine != SAMPLE_EMPTY);
+    return hit ? __shfl_sync(0xFFFFFFFFu, mine, __ffs(hit) - 1) : 0u;      // no hit: unreachable for len >= batch (the reference would loop forever)
 }
 
 // index-only form: one warp per minibatch
 __global__ void __launch_bounds__(32) replay_sample_kernel(uint32_t* out, uint32_t batch, uint32_t len, uint64_t seed, uint64_t call0) {
-    __shared__ uint32_t table[2 * 4096];
+    __shared__ __align__(16) uint32_t table[2 * 4096];
     const int lane = threadIdx.x;
     const uint32_t tsize = sample_table_size(batch);
-    for (uint32_t i = lane; i < 2u * tsize; i += 32) table[i] = SAMPLE_EMPTY;
+    sample_table_clear(table, tsize, lane, 32);
     __syncwarp();
-    sample_distinct_warp<true>(table, tsize, len, seed, call0 + blockIdx.x, 0u, batch, out + (size_t)blockIdx.x * batch, lane);
+    uint32_t* dst = out + (size_t)blockIdx.x * batch;
+    sample_distinct_warp(table, tsize, len, seed, call0 + blockIdx.x, 0u, batch - 1u, lane, [&](uint32_t rank, uint32_t v) { dst[rank] = v; });
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -706,7 +696,7 @@ __global__ void __launch_bounds__(32) gather_u8_kernel(GatherParams g) {
         sample_table_clear(table, sample_table_size(g.sample_batch), lane, 32);
         __syncwarp();
         const uint32_t mb = b / g.sample_batch, j = b - mb * g.sample_batch;
-        idx = sample_distinct_warp<false>(table, sample_table_size(g.sample_batch), g.sample_len, g.seed, g.call0 + mb, j, g.sample_batch, nullptr, lane);
+        idx = sample_one(table, sample_table_size(g.sample_batch), g.sample_len, g.seed, g.call0 + mb, j, lane);
     }
     // launched with programmatic stream serialization: everything above neither reads nor writes anything an earlier kernel touches
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -773,16 +763,14 @@ __global__ void __launch_bounds__(GATHER_XYH_THREADS) gather_xyh_kernel(GatherPa
         __syncthreads();
         if (tid < 32) {
             const uint32_t mb = b / g.sample_batch, j = b - mb * g.sample_batch;
-            const uint32_t v = sample_distinct_warp<false>(table, sample_table_size(g.sample_batch), g.sample_len, g.seed, g.call0 + mb, j, g.sample_batch, nullptr, tid);
+            const uint32_t v = sample_one(table, sample_table_size(g.sample_batch), g.sample_len, g.seed, g.call0 + mb, j, tid);
             if (tid == 0) s_idx = v;
         }
-    }
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic stream serialization: nothing above touches an earlier kernel's data
-    if (g.mode == GATHER_SAMPLE) {
         __syncthreads();
         idx = s_idx;
-        if (tid == 0 && slice == 0 && g.idx_out && (which == 0 || !g.out_state)) g.idx_out[b] = idx;
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic stream serialization: nothing above touches an earlier kernel's data
+    if (g.mode == GATHER_SAMPLE && tid == 0 && slice == 0 && g.idx_out && (which == 0 || !g.out_state)) g.idx_out[b] = idx;
     if (g.mode == GATHER_INDICES) idx = g.indices[b];
     uint64_t T; uint32_t e, k, rec;
     const bool exists = locate(g, b, idx, T, e, k, rec);

@@ -528,7 +528,7 @@ static bool known_layout(int32_t layout) { return layout == QLC_LAYOUT_U8_BHYX |
 static size_t smem_for_cap(size_t needed, uint32_t cap) {
     if (cap == 0 || cap >= 8) return needed;
     const size_t want = (size_t)228 * 1024 / (cap + 1) + 16;     // cap + 1 CTAs of this size do not fit
-    const size_t most = (size_t)227 * 1024;
+    const size_t most = (size_t)226 * 1024;            // the opt-in limit set below (227 KB minus the kernels' static shared memory)
     return needed > want ? needed : (want > most ? most : want);
 }
 
@@ -537,9 +537,9 @@ static int32_t launch_gather(qlc_env* env, const GatherParams& g_in, int32_t lay
     GatherParams g = g_in;
     static bool configured[64] = {};
     if (!configured[env->cfg.device & 63]) {     // opt in to large dynamic shared memory (6 frames; occupancy caps)
-        CUDA_TRY(cudaFuncSetAttribute(gather_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(gather_xyh_kernel<float4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(gather_xyh_kernel<uchar4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(gather_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(gather_xyh_kernel<float4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(gather_xyh_kernel<uchar4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         configured[env->cfg.device & 63] = true;
     }
     static const int slices_force = getenv("QLC_GATHER_SLICES") ? atoi(getenv("QLC_GATHER_SLICES")) : 0;
@@ -558,7 +558,7 @@ static int32_t launch_gather(qlc_env* env, const GatherParams& g_in, int32_t lay
         g.slices = units * 4u <= 2u * sms ? 4u : (units * 2u <= 2u * sms ? 2u : 1u);
         if (slices_force == 1 || slices_force == 2 || slices_force == 4) g.slices = (uint32_t)slices_force;
         const uint32_t ctas = units * g.slices;
-        size_t smem = 4 * FRAME_BYTES;           // 4 slot frames; the in-kernel sampler's table (batch > 896: 32 KB) borrows the same bytes
+        size_t smem = 4 * FRAME_BYTES;           // 4 slot frames; the in-kernel sampler's table (batch > 384: 32 KB) borrows the same bytes
         if (g.mode == GATHER_SAMPLE && 8u * (size_t)sample_table_size(g.sample_batch) > smem) smem = 8u * (size_t)sample_table_size(g.sample_batch);
         uint32_t cap = (ctas + sms - 1) / sms;
         if (cap_force >= 0) cap = (uint32_t)cap_force;
