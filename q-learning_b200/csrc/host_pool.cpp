@@ -4,6 +4,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <thread>
@@ -17,28 +18,97 @@ void widen_range(const uint8_t* __restrict__ s, float* __restrict__ d, size_t n)
     for (size_t i = 0; i < n; ++i) d[i] = (float)s[i];
 }
 
+// Non-temporal variant for outputs far larger than the caches (a 512-minibatch is 115 MB of f32): plain stores read every
+// destination line before overwriting it (read-for-ownership), streaming stores do not - the host's DRAM sees 5 instead of 9
+// bytes per pixel. Only used from NT_MIN_BYTES on: a minibatch of 32 (7.2 MB) is better left in the cache for its reader.
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx512f"))) void widen_nt_avx512(const uint8_t* __restrict__ s, float* __restrict__ d, size_t n) {
+    size_t i = 0;
+    for (; i < n && ((uintptr_t)(d + i) & 63u); ++i) d[i] = (float)s[i];
+    for (; i + 16 <= n; i += 16)
+        _mm512_stream_ps(d + i, _mm512_cvtepi32_ps(_mm512_cvtepu8_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i)))));
+    for (; i < n; ++i) d[i] = (float)s[i];
+    _mm_sfence();
+}
+__attribute__((target("avx2"))) void widen_nt_avx2(const uint8_t* __restrict__ s, float* __restrict__ d, size_t n) {
+    size_t i = 0;
+    for (; i < n && ((uintptr_t)(d + i) & 31u); ++i) d[i] = (float)s[i];
+    for (; i + 8 <= n; i += 8)
+        _mm256_stream_ps(d + i, _mm256_cvtepi32_ps(_mm256_cvtepu8_epi32(_mm_loadl_epi64(reinterpret_cast<const __m128i*>(s + i)))));
+    for (; i < n; ++i) d[i] = (float)s[i];
+    _mm_sfence();
+}
+void widen_nt(const uint8_t* s, float* d, size_t n) {
+    static const int level = __builtin_cpu_supports("avx512f") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
+    if (level == 2) widen_nt_avx512(s, d, n);
+    else if (level == 1) widen_nt_avx2(s, d, n);
+    else widen_range(s, d, n);
+}
+#else
+void widen_nt(const uint8_t* s, float* d, size_t n) { widen_range(s, d, n); }
+#endif
+constexpr size_t NT_MIN_BYTES = (size_t)32 << 20;
+
 constexpr size_t CHUNK = 32 * 1024;     // elements per work item: 32 KB read, 128 KB written
+
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+}
 
 struct Pool {
     std::mutex m;
     std::condition_variable cv;
     std::vector<std::thread> workers;
-    // the current job. `ticket` = job number << 32 | next chunk to hand out: a chunk is claimed by compare-and-swap on the whole
-    // word, so a worker that is late for job g can never take (or skip) a chunk of job g+1 with job g's view of the fields.
+    // the current job. `ticket` = job number << 32 | next item to hand out: an item is claimed by compare-and-swap on the whole
+    // word, so a worker that is late for job g can never take (or skip) an item of job g+1 with job g's view of the fields.
     std::atomic<uint64_t> ticket{0};
-    const uint8_t* src = nullptr; float* dst = nullptr; size_t n = 0, n_chunks = 0;
+    // plain job: item c = elements [c * CHUNK, ...) of src -> dst
+    const uint8_t* src = nullptr; float* dst = nullptr; size_t n = 0;
+    // streamed job (pieces != nullptr): item c = pieces[c], ready when flags[c] == flag_value
+    const qlc_host::StreamPiece* pieces = nullptr; const volatile uint32_t* flags = nullptr; uint32_t flag_value = 0;
+    std::atomic<bool> abandon{false};
+    std::atomic<size_t> missed{0};
+    size_t n_items = 0, n_pieces = 0, group = 1;
+    bool nt = false;                         // this job's output is far larger than the caches: streaming stores
     std::atomic<size_t> done{0};
     int n_threads = 1;
 
-    void run_chunks(uint64_t job) {
+    void run_item(size_t c, bool (*still_running)(void*) = nullptr, void* ctx = nullptr) {
+        if (!pieces) {
+            const size_t at = c * CHUNK, len = n - at < CHUNK ? n - at : CHUNK;
+            if (nt) widen_nt(src + at, dst + at, len); else widen_range(src + at, dst + at, len);
+            return;
+        }
+        for (size_t i = c * group; i < (c + 1) * group && i < n_pieces; ++i) {     // the pieces of one claim, in arrival order
+            const qlc_host::StreamPiece& p = pieces[i];
+            if (!p.dst) continue;
+            bool landed = true;
+            unsigned spins = 0;
+            while (__atomic_load_n(const_cast<const uint32_t*>(&flags[i]), __ATOMIC_ACQUIRE) != flag_value) {
+                // the calling thread keeps an eye on the producer: once the stream is over, flags that are still missing never come
+                if (still_running && (++spins & 255u) == 0 && !still_running(ctx)) abandon.store(true, std::memory_order_release);
+                if (abandon.load(std::memory_order_acquire)) {
+                    landed = __atomic_load_n(const_cast<const uint32_t*>(&flags[i]), __ATOMIC_ACQUIRE) == flag_value;   // it may have landed meanwhile
+                    break;
+                }
+                cpu_relax();
+            }
+            if (landed) { if (nt) widen_nt(p.src, p.dst, p.n); else widen_range(p.src, p.dst, p.n); }
+            else missed.fetch_add(1, std::memory_order_relaxed);
+        }
+    }
+
+    void run_items(uint64_t job) {
         for (;;) {
             uint64_t v = ticket.load(std::memory_order_acquire);
             if ((v >> 32) != job) return;                            // that job is over
             const size_t c = (size_t)(v & 0xFFFFFFFFu);
-            if (c >= n_chunks) return;                               // fields belong to `job`: published before its ticket
+            if (c >= n_items) return;                                // fields belong to `job`: published before its ticket
             if (!ticket.compare_exchange_weak(v, v + 1, std::memory_order_acq_rel)) continue;
-            const size_t at = c * CHUNK, len = n - at < CHUNK ? n - at : CHUNK;
-            widen_range(src + at, dst + at, len);
+            run_item(c);
             done.fetch_add(1, std::memory_order_release);
         }
     }
@@ -57,7 +127,7 @@ struct Pool {
                 std::this_thread::yield();
             }
             seen = ticket.load(std::memory_order_acquire) >> 32;
-            run_chunks(seen);
+            run_items(seen);
         }
     }
 
@@ -78,20 +148,74 @@ struct Pool {
         for (auto& t : workers) t.detach();      // parked on the condition variable for the life of the process
     }
 
-    void widen(const uint8_t* s, float* d, size_t count) {
-        if (count == 0) return;
-        if (n_threads == 1 || count <= 2 * CHUNK) { widen_range(s, d, count); return; }
+    uint64_t publish() {                     // fields of the new job are set: hand it out
         uint64_t job;
         {
             std::lock_guard<std::mutex> lk(m);
-            src = s; dst = d; n = count; n_chunks = (count + CHUNK - 1) / CHUNK;
             done.store(0, std::memory_order_relaxed);
             job = (ticket.load(std::memory_order_relaxed) >> 32) + 1;
             ticket.store(job << 32, std::memory_order_release);
         }
         cv.notify_all();
-        run_chunks(job);
-        while (done.load(std::memory_order_acquire) < n_chunks) std::this_thread::yield();   // every claimed chunk has been written
+        return job;
+    }
+
+    // no item of this job can be claimed any more: a straggler that still holds the job's ticket value fails its compare-and-swap,
+    // so the fields may be rewritten for the next job
+    void close(uint64_t job) { ticket.store((job << 32) | 0xFFFFFFFFull, std::memory_order_release); }
+
+    void widen(const uint8_t* s, float* d, size_t count) {
+        if (count == 0) return;
+        if (n_threads == 1 || count <= 2 * CHUNK) { if (count * 4 >= NT_MIN_BYTES) widen_nt(s, d, count); else widen_range(s, d, count); return; }
+        pieces = nullptr; src = s; dst = d; n = count; n_items = (count + CHUNK - 1) / CHUNK; nt = count * 4 >= NT_MIN_BYTES;
+        const uint64_t job = publish();
+        run_items(job);
+        while (done.load(std::memory_order_acquire) < n_items) std::this_thread::yield();   // every claimed item has been written
+        close(job);
+    }
+
+    size_t stream(const qlc_host::StreamPiece* ps, size_t count, size_t grp, const volatile uint32_t* fl, uint32_t value, bool (*still_running)(void*), void* ctx) {
+        if (count == 0) return 0;
+        static const bool timing = getenv("QLC_HOST_TIMING") != nullptr;
+        const auto t_pub = std::chrono::steady_clock::now();
+        if (timing) {      // one thread, in order: when does the first / the last flag come up, how long does the widening take behind it
+            double first = -1, last = 0, work = 0;
+            for (size_t c = 0; c < count; ++c) {
+                if (!ps[c].dst) continue;
+                while (__atomic_load_n(const_cast<const uint32_t*>(&fl[c]), __ATOMIC_ACQUIRE) != value) cpu_relax();
+                const auto a = std::chrono::steady_clock::now();
+                if (first < 0) first = std::chrono::duration<double, std::micro>(a - t_pub).count();
+                last = std::chrono::duration<double, std::micro>(a - t_pub).count();
+                widen_range(ps[c].src, ps[c].dst, ps[c].n);
+                work += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - a).count();
+            }
+            std::fprintf(stderr, "[qlc host stream] %zu pieces: first flag %.1f us after publish, last flag seen at %.1f us, widening %.1f us (1 thread)\n", count, first, last, work);
+            return 0;
+        }
+        pieces = ps; flags = fl; flag_value = value; n_pieces = count; group = grp ? grp : 1; n_items = (count + group - 1) / group;
+        size_t out_bytes = 0;
+        for (size_t i = 0; i < count; ++i) if (ps[i].dst) out_bytes += (size_t)ps[i].n * 4;
+        nt = out_bytes >= NT_MIN_BYTES;
+        abandon.store(false, std::memory_order_relaxed); missed.store(0, std::memory_order_relaxed);
+        const uint64_t job = publish();
+        // the calling thread takes pieces like a worker, but looks after the producer between them: when the stream is over, flags
+        // that are still missing will never come
+        for (;;) {
+            uint64_t v = ticket.load(std::memory_order_acquire);
+            const size_t c = (size_t)(v & 0xFFFFFFFFu);
+            if (c >= n_items) break;
+            if (!ticket.compare_exchange_weak(v, v + 1, std::memory_order_acq_rel)) continue;
+            run_item(c, still_running, ctx);
+            done.fetch_add(1, std::memory_order_release);
+        }
+        unsigned spins = 0;
+        while (done.load(std::memory_order_acquire) < n_items) {
+            if ((++spins & 255u) == 0 && !still_running(ctx)) abandon.store(true, std::memory_order_release);
+            cpu_relax();
+        }
+        close(job);
+        pieces = nullptr;
+        return missed.load(std::memory_order_relaxed);
     }
 };
 
@@ -105,4 +229,7 @@ Pool& pool() {
 namespace qlc_host {
 int pool_threads() { return pool().n_threads; }
 void widen_u8_f32(const uint8_t* src, float* dst, size_t n) { pool().widen(src, dst, n); }
+size_t widen_stream(const StreamPiece* pieces, size_t n_pieces, size_t group, const volatile uint32_t* flags, uint32_t flag_value, bool (*still_running)(void*), void* ctx) {
+    return pool().stream(pieces, n_pieces, group, flags, flag_value, still_running, ctx);
+}
 }  // namespace qlc_host

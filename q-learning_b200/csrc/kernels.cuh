@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             }
         }
         }   // batches
-        if (lane == 0) bulk_wait<0>();
+        if (lane == 0) bulk_wait<0>();     // (waiting only for the reads, cp.async.bulk.wait_group.read, measured the same: 10.87 vs 10.80 us per single-step launch)
     }
 }
 
@@ -515,7 +515,9 @@ constexpr int SAMPLE_MAX_BATCH = 1024;
 constexpr uint32_t SAMPLE_EMPTY = 0xFFFFFFFFu;           // never a value: len < 2^32 - 1 is checked by the host
 constexpr uint32_t SAMPLE_MAX_ROUNDS = 1u << 19;         // x 128 stream positions: the bound of the "loop" in the reference
 
+constexpr uint32_t SAMPLE_BLOCK_MIN_BATCH = 129;    // from this batch size on a CTA's warps walk the stream side by side (sample_distinct_block)
 __host__ __device__ __forceinline__ uint32_t sample_table_size(uint32_t batch) {   // slots: power of two >= 4 * (batch + 128)
+    if (batch >= SAMPLE_BLOCK_MIN_BATCH) return 4096u;                              // batch + 8 * 128 entries at most: load <= 0.5
     uint32_t n = 1024;
     while (n < 4u * (batch + 128u) && n < 4096u) n <<= 1;
     return n;                                                                       // <= 4096 slots x (value, position) = 32 KB
@@ -601,15 +603,77 @@ __device__ __forceinline__ uint32_t sample_one(uint32_t* table, uint32_t tsize, 
     return hit ? __shfl_sync(0xFFFFFFFFu, mine, __ffs(hit) - 1) : 0u;      // no hit: unreachable for len >= batch (the reference would loop forever)
 }
 
-// index-only form: one warp per minibatch
-__global__ void __launch_bounds__(32) replay_sample_kernel(uint32_t* out, uint32_t batch, uint32_t len, uint64_t seed, uint64_t call0) {
+// CTA-wide form for big minibatches (batch >= SAMPLE_BLOCK_MIN_BATCH): the NW warps of the CTA take NW consecutive rounds of the
+// stream at once (warp w of pass s = round s * NW + w), so a minibatch of 512 is ONE pass of 8 warps instead of five rounds of
+// one. Every accepted draw claims the slot of its value (atomicCAS) and bids for it with its stream position (atomicMin); after
+// the CTA barrier a draw is a first occurrence iff the slot still shows its own position - entries of earlier passes always win.
+// Ranks: warp prefix sum, then the warp totals in round order. Same deliver(rank, value) contract as sample_distinct_warp.
+template <int NW, class Deliver>
+__device__ __forceinline__ void sample_distinct_block(uint32_t* table, uint32_t tsize, uint32_t len, uint64_t seed, uint64_t call,
+                                                      uint32_t j_lo, uint32_t j_hi, int tid, uint32_t* warp_totals /* [NW] shared */, Deliver deliver) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t thresh = (uint32_t)((0x100000000ull - (uint64_t)len) % (uint64_t)len);
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t tmask = tsize - 1u;
+    uint32_t* tval = table; uint32_t* tpos = table + tsize;
+    uint32_t kept = 0;
+    for (uint32_t pass = 0; pass < SAMPLE_MAX_ROUNDS / NW; ++pass) {
+        const uint32_t ctr = (pass * NW + (uint32_t)warp) * 32u + (uint32_t)lane;
+        const uint4 r = philox4x32_10(make_uint4(ctr, (uint32_t)call, (uint32_t)(call >> 32), STREAM_SAMPLE), key);
+        const uint32_t raw[4] = {r.x, r.y, r.z, r.w};
+        uint32_t val[4], slot[4]; bool valid[4];
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint64_t m = (uint64_t)raw[w] * (uint64_t)len;
+            valid[w] = !((uint32_t)m < thresh);
+            val[w] = (uint32_t)(m >> 32);
+            slot[w] = ((val[w] * 0x9E3779B1u) >> 12) & tmask;
+        }
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            if (valid[w]) {
+                uint32_t old = atomicCAS(&tval[slot[w]], SAMPLE_EMPTY, val[w]);
+                while (old != SAMPLE_EMPTY && old != val[w]) { slot[w] = (slot[w] + 1u) & tmask; old = atomicCAS(&tval[slot[w]], SAMPLE_EMPTY, val[w]); }
+                atomicMin(&tpos[slot[w]], ctr * 4u + (uint32_t)w);          // positions start as SAMPLE_EMPTY = the largest value
+            }
+        }
+        __syncthreads();
+        bool first[4]; uint32_t cnt = 0;
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) { first[w] = valid[w] && tpos[slot[w]] == ctr * 4u + (uint32_t)w; cnt += first[w] ? 1u : 0u; }
+        uint32_t incl = cnt;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) warp_totals[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0, all = 0;
+        #pragma unroll
+        for (int w = 0; w < NW; ++w) { const uint32_t t = warp_totals[w]; all += t; if (w < warp) before += t; }
+        uint32_t rank = kept + before + incl - cnt;
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) if (first[w]) { if (rank >= j_lo && rank <= j_hi) deliver(rank, val[w]); ++rank; }
+        kept += all;
+        if (kept > j_hi) return;                                            // the same decision in every thread
+        __syncthreads();                                                    // warp_totals is rewritten by the next pass
+    }
+}
+
+// index-only form: one CTA of NW warps per minibatch (NW = 1: the warp routine; NW = 8 for batch >= SAMPLE_BLOCK_MIN_BATCH)
+template <int NW>
+__global__ void __launch_bounds__(32 * NW) replay_sample_kernel(uint32_t* out, uint32_t batch, uint32_t len, uint64_t seed, uint64_t call0) {
     __shared__ __align__(16) uint32_t table[2 * 4096];
-    const int lane = threadIdx.x;
+    __shared__ uint32_t warp_totals[NW];
+    const int tid = threadIdx.x;
     const uint32_t tsize = sample_table_size(batch);
-    sample_table_clear(table, tsize, lane, 32);
-    __syncwarp();
+    sample_table_clear(table, tsize, tid, 32 * NW);
     uint32_t* dst = out + (size_t)blockIdx.x * batch;
-    sample_distinct_warp(table, tsize, len, seed, call0 + blockIdx.x, 0u, batch - 1u, lane, [&](uint32_t rank, uint32_t v) { dst[rank] = v; });
+    if (NW == 1) {
+        __syncwarp();
+        sample_distinct_warp(table, tsize, len, seed, call0 + blockIdx.x, 0u, batch - 1u, tid, [&](uint32_t rank, uint32_t v) { dst[rank] = v; });
+    } else {
+        __syncthreads();
+        sample_distinct_block<NW>(table, tsize, len, seed, call0 + blockIdx.x, 0u, batch - 1u, tid, warp_totals, [&](uint32_t rank, uint32_t v) { dst[rank] = v; });
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -635,6 +699,10 @@ struct GatherParams {
     uint32_t slices;           // [b][x][y][slot] kernel: CTAs per (item, state | next), each writes 1/slices of the pixels
     void* out_state; void* out_next;
     float* reward; uint8_t* action; uint8_t* done;
+    // streamed host gathers (gather_xyh_stream_kernel, outputs in page-locked host memory): piece i raises cta_flags[i] = flag_value
+    // (system scope, after its bulk store has been performed) so that host threads can consume it while the pieces behind it are
+    // still crossing PCIe
+    uint32_t* cta_flags; uint32_t flag_value; uint32_t preload;   // preload: copy the indices / handles into shared memory first
 };
 
 // false = the item does not exist (index >= len, handle whose frames have left the ring): every slot is zero-filled
@@ -680,24 +748,38 @@ __device__ __forceinline__ void write_scalars(const GatherParams& g, uint32_t b,
     if (g.done) g.done[b] = (uint8_t)((rec >> 2) & 1u);
 }
 
-// u8 [b][slot][y][x]: one warp per item; <= 5 distinct frames in, 8 frames out, all as 7,056-byte bulk copies.
-__global__ void __launch_bounds__(32) gather_u8_kernel(GatherParams g) {
+// u8 [b][slot][y][x]: one warp per item; <= 5 distinct frames in, 8 frames out, all as 7,056-byte bulk copies. NW > 1 (sampled
+// minibatches of >= SAMPLE_BLOCK_MIN_BATCH): NW - 1 more warps help with the index draw and leave.
+template <int NW>
+__global__ void __launch_bounds__(32 * NW) gather_u8_kernel(GatherParams g) {
     extern __shared__ __align__(128) uint8_t sm[];     // 5 frames + 1 zero frame; the sampler's hash table borrows the first <= 32 KB
     __shared__ uint64_t bar;
-    const int lane = threadIdx.x;
+    __shared__ uint32_t warp_totals[NW], s_idx;
+    const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t b = blockIdx.x;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's prologue may overlap this grid (see env_advance_kernel)
     uint8_t* zero = sm + 5 * FRAME_BYTES;
-    for (int i = lane; i < FRAME_VEC16; i += 32) reinterpret_cast<uint4*>(zero)[i] = make_uint4(0, 0, 0, 0);
-    if (lane == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    for (int i = tid; i < FRAME_VEC16; i += 32 * NW) reinterpret_cast<uint4*>(zero)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     uint32_t idx = 0;
     uint32_t* table = reinterpret_cast<uint32_t*>(sm);
     if (g.mode == GATHER_SAMPLE) {
-        sample_table_clear(table, sample_table_size(g.sample_batch), lane, 32);
-        __syncwarp();
+        const uint32_t tsize = sample_table_size(g.sample_batch);
+        sample_table_clear(table, tsize, tid, 32 * NW);
         const uint32_t mb = b / g.sample_batch, j = b - mb * g.sample_batch;
-        idx = sample_one(table, sample_table_size(g.sample_batch), g.sample_len, g.seed, g.call0 + mb, j, lane);
+        if (NW == 1) {
+            __syncwarp();
+            idx = sample_one(table, tsize, g.sample_len, g.seed, g.call0 + mb, j, lane);
+        } else {
+            __syncthreads();
+            sample_distinct_block<NW>(table, tsize, g.sample_len, g.seed, g.call0 + mb, j, j, tid, warp_totals, [&](uint32_t, uint32_t v) { s_idx = v; });
+            fence_proxy_async_smem();                    // the helpers' share of the zero frame and of the table, before the bulk copies
+            __syncthreads();
+            idx = s_idx;
+        }
     }
+    if (NW > 1 && g.mode != GATHER_SAMPLE) { fence_proxy_async_smem(); __syncthreads(); }   // (not launched this way: keeps the zero frame whole)
+    if (NW > 1 && tid >= 32) return;                     // the helper warps are done
     // launched with programmatic stream serialization: everything above neither reads nor writes anything an earlier kernel touches
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (g.mode == GATHER_SAMPLE && lane == 0 && g.idx_out) g.idx_out[b] = idx;
@@ -749,7 +831,7 @@ template <class Px>
 __global__ void __launch_bounds__(GATHER_XYH_THREADS) gather_xyh_kernel(GatherParams g) {
     extern __shared__ __align__(128) uint8_t sm[];     // 4 slot frames; the sampler's hash table borrows the first <= 32 KB
     __shared__ uint64_t bar;
-    __shared__ uint32_t s_idx;
+    __shared__ uint32_t s_idx, warp_totals[GATHER_XYH_THREADS / 32];
     const int tid = threadIdx.x;
     const uint32_t unit = blockIdx.x / g.slices, slice = blockIdx.x - unit * g.slices;
     const uint32_t b = unit >> 1, which = unit & 1u;   // 0 = state, 1 = next
@@ -759,11 +841,14 @@ __global__ void __launch_bounds__(GATHER_XYH_THREADS) gather_xyh_kernel(GatherPa
     uint32_t idx = 0;
     uint32_t* table = reinterpret_cast<uint32_t*>(sm);
     if (g.mode == GATHER_SAMPLE) {
-        sample_table_clear(table, sample_table_size(g.sample_batch), tid, GATHER_XYH_THREADS);
+        const uint32_t tsize = sample_table_size(g.sample_batch);
+        const uint32_t mb = b / g.sample_batch, j = b - mb * g.sample_batch;
+        sample_table_clear(table, tsize, tid, GATHER_XYH_THREADS);
         __syncthreads();
-        if (tid < 32) {
-            const uint32_t mb = b / g.sample_batch, j = b - mb * g.sample_batch;
-            const uint32_t v = sample_one(table, sample_table_size(g.sample_batch), g.sample_len, g.seed, g.call0 + mb, j, tid);
+        if (g.sample_batch >= SAMPLE_BLOCK_MIN_BATCH) {   // all 8 warps walk the stream side by side
+            sample_distinct_block<GATHER_XYH_THREADS / 32>(table, tsize, g.sample_len, g.seed, g.call0 + mb, j, j, tid, warp_totals, [&](uint32_t, uint32_t v) { s_idx = v; });
+        } else if (tid < 32) {
+            const uint32_t v = sample_one(table, tsize, g.sample_len, g.seed, g.call0 + mb, j, tid);
             if (tid == 0) s_idx = v;
         }
         __syncthreads();
@@ -807,6 +892,99 @@ __global__ void __launch_bounds__(GATHER_XYH_THREADS) gather_xyh_kernel(GatherPa
         const int x = i / FRAME_H, y = i - x * FRAME_H;
         const int src = y * FRAME_W + x;
         store_pixel(o, i, sm[src], sm[FRAME_BYTES + src], sm[2 * FRAME_BYTES + src], sm[3 * FRAME_BYTES + src]);
+    }
+}
+
+// Streamed host gather (f32 [b][x][y][slot] requests of the *_host entry points): the u8 stacks go straight into page-locked HOST
+// memory, in order, and every piece (1/slices of a stack) raises an arrival flag at system scope, so that host threads widen
+// piece i into the caller's tensor while the pieces behind it are still crossing PCIe. A small persistent grid walks the pieces
+// with stride gridDim.x: few CTAs in flight = pieces land in order (a grid of one CTA per piece finishes them all at once, after
+// the whole transfer: first flag 55 us after the launch, measured). Each piece is transposed in shared memory and leaves as ONE
+// bulk copy - large PCIe writes.
+__global__ void __launch_bounds__(GATHER_XYH_THREADS) gather_xyh_stream_kernel(GatherParams g) {
+    extern __shared__ __align__(128) uint8_t sm[];     // 4 slot frames + the transposed piece
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    const int per_slice = FRAME_BYTES / (int)g.slices;
+    const uint32_t n_pieces = g.n_items * 2u * g.slices;
+    // The indices / handles sit in page-locked host memory: fetch them ONCE, before any store is in flight - a PCIe read issued
+    // per piece queues up behind the outbound frame data (measured: ~13 us per piece, whatever its size).
+    const uint32_t* my_indices = g.indices; const ObsHandle* my_handles = g.handles;
+    if (g.preload) {
+        uint8_t* pre = sm + 4 * FRAME_BYTES + 2 * (size_t)per_slice * 4u;
+        if (g.mode == GATHER_INDICES) {
+            for (uint32_t i = tid; i < g.n_items; i += GATHER_XYH_THREADS) reinterpret_cast<uint32_t*>(pre)[i] = g.indices[i];
+            my_indices = reinterpret_cast<const uint32_t*>(pre);
+        } else if (g.mode == GATHER_HANDLES) {
+            for (uint32_t i = tid; i < g.n_items; i += GATHER_XYH_THREADS) reinterpret_cast<uint4*>(pre)[i] = reinterpret_cast<const uint4*>(g.handles)[i];
+            my_handles = reinterpret_cast<const ObsHandle*>(pre);
+        }
+        __syncthreads();
+    }
+    GatherParams gl = g; gl.handles = my_handles;
+    uint32_t phase = 0, it = 0;
+    uint32_t prev_piece = 0xFFFFFFFFu;                   // thread 0: the piece whose store is in flight, its flag not raised yet
+    for (uint32_t piece = blockIdx.x; piece < n_pieces; piece += gridDim.x) {
+        uchar4* stg = reinterpret_cast<uchar4*>(sm + 4 * FRAME_BYTES + (size_t)(it & 1u) * (size_t)per_slice * 4u);   // two staging buffers
+        ++it;
+        const uint32_t unit = piece / g.slices, slice = piece - unit * g.slices;
+        const uint32_t b = unit >> 1, which = unit & 1u;
+        uchar4* out = reinterpret_cast<uchar4*>(which ? g.out_next : g.out_state);
+        if (!out) continue;
+        uint64_t T; uint32_t e, k, rec;
+        const bool exists = locate(gl, b, g.mode == GATHER_INDICES ? my_indices[b] : 0u, T, e, k, rec);
+        if (tid == 0 && slice == 0 && (which == 0 || !g.out_state)) write_scalars(g, b, rec);
+        uint32_t dsl[4];
+        #pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            dsl[h] = which ? ((k - h) & 3u) : (((k - h - 1u) & 3u) + 1u);
+            if (!exists) dsl[h] = 0xFFFFu;
+            if (dsl[h] > k)
+                for (int i = tid; i < FRAME_VEC16; i += GATHER_XYH_THREADS) reinterpret_cast<uint4*>(sm + h * FRAME_BYTES)[i] = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();                                 // also: thread 0 is back from the previous piece's store
+        uint32_t bytes = 0;
+        #pragma unroll
+        for (int h = 0; h < 4; ++h) if (dsl[h] <= k) bytes += FRAME_BYTES;
+        if (bytes) {
+            if (tid == 0) {
+                mbar_expect_tx(&bar, bytes);
+                for (int h = 0; h < 4; ++h)
+                    if (dsl[h] <= k) {
+                        const uint64_t Tf = T - (uint64_t)dsl[h];
+                        bulk_load(sm + h * FRAME_BYTES, g.frames + ((size_t)(Tf % g.time_slots) * g.n_envs + e) * FRAME_BYTES, FRAME_BYTES, &bar);
+                    }
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+        }
+        for (int i = (int)slice * per_slice + tid, q = tid; q < per_slice; i += GATHER_XYH_THREADS, q += GATHER_XYH_THREADS) {
+            const int x = i / FRAME_H, y = i - x * FRAME_H;
+            const int src = y * FRAME_W + x;
+            stg[q] = make_uchar4(sm[src], sm[FRAME_BYTES + src], sm[2 * FRAME_BYTES + src], sm[3 * FRAME_BYTES + src]);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_store(out + (size_t)b * FRAME_BYTES + (size_t)slice * per_slice, stg, (uint32_t)per_slice * 4u);
+            bulk_commit();
+            // this piece's store stays in flight while the next piece is loaded and transposed (into the other staging buffer); the
+            // piece BEFORE it has been performed by now ...
+            bulk_wait<1>();
+            if (prev_piece != 0xFFFFFFFFu) {
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(g.cta_flags + prev_piece), "r"(g.flag_value) : "memory");   // ... so its flag goes up
+            }
+            prev_piece = piece;
+        }
+    }
+    if (tid == 0 && prev_piece != 0xFFFFFFFFu) {
+        bulk_wait<0>();
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(g.cta_flags + prev_piece), "r"(g.flag_value) : "memory");
     }
 }
 

@@ -9,6 +9,7 @@
 
 #include <nvtx3/nvToolsExt.h>   // header-only; ranges cost a few ns unless a tool (ncu --nvtx, nsys) is attached
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -72,6 +73,8 @@ struct qlc_env {
     cudaStream_t own_stream = nullptr;         // used by the *_host entry points
     // pinned staging for the host-buffer entry points
     void* pin = nullptr; size_t pin_bytes = 0;
+    std::vector<qlc_host::StreamPiece> stream_pieces;
+    uint32_t flag_serial = 0;                  // streamed host gathers: value the kernel raises its arrival flags to (never 0)
     void* dev_stage = nullptr; size_t dev_stage_bytes = 0;
     // episode reward window (replay_buffer.rs:100-124) — host side, fed by the caller like the reference
     std::deque<float> window;
@@ -105,6 +108,7 @@ static int32_t ensure_pin(qlc_env* env, size_t bytes) {
     if (env->pin) cudaFreeHost(env->pin);
     env->pin = nullptr; env->pin_bytes = 0;
     CUDA_TRY(cudaMallocHost(&env->pin, bytes));
+    memset(env->pin, 0, bytes);                // streamed gathers keep arrival flags in here: a fresh block must not hold a serial by accident
     env->pin_bytes = bytes;
     return QLC_OK;
 }
@@ -537,7 +541,8 @@ static int32_t launch_gather(qlc_env* env, const GatherParams& g_in, int32_t lay
     GatherParams g = g_in;
     static bool configured[64] = {};
     if (!configured[env->cfg.device & 63]) {     // opt in to large dynamic shared memory (6 frames; occupancy caps)
-        CUDA_TRY(cudaFuncSetAttribute(gather_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(gather_u8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(gather_u8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(gather_xyh_kernel<float4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(gather_xyh_kernel<uchar4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         configured[env->cfg.device & 63] = true;
@@ -551,7 +556,11 @@ static int32_t launch_gather(qlc_env* env, const GatherParams& g_in, int32_t lay
         if (!known_layout(layout)) return fail(QLC_ERR_INVALID_ARG, "unknown layout");
         uint32_t cap = (g.n_items + sms - 1) / sms;                  // spread a small grid over the SMs
         if (cap_force >= 0) cap = (uint32_t)cap_force;
-        CUDA_TRY(launch_pdl(gather_u8_kernel, dim3(g.n_items), dim3(32), smem_for_cap(6 * FRAME_BYTES, cap), s, g));
+        // a sampled minibatch of >= 129: 7 helper warps per CTA join the index draw (one pass over the Philox stream instead of five rounds)
+        if (g.mode == GATHER_SAMPLE && g.sample_batch >= SAMPLE_BLOCK_MIN_BATCH)
+            CUDA_TRY(launch_pdl(gather_u8_kernel<8>, dim3(g.n_items), dim3(256), smem_for_cap(6 * FRAME_BYTES, cap), s, g));
+        else
+            CUDA_TRY(launch_pdl(gather_u8_kernel<1>, dim3(g.n_items), dim3(32), smem_for_cap(6 * FRAME_BYTES, cap), s, g));
     } else if (layout == QLC_LAYOUT_F32_BXYH || layout == QLC_LAYOUT_U8_BXYH) {
         // slices: enough CTAs to put a single small minibatch on every SM (each CTA stages the 4 frames again, from L2)
         const uint32_t units = g.n_items * 2u;
@@ -690,7 +699,8 @@ int32_t qlc_replay_sample(qlc_env* env, uint32_t batch, uint32_t n_batches, uint
     int32_t rc = check_sample_args(env, batch, &len); if (rc) return rc;
     if (n_batches == 0) return QLC_OK;
     rc = set_device(env); if (rc) return rc;
-    replay_sample_kernel<<<n_batches, 32, 0, (cudaStream_t)stream>>>(idx_dev, batch, (uint32_t)len, env->cfg.seed, call_index);
+    if (batch >= SAMPLE_BLOCK_MIN_BATCH) replay_sample_kernel<8><<<n_batches, 256, 0, (cudaStream_t)stream>>>(idx_dev, batch, (uint32_t)len, env->cfg.seed, call_index);
+    else replay_sample_kernel<1><<<n_batches, 32, 0, (cudaStream_t)stream>>>(idx_dev, batch, (uint32_t)len, env->cfg.seed, call_index);
     CUDA_TRY(cudaGetLastError());
     return QLC_OK;
 }
@@ -755,6 +765,81 @@ static int32_t run_host_gather(qlc_env* env, HostGather& hg) {
     // hundred bytes over PCIe instead of two more copy launches): in | reward | action | done | idx_out | state | next
     const size_t o_in = 0, o_r = (hg.h2d_bytes + 255) & ~(size_t)255, o_a = o_r + (size_t)n * 4, o_d = o_a + n, o_i = (o_d + n + 15) & ~(size_t)15;
     const size_t o_s = (o_i + (size_t)n * 4 + 255) & ~(size_t)255, o_n = o_s + ib * n, total = o_n + ib * n;
+    // f32 requests, streamed (QLC_HOST_STREAM=0: the piecewise copies below): the kernel stores the u8 stacks straight into the
+    // page-locked staging while it runs and raises one arrival flag per CTA; the host pool widens slice i into the caller's
+    // tensor as soon as its flag is up, while the slices behind it are still crossing PCIe. One launch, no copy calls, no events.
+    static const bool stream_mode = getenv("QLC_HOST_STREAM") ? atoi(getenv("QLC_HOST_STREAM")) != 0 : true;
+    if (widen && stream_mode && (hg.state_host || hg.next_host)) {      // (scalars only: the one-warp kernel below)
+        static const bool timing = getenv("QLC_HOST_TIMING") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
+        const size_t o_f = (total + 255) & ~(size_t)255, total_f = o_f + (size_t)n * 2 * 4 * sizeof(uint32_t);   // <= 4 CTAs per (item, s | s')
+        int32_t rc = ensure_pin(env, total_f); if (rc) return rc;
+        uint8_t* pin = (uint8_t*)env->pin;
+        cudaStream_t s = env->own_stream;
+        if (hg.h2d_bytes) memcpy(pin + o_in, hg.h2d_src, hg.h2d_bytes);
+        GatherParams& g = hg.g;
+        if (g.mode == GATHER_INDICES) g.indices = (const uint32_t*)(pin + o_in);
+        if (g.mode == GATHER_HANDLES) g.handles = (const ObsHandle*)(pin + o_in);
+        if (g.mode == GATHER_SAMPLE) g.idx_out = hg.idx_out_host ? (uint32_t*)(pin + o_i) : nullptr;
+        g.n_items = n;
+        g.out_state = hg.state_host ? pin + o_s : nullptr; g.out_next = hg.next_host ? pin + o_n : nullptr;
+        const bool scalars = g.mode == GATHER_INDICES || g.mode == GATHER_SAMPLE;
+        g.reward = scalars ? (float*)(pin + o_r) : nullptr; g.action = scalars ? pin + o_a : nullptr; g.done = scalars ? pin + o_d : nullptr;
+        if (++env->flag_serial == 0) env->flag_serial = 1;
+        g.cta_flags = (uint32_t*)(pin + o_f); g.flag_value = env->flag_serial;
+        if (g.mode == GATHER_SAMPLE) {        // the persistent kernel takes given indices: draw them first (into the staging, the caller wants them anyway)
+            uint32_t* idx = (uint32_t*)(pin + o_i);
+            if (g.sample_batch >= SAMPLE_BLOCK_MIN_BATCH) replay_sample_kernel<8><<<1, 256, 0, s>>>(idx, g.sample_batch, g.sample_len, g.seed, g.call0);
+            else replay_sample_kernel<1><<<1, 32, 0, s>>>(idx, g.sample_batch, g.sample_len, g.seed, g.call0);
+            CUDA_TRY(cudaGetLastError());
+            g.mode = GATHER_INDICES; g.indices = idx; g.idx_out = nullptr;
+        }
+        static const int slices_env = getenv("QLC_STREAM_SLICES") ? atoi(getenv("QLC_STREAM_SLICES")) : 0;
+        static const int ctas_env = getenv("QLC_STREAM_CTAS") ? atoi(getenv("QLC_STREAM_CTAS")) : 0;
+        // pieces of 14 KB for minibatch-sized requests (finer overlap of transfer and widening), whole 28 KB stacks beyond; enough CTAs
+        // in flight to keep PCIe busy (each spends most of a piece's time loading and transposing), few enough that pieces land in order
+        uint32_t slices = (slices_env == 1 || slices_env == 2 || slices_env == 4) ? (uint32_t)slices_env : (n <= 64 ? 2u : 1u);
+        g.slices = slices;
+        const uint32_t n_ctas_all = n * 2u * slices;
+        uint32_t grid = ctas_env > 0 ? (uint32_t)ctas_env : 48u;
+        if (grid > n_ctas_all) grid = n_ctas_all;
+        size_t smem = 4 * (size_t)FRAME_BYTES + 2 * (4 * (size_t)FRAME_BYTES / slices);      // 4 slot frames + two staging buffers
+        const size_t pre_bytes = g.mode == GATHER_INDICES ? (size_t)n * 4 : (g.mode == GATHER_HANDLES ? (size_t)n * sizeof(ObsHandle) : 0);
+        g.preload = pre_bytes > 0 && pre_bytes <= 64 * 1024 ? 1u : 0u;                        // + the indices / handles, fetched over PCIe once per CTA
+        if (g.preload) smem += pre_bytes;
+        static bool configured[64] = {};
+        if (!configured[env->cfg.device & 63]) {
+            CUDA_TRY(cudaFuncSetAttribute(gather_xyh_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * FRAME_BYTES + 64 * 1024));
+            configured[env->cfg.device & 63] = true;
+        }
+        gather_xyh_stream_kernel<<<grid, GATHER_XYH_THREADS, smem, s>>>(g);
+        CUDA_TRY(cudaGetLastError());
+        const auto t1 = std::chrono::steady_clock::now();
+        const uint32_t per = (uint32_t)(ib / slices);                 // elements per CTA: its share of the 7,056 pixels x 4 slots
+        std::vector<qlc_host::StreamPiece>& pieces = env->stream_pieces;
+        pieces.resize((size_t)n * 2 * slices);
+        for (size_t c = 0; c < pieces.size(); ++c) {
+            const size_t unit = c / slices, slice = c % slices, b = unit >> 1, which = unit & 1;
+            float* host = (float*)(which ? hg.next_host : hg.state_host);
+            const size_t off = b * ib + slice * per;
+            pieces[c] = qlc_host::StreamPiece{pin + (which ? o_n : o_s) + off, host ? host + off : nullptr, per};
+        }
+        const size_t missed = qlc_host::widen_stream(pieces.data(), pieces.size(), slices, (const volatile uint32_t*)(pin + o_f), g.flag_value,
+                                                     [](void* st) { return cudaStreamQuery((cudaStream_t)st) == cudaErrorNotReady; }, (void*)s);
+        const auto t2 = std::chrono::steady_clock::now();
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (timing) {
+            const auto t3 = std::chrono::steady_clock::now();
+            auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+            fprintf(stderr, "[qlc host gather] n=%u slices=%u: setup+launch %.1f us, widen_stream %.1f us, sync %.1f us\n", n, slices, us(t0, t1), us(t1, t2), us(t2, t3));
+        }
+        if (missed) return fail(QLC_ERR_CUDA, "streamed gather: the kernel finished without delivering every slice");
+        if (hg.reward_host) memcpy(hg.reward_host, pin + o_r, (size_t)n * 4);
+        if (hg.action_host) memcpy(hg.action_host, pin + o_a, n);
+        if (hg.done_host) memcpy(hg.done_host, pin + o_d, n);
+        if (hg.idx_out_host) memcpy(hg.idx_out_host, pin + o_i, (size_t)n * 4);
+        return QLC_OK;
+    }
     int32_t rc = ensure_dev_stage(env, 2 * ib * n); if (rc) return rc;
     rc = ensure_pin(env, total); if (rc) return rc;
     uint8_t* dev = (uint8_t*)env->dev_stage; uint8_t* pin = (uint8_t*)env->pin;

@@ -266,7 +266,7 @@ def test_host_gather_into_page_locked_buffers(qlb, O):
     env.close(); ora.close()
 
 
-@pytest.mark.parametrize("length_steps,batch", [(40, 32), (5, 32), (200, 512), (33, 1024)])
+@pytest.mark.parametrize("length_steps,batch", [(40, 32), (5, 32), (200, 512), (33, 1024), (5, 129), (5, 160), (9, 128)])
 def test_sampler_parity(qlb, O, length_steps, batch):
     """generate_distinct_random_ids: distinct, in range (the reference's own property test :346-361) and equal to
     the oracle's sequential rejection on the same Philox stream — including ranges barely larger than the batch."""

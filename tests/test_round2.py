@@ -114,7 +114,7 @@ def _run(env, ora, O, seed, n, steps, t0=0):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_envs,steps,batch,n_batches", [(64, 40, 32, 1), (64, 40, 32, 9), (32, 40, 512, 1), (32, 40, 512, 3), (32, 33, 1024, 2),
-                                                          (4, 9, 32, 2), (1, 1, 1, 1), (16, 300, 7, 5)])
+                                                          (4, 9, 32, 2), (1, 1, 1, 1), (16, 300, 7, 5), (16, 9, 129, 3), (16, 9, 143, 2), (32, 60, 300, 2)])
 def test_sample_gather_in_one_launch(qlb, O, n_envs, steps, batch, n_batches):
     """qlc_replay_sample_gather: the gather kernels draw the indices themselves. Indices equal the oracle's sequential rejection
     loop (and qlc_replay_sample), stacks and scalars equal the oracle's get_many of those indices, all three layouts."""
@@ -457,6 +457,41 @@ def test_host_widening_equals_device_f32(qlb, O, monkeypatch):
             assert np.array_equal(g.state, o["state"]) and np.array_equal(g.state_next, o["state_next"])
     assert np.array_equal(env.obs(qlb.LAYOUT_F32_BXYH), ora.obs_f32())
     env.close(); ora.close()
+
+
+_PIECEWISE = """
+import importlib, sys
+import numpy as np
+sys.path.insert(0, %r)
+q = importlib.import_module("q-learning_b200")
+from oracle import oracle as O
+n, seed = 16, 43
+env = q.BreakoutEnvironment(n_envs=n, seed=seed, replay_capacity=n * 32)
+rb = q.ReplayBuffer(env)
+ora = O.VecEnv(n, seed=seed, replay_capacity=n * 32)
+acts = O.synthetic_actions(seed, 0, n, 0, 30)
+env.step_many(acts)
+for a in acts:
+    ora.step(a)
+for batch in (1, 32, 200):
+    idx = rb.generate_distinct_random_ids(batch, batch)
+    o = ora.get_many(idx, "f32")
+    for reuse in (False, True):
+        g = rb.get_many(idx, q.LAYOUT_F32_BXYH, reuse=reuse)
+        assert np.array_equal(g.state, o["state"]) and np.array_equal(g.state_next, o["state_next"]) and np.array_equal(g.reward, o["reward"])
+print("piecewise ok")
+"""
+
+
+@pytest.mark.gpu
+def test_host_gather_piecewise_copy_path():
+    """QLC_HOST_STREAM=0 keeps the older transport of f32 host gathers (device staging, piecewise device->host copies widened as they
+    arrive) for A/B measurements; the default is the streamed one (the kernel stores into page-locked memory and raises arrival flags,
+    covered by every other host-gather test). Same bytes either way. The switch is read once per process, hence the subprocess."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _PIECEWISE % root], env=dict(os.environ, QLC_HOST_STREAM="0"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "piecewise ok" in r.stdout, r.stdout + r.stderr
 
 
 @pytest.mark.gpu
