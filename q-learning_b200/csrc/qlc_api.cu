@@ -317,6 +317,11 @@ static int32_t launch_advance(qlc_env* env, StepParams& p, cudaStream_t s, uint3
     if (env->persistent) {       // CTAs take (chunk, batch) items; frames, raster tables and barriers are set up once per CTA
         grid = n_batches * n_chunks;
         if (grid > resident) grid = resident;
+        // While the caller reduces the statistics after every launch, the collective's kernels (side stream) hold a few SM slots when
+        // the next step launch arrives; a cooperative grid that needs EVERY slot would wait for them. Leave room: the work is handed
+        // out dynamically, a few CTAs fewer cost nothing measurable on an HBM-bound launch.
+        static const int reserve_sms = getenv("QLC_COMM_RESERVE_SMS") ? atoi(getenv("QLC_COMM_RESERVE_SMS")) : 4;
+        if (p.snap && reserve_sms > 0 && grid == resident && env->sm_count > 2 * reserve_sms) grid = (uint32_t)(o > 0 ? o : 1) * (uint32_t)(env->sm_count - reserve_sms);
     }
     p.tables = env->tables; p.work_counter = env->work_counter; p.work_base = env->work_base;
     p.chunk_len = chunk; p.launch_serial = ++env->launch_serial; p.progress = env->progress; p.spin_error = env->spin_error;
