@@ -39,8 +39,18 @@ struct RasterTables;
 #define QLC_DEBUG_SKIP_IS(p, v) false
 #endif
 
+// Timeline of a launch (profiling builds only, QLC_TIMELINE_FILE): clock64 stamps of CTA b at fixed points, 16 slots per CTA.
+#ifdef QLC_PROFILING
+#define QLC_STAMP(p, slot) do { if ((p).timeline && blockIdx.x < 1024u) (p).timeline[blockIdx.x * 16u + (slot)] = (unsigned long long)clock64(); } while (0)
+#define QLC_STAMP_GT(p, slot) do { if ((p).timeline && blockIdx.x < 1024u) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); (p).timeline[blockIdx.x * 16u + (slot)] = t_; } } while (0)
+#else
+#define QLC_STAMP(p, slot) do { } while (0)
+#define QLC_STAMP_GT(p, slot) do { } while (0)
+#endif
+
 struct StepParams {
     uint32_t n_envs, env_id_base, time_slots, max_episode_steps, auto_reset, n_steps;
+    unsigned long long* timeline;   // profiling builds: [1024][16] stamps of the LAST launch (NULL = off)
     uint32_t debug_skip;       // ablation aid, only honoured in -DQLC_PROFILING builds (QLC_DEBUG_SKIP): 1 = no physics, 2 = no frame stores
     const RasterTables* tables;   // built once per env handle by raster_tables_kernel
     unsigned int* work_counter; uint32_t work_base;   // work hand-out: first item = blockIdx.x, then gridDim.x + atomicAdd(counter, 1) - base
@@ -50,6 +60,7 @@ struct StepParams {
     uint32_t chunk_len; uint32_t launch_serial; unsigned long long* progress; unsigned int* spin_error;
     uint32_t epc;              // envs per CTA (<= R*NE), chosen by the host so that the grid fills all SMs evenly
     uint64_t t0, seed;
+    uint32_t slot0;            // t0 mod time_slots (n_steps <= time_slots: the slot of step s is slot0 + s, minus time_slots if it wraps)
     uint8_t* frames; uint32_t* records; DeviceStats* stats;
     // statistics snapshot (NULL = off): the last CTA to finish copies the shard accumulators here, so that a reduction running on
     // a side stream reads the state "after this launch" while later launches already mutate `stats`
@@ -198,24 +209,31 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
     __shared__ AdvanceSmem<D, R * NE> S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t n_batches = (p.n_envs + EPC - 1) / EPC;   // env batches, handed out to the CTAs dynamically
+    if (tid == 0) { QLC_STAMP_GT(p, 0); QLC_STAMP(p, 1); }
 
     if (tid == 0) {
         for (int q = 0; q < D; ++q) { mbar_init(&S.full[q], 1); mbar_init(&S.empty[q], R); }
         fence_mbar_init();
     }
-    if (warp != 0) {   // zero the resident frames while the tables are being built
-        uint4* z = reinterpret_cast<uint4*>(dyn_smem + (size_t)(warp - 1) * NE * FRAME_BYTES);
-        for (int i = lane; i < NE * FRAME_VEC16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
-    }
-    {   // raster tables: ~1 KB copy from the per-handle global copy
-        static_assert(sizeof(RasterTables) % 4 == 0, "word copy");
+    {   // raster tables: ~1 KB copy from the per-handle global copy, requested first so that the zero fill hides its latency
+        static_assert(sizeof(RasterTables) % 4 == 0 && sizeof(RasterTables) / 4 <= 2 * 32 * (R + 1), "word copy, at most two words per thread");
         const uint32_t* src = reinterpret_cast<const uint32_t*>(p.tables); uint32_t* dst = reinterpret_cast<uint32_t*>(&S.tables);
-        for (int i = tid; i < (int)(sizeof(RasterTables) / 4); i += blockDim.x) dst[i] = __ldg(src + i);
+        constexpr int WORDS = (int)(sizeof(RasterTables) / 4), NT = 32 * (R + 1);
+        const uint32_t w0 = tid < WORDS ? __ldg(src + tid) : 0u;
+        const uint32_t w1 = tid + NT < WORDS ? __ldg(src + tid + NT) : 0u;
+        if (warp != 0) {   // zero the resident frames
+            uint4* z = reinterpret_cast<uint4*>(dyn_smem + (size_t)(warp - 1) * NE * FRAME_BYTES);
+            for (int i = lane; i < NE * FRAME_VEC16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        if (tid < WORDS) dst[tid] = w0;
+        if (tid + NT < WORDS) dst[tid + NT] = w1;
     }
     __syncthreads();
     // Programmatic dependent launch (single-step launches, qlc_api.cu): everything above touches nothing an earlier kernel
     // wrote, so it may overlap the predecessor's tail; from here on its results (actions, env state, frame ring) are needed.
+    if (tid == 0) QLC_STAMP(p, 2);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid == 0) QLC_STAMP(p, 3);
 
     if (warp == 0) {
         // ------------------------------- physics warp -------------------------------
@@ -258,6 +276,13 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
         const uint32_t n_here = min(EPC, p.n_envs - env0);
         const uint32_t e = env0 + lane;
         const bool active = lane < n_here;
+        // Shapes with register headroom (<= 2 CTAs per SM: the learner-driven single-step launches) request the first action before
+        // the state, so that its trip to HBM hides behind the state loads and the move cache instead of following them (timeline of
+        // a single-step launch: 3,500 -> 2,600 cycles from the dependency wait to the physics). The 3-CTA shapes sit exactly at their
+        // 72-register budget: one more live value there is a spill in the headline launch.
+        uint32_t action = 0u;
+        constexpr bool EARLY_ACTION = MINB <= 2;
+        if (EARLY_ACTION && active && p.actions) action = p.actions[(size_t)s_begin * p.n_envs + e];
         Env env; uint32_t k = 0, episode = 0;
         if (active) {   // __ldcg: read at L2 — with chunking another SM may have written this state during the launch
             env.cx = __ldcg(&st.ball_cx[e]); env.cy = __ldcg(&st.ball_cy[e]); env.dx = __ldcg(&st.ball_dx[e]); env.dy = __ldcg(&st.ball_dy[e]);
@@ -268,8 +293,7 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             env_init(env, -0.25f); env.err = 0;
         }
         MoveCache mc; move_cache_update(mc, env);
-        uint32_t action = 0u;
-        if (active) action = p.actions ? p.actions[(size_t)s_begin * p.n_envs + e] : policy_action(p.seed, p.env_id_base + e, (uint32_t)(p.t0 + s_begin));
+        if (active && !(EARLY_ACTION && p.actions)) action = p.actions ? p.actions[(size_t)s_begin * p.n_envs + e] : policy_action(p.seed, p.env_id_base + e, (uint32_t)(p.t0 + s_begin));
         for (uint32_t s = s_begin; s < s_end; ++s, ++seq) {
             const int q = seq % D;
             uint32_t next_action = 0u;
@@ -277,7 +301,10 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             if (active && p.actions_out) p.actions_out[(size_t)s * p.n_envs + e] = (uint8_t)action;
             if (action >= 3u) { env.err |= ENVERR_ACTION; action = 0u; }
             const uint32_t score_before = env.score;
+            if (lane == 0 && seq == 0) QLC_STAMP(p, 4);
             if (active && !QLC_DEBUG_SKIP_IS(p, 1u)) time_step(env, action, mc);
+            __syncwarp();
+            if (lane == 0 && seq == 0) QLC_STAMP(p, 5);
             if (seq >= (uint32_t)D) mbar_wait(&S.empty[q], ((seq / D) - 1) & 1);
             if (active) {
                 RenderRec rr;
@@ -310,6 +337,7 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.full[q]);
+            if (lane == 0 && seq == 0) QLC_STAMP(p, 6);
             action = next_action;
         }
         if (active) {
@@ -330,6 +358,7 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
         // griddepcontrol.wait until this grid has completed and flushed. (Triggering at the top of the kernel would let a small
         // dependent grid — a minibatch gather — pile onto the few SMs this grid leaves free.)
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (lane == 0) QLC_STAMP(p, 7);
         if (p.snap) {    // every statistics atomic of this CTA is done: count it out, the last one takes the snapshot
             __threadfence();
             __syncwarp();
@@ -368,6 +397,7 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             mbar_wait(&S.full[q], (seq / D) & 1);
             const uint32_t env0 = S.item_env0[q], n_here = S.item_n[q], s = S.item_step[q];
             if (n_here == 0u) break;                       // the physics warp found no more env batches
+            if (rw == 0 && lane == 0 && seq == 0) QLC_STAMP(p, 8);
             RenderRec rr[NE];
             #pragma unroll
             for (int i = 0; i < NE; ++i) {
@@ -376,7 +406,7 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.empty[q]);      // records are in registers: hand the queue slot back early
-            const uint32_t slot = (uint32_t)((p.t0 + s) % p.time_slots);
+            const uint32_t slot = p.slot0 + s >= p.time_slots ? p.slot0 + s - p.time_slots : p.slot0 + s;
             uint8_t* slot_base = p.frames + ((size_t)slot * p.n_envs + env0) * FRAME_BYTES;
             #pragma unroll
             for (int g = 0; g < G; ++g) {
@@ -432,6 +462,7 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
                     }
                 }
                 __syncwarp();
+                if (rw == 0 && lane == 0 && seq == 0 && g == 0) QLC_STAMP(p, 9);
                 // ---- phase 2: ball ring on top of bricks, under the paddle ----
                 #pragma unroll
                 for (int f = 0; f < FPG; ++f) {
@@ -457,8 +488,10 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
                         }
                     }
                 }
+                if (rw == 0 && lane == 0 && seq == 0 && g == 0) QLC_STAMP(p, 10);
                 fence_proxy_async_smem();
                 __syncwarp();
+                if (rw == 0 && lane == 0 && seq == 0 && g == 0) QLC_STAMP(p, 14);
                 // ---- the group's frames leave as one bulk group (committed even when empty, so the count stays uniform) ----
                 if (lane == 0) {
                     if (!QLC_DEBUG_SKIP_IS(p, 2u)) {
@@ -470,11 +503,15 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
                         }
                     }
                     bulk_commit();
+                    if (rw == 0 && seq == 0 && g == 0) QLC_STAMP(p, 15);
                 }
             }
         }
         }   // batches
-        if (lane == 0) bulk_wait<0>();     // (waiting only for the reads, cp.async.bulk.wait_group.read, measured the same: 10.87 vs 10.80 us per single-step launch)
+        if (rw == 0 && lane == 0) QLC_STAMP(p, 11);
+        if (lane == 0) bulk_wait<0>();
+        if (rw == 0 && lane == 0) { QLC_STAMP(p, 12); QLC_STAMP_GT(p, 13); }
+        // (waiting only for the reads, cp.async.bulk.wait_group.read, measured the same: 10.87 vs 10.80 us per single-step launch)
     }
 }
 

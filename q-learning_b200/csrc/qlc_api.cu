@@ -82,6 +82,7 @@ struct qlc_env {
     int epc_override = 0;                      // QLC_EPC: force envs per CTA (0 = auto)
     int sm_count = 148;
     int debug_skip = 0;                        // QLC_DEBUG_SKIP (profiling aid)
+    unsigned long long* timeline = nullptr;    // profiling builds with QLC_TIMELINE_FILE: clock stamps of the last step launch, dumped at destroy
     int persistent = 1;                        // QLC_PERSISTENT=0: one CTA per env batch
     std::vector<void*> allocs;
     std::vector<struct qlc_qnet*> qnets;       // Q-networks created on this env: invalidated (not dangling) when the env goes first
@@ -233,6 +234,9 @@ int32_t qlc_env_create(const qlc_config* cfg, qlc_env** out) {
     DeviceStats init{0ull, 0ull, 0xFFFFFFFFu, 0u};
     ce = cudaMemcpy(env->stats, &init, sizeof init, cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { qlc_env_destroy(env); return fail(QLC_ERR_CUDA, std::string("stats init: ") + cudaGetErrorString(ce)); }
+#ifdef QLC_PROFILING
+    if (getenv("QLC_TIMELINE_FILE")) { rc = dev_alloc(env, &env->timeline, 1024 * 16, true); if (rc) { qlc_env_destroy(env); return rc; } }
+#endif
     raster_tables_kernel<<<1, 128>>>(env->tables);
     rc = launch_reset(env, nullptr, nullptr, 1, nullptr);
     if (rc) { qlc_env_destroy(env); return rc; }
@@ -246,6 +250,14 @@ int32_t qlc_env_destroy(qlc_env* env) {
     if (!env) return QLC_OK;
     cudaSetDevice(env->cfg.device);
     cudaDeviceSynchronize();
+#ifdef QLC_PROFILING
+    if (env->timeline)
+        if (const char* path = getenv("QLC_TIMELINE_FILE")) {
+            std::vector<unsigned long long> h(1024 * 16);
+            if (cudaMemcpy(h.data(), env->timeline, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess)
+                if (FILE* f = fopen(path, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+        }
+#endif
     qlc_comm_destroy(env);
     for (struct qlc_qnet* q : env->qnets) qnet_release_device(q);      // their handles stay valid for qlc_qnet_destroy, every other call fails
     for (void* p : env->allocs) cudaFree(p);
@@ -358,9 +370,10 @@ static int32_t step_launch(qlc_env* env, const uint8_t* actions_dev, uint8_t* ac
     StepParams p{};
     p.n_envs = env->cfg.n_envs; p.env_id_base = env->cfg.env_id_base; p.time_slots = env->time_slots;
     p.max_episode_steps = env->cfg.max_episode_steps; p.auto_reset = env->cfg.auto_reset; p.n_steps = n_steps;
-    p.t0 = env->t; p.seed = env->cfg.seed; p.frames = env->frames; p.records = env->records; p.stats = env->stats;
+    p.t0 = env->t; p.slot0 = (uint32_t)(env->t % env->time_slots); p.seed = env->cfg.seed; p.frames = env->frames; p.records = env->records; p.stats = env->stats;
     p.actions = actions_dev; p.actions_out = actions_out_dev; p.reward = reward_dev; p.done = done_dev;
     p.debug_skip = (uint32_t)env->debug_skip;
+    p.timeline = env->timeline;
     cudaStream_t s = (cudaStream_t)stream;
     if (qlc_env::Comm* c = env->comm; c && c->armed) {           // snapshots only while the caller keeps reducing (an atomic per CTA otherwise saved)
         const uint32_t slot = (env->launch_serial + 1u) & 3u;     // launch_advance pre-increments the serial
