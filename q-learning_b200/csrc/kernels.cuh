@@ -935,9 +935,10 @@ __global__ void __launch_bounds__(GATHER_XYH_THREADS) gather_xyh_kernel(GatherPa
 // Streamed host gather (f32 [b][x][y][slot] requests of the *_host entry points): the u8 stacks go straight into page-locked HOST
 // memory, in order, and every piece (1/slices of a stack) raises an arrival flag at system scope, so that host threads widen
 // piece i into the caller's tensor while the pieces behind it are still crossing PCIe. A small persistent grid walks the pieces
-// with stride gridDim.x: few CTAs in flight = pieces land in order (a grid of one CTA per piece finishes them all at once, after
-// the whole transfer: first flag 55 us after the launch, measured). Each piece is transposed in shared memory and leaves as ONE
-// bulk copy - large PCIe writes.
+// with stride gridDim.x, two stores in flight per CTA. Stores of different CTAs interleave on the bus, so what is in flight completes
+// together: one CTA per piece raised its first flag 55 us after the launch (the whole transfer), 48 CTAs raise it after ~30 us; an
+// issue window that limits the pieces in flight makes the arrival order strict but starves the bus (12 pieces: 128 us instead of 98).
+// Each piece is transposed in shared memory and leaves as ONE bulk copy.
 __global__ void __launch_bounds__(GATHER_XYH_THREADS) gather_xyh_stream_kernel(GatherParams g) {
     extern __shared__ __align__(128) uint8_t sm[];     // 4 slot frames + the transposed piece
     __shared__ uint64_t bar;
@@ -945,7 +946,8 @@ __global__ void __launch_bounds__(GATHER_XYH_THREADS) gather_xyh_stream_kernel(G
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     __syncthreads();
     const int per_slice = FRAME_BYTES / (int)g.slices;
-    const uint32_t n_pieces = g.n_items * 2u * g.slices;
+    const bool both = g.out_state && g.out_next;         // pieces are numbered over the stacks that are wanted: no gaps in the arrival order
+    const uint32_t n_pieces = g.n_items * (both ? 2u : 1u) * g.slices;
     // The indices / handles sit in page-locked host memory: fetch them ONCE, before any store is in flight - a PCIe read issued
     // per piece queues up behind the outbound frame data (measured: ~13 us per piece, whatever its size).
     const uint32_t* my_indices = g.indices; const ObsHandle* my_handles = g.handles;
@@ -967,9 +969,8 @@ __global__ void __launch_bounds__(GATHER_XYH_THREADS) gather_xyh_stream_kernel(G
         uchar4* stg = reinterpret_cast<uchar4*>(sm + 4 * FRAME_BYTES + (size_t)(it & 1u) * (size_t)per_slice * 4u);   // two staging buffers
         ++it;
         const uint32_t unit = piece / g.slices, slice = piece - unit * g.slices;
-        const uint32_t b = unit >> 1, which = unit & 1u;
+        const uint32_t b = both ? unit >> 1 : unit, which = both ? unit & 1u : (g.out_next ? 1u : 0u);
         uchar4* out = reinterpret_cast<uchar4*>(which ? g.out_next : g.out_state);
-        if (!out) continue;
         uint64_t T; uint32_t e, k, rec;
         const bool exists = locate(gl, b, g.mode == GATHER_INDICES ? my_indices[b] : 0u, T, e, k, rec);
         if (tid == 0 && slice == 0 && (which == 0 || !g.out_state)) write_scalars(g, b, rec);

@@ -786,8 +786,8 @@ static int32_t run_host_gather(qlc_env* env, HostGather& hg) {
     // f32 requests, streamed (QLC_HOST_STREAM=0: the piecewise copies below): the kernel stores the u8 stacks straight into the
     // page-locked staging while it runs and raises one arrival flag per CTA; the host pool widens slice i into the caller's
     // tensor as soon as its flag is up, while the slices behind it are still crossing PCIe. One launch, no copy calls, no events.
-    static const bool stream_mode = getenv("QLC_HOST_STREAM") ? atoi(getenv("QLC_HOST_STREAM")) != 0 : true;
-    if (widen && stream_mode && (hg.state_host || hg.next_host)) {      // (scalars only: the one-warp kernel below)
+    static const int stream_mode = getenv("QLC_HOST_STREAM") ? atoi(getenv("QLC_HOST_STREAM")) : 1;
+    if (widen && stream_mode == 1 && (hg.state_host || hg.next_host)) {      // (scalars only: the one-warp kernel below)
         static const bool timing = getenv("QLC_HOST_TIMING") != nullptr;
         const auto t0 = std::chrono::steady_clock::now();
         const size_t o_f = (total + 255) & ~(size_t)255, total_f = o_f + (size_t)n * 2 * 4 * sizeof(uint32_t);   // <= 4 CTAs per (item, s | s')
@@ -818,7 +818,9 @@ static int32_t run_host_gather(qlc_env* env, HostGather& hg) {
         // in flight to keep PCIe busy (each spends most of a piece's time loading and transposing), few enough that pieces land in order
         uint32_t slices = (slices_env == 1 || slices_env == 2 || slices_env == 4) ? (uint32_t)slices_env : (n <= 64 ? 2u : 1u);
         g.slices = slices;
-        const uint32_t n_ctas_all = n * 2u * slices;
+        const bool both = hg.state_host && hg.next_host;
+        const uint32_t n_ctas_all = n * (both ? 2u : 1u) * slices;
+
         uint32_t grid = ctas_env > 0 ? (uint32_t)ctas_env : 48u;
         if (grid > n_ctas_all) grid = n_ctas_all;
         size_t smem = 4 * (size_t)FRAME_BYTES + 2 * (4 * (size_t)FRAME_BYTES / slices);      // 4 slot frames + two staging buffers
@@ -835,9 +837,9 @@ static int32_t run_host_gather(qlc_env* env, HostGather& hg) {
         const auto t1 = std::chrono::steady_clock::now();
         const uint32_t per = (uint32_t)(ib / slices);                 // elements per CTA: its share of the 7,056 pixels x 4 slots
         std::vector<qlc_host::StreamPiece>& pieces = env->stream_pieces;
-        pieces.resize((size_t)n * 2 * slices);
+        pieces.resize((size_t)n_ctas_all);
         for (size_t c = 0; c < pieces.size(); ++c) {
-            const size_t unit = c / slices, slice = c % slices, b = unit >> 1, which = unit & 1;
+            const size_t unit = c / slices, slice = c % slices, b = both ? unit >> 1 : unit, which = both ? (unit & 1) : (hg.next_host ? 1 : 0);
             float* host = (float*)(which ? hg.next_host : hg.state_host);
             const size_t off = b * ib + slice * per;
             pieces[c] = qlc_host::StreamPiece{pin + (which ? o_n : o_s) + off, host ? host + off : nullptr, per};
