@@ -388,9 +388,43 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
         #pragma unroll
         for (int i = 0; i < NE; ++i) { prev_bricks[i] = 0ull; prev_box[i] = (int)0x80008000u; }   // box far outside the frame
 
-        constexpr int G = NE >= 2 ? 2 : 1;          // bulk groups per step: one half drains while the other is drawn
+        // bulk groups per step: one half of the warp's frames drains while the other is drawn. (One group - all frames drawn, one proxy
+        // fence, all stores - is no faster for single-step launches, 10.91 vs 10.60 us: the SM's bulk-copy unit takes the 16 frames of a
+        // CTA one after the other either way, ~0.8 us per 7 KB store issue when every warp issues at once.)
+        constexpr int G = NE >= 2 ? 2 : 1;
         constexpr int FPG = NE / G;                 // frames per group
         static_assert(NE % G == 0, "NE must be 1 or even");
+        // Learner-driven launches (a step or two per launch): while the physics warp is still loading the state and advancing the
+        // ball, draw the brick band of this CTA's first (static) item from the brick masks as they are BEFORE the step - most steps
+        // leave them alone, and the incremental redraw below rewrites the band whenever a brick did vanish. Takes the band (the bulk
+        // of a fresh frame's phase 1) off the launch's critical path; same pixels by construction.
+        if (p.n_steps < 4u && p.chunk_len == 0u && blockIdx.x < n_batches) {
+            const uint32_t env0 = blockIdx.x * EPC, n_here = min(EPC, p.n_envs - env0);
+            #pragma unroll
+            for (int i = 0; i < NE; ++i) {
+                const uint32_t j = (uint32_t)(i * R + rw);
+                if (j < n_here) {
+                    const uint64_t bricks = __ldcg(&st.bricks[env0 + j]);
+                    uint32_t* wbuf = reinterpret_cast<uint32_t*>(my_bufs + (size_t)i * FRAME_BYTES);
+                    {
+                        const uint32_t m = (uint32_t)(bricks >> (20 * bg0)) & 0xFFFFFu;
+                        const uint4 b = T.word_bits[bw0];
+                        const uint32_t v = ((m & b.x) ? 96u : 0u) | ((m & b.y) ? 96u << 8 : 0u) | ((m & b.z) ? 96u << 16 : 0u) | ((m & b.w) ? 96u << 24 : 0u);
+                        const int first = T.grp_first[bg0], count = T.grp_count[bg0];
+                        for (int r = 0; r < count; ++r) wbuf[(first + r) * WPR + bw0] = v;
+                    }
+                    if (lane < 3 * WPR - 32) {
+                        const uint32_t m = (uint32_t)(bricks >> (20 * bg1)) & 0xFFFFFu;
+                        const uint4 b = T.word_bits[bw1];
+                        const uint32_t v = ((m & b.x) ? 96u : 0u) | ((m & b.y) ? 96u << 8 : 0u) | ((m & b.z) ? 96u << 16 : 0u) | ((m & b.w) ? 96u << 24 : 0u);
+                        const int first = T.grp_first[bg1], count = T.grp_count[bg1];
+                        for (int r = 0; r < count; ++r) wbuf[(first + r) * WPR + bw1] = v;
+                    }
+                    prev_bricks[i] = bricks;
+                }
+            }
+            __syncwarp();
+        }
         for (uint32_t seq = 0;; ++seq) {
         {
             const int q = seq % D;
