@@ -543,12 +543,12 @@ def measure_replay_sampling(q, torch, dist, rb, dev, stream, world, barrier):
         for layout, name, isz in ((q.LAYOUT_U8_BHYX, "u8", 1), (q.LAYOUT_F32_BXYH, "f32", 4)):
             for c in range(3):
                 rb.get_many(host_rng.choice(rb.len(), size=batch, replace=False).astype(np.uint32), layout, reuse=True)
-            barrier()
             reps = 20
+            id_lists = [host_rng.choice(rb.len(), size=batch, replace=False).astype(np.uint32) for _ in range(reps)]   # the learner's own draw, not this repo's code
+            barrier()
             t0 = time.perf_counter()
             for c in range(reps):
-                ids = host_rng.choice(rb.len(), size=batch, replace=False).astype(np.uint32)
-                g = rb.get_many(ids, layout, reuse=True)
+                g = rb.get_many(id_lists[c], layout, reuse=True)
                 host_check += float(g.reward.sum()) + float(g.state_next[batch - 1].ravel()[-1])
             times.append((time.perf_counter() - t0) / reps * 1e3)
             host_keys.append((batch, name, batch * (2 * per + 4 + 1 + 1), batch * 2 * per * isz))
@@ -574,7 +574,7 @@ def measure_replay_sampling(q, torch, dist, rb, dev, stream, world, barrier):
             res["batch%d_x%d_%s" % (batch, n_batches, name)]["sample_prefetched_on_second_stream"] = {
                 "transitions_per_sec": world * n / (ms_p * 1e-3), "ms_per_call": ms_p, "frac_of_peak": n * bps / (ms_p * 1e-3) / 1e9 / peak}
     return {"metric": "sampled_transitions_per_sec", "n_gpus": world, "replay_len_per_gpu": rb.len(), "results": res,
-            "e2e_host": dict(e2e_host, timing="perf_counter around host-drawn distinct ids + ReplayBuffer.get_many(reuse=True) per minibatch (host index array in, "
+            "e2e_host": dict(e2e_host, timing="perf_counter around ReplayBuffer.get_many(reuse=True) per minibatch with host-drawn distinct ids (drawn before the timed loop; host index array in, "
                                               "page-locked host stacks out, read on the host), max over ranks; stacks cross PCIe as u8, f32 ones are widened by %d host threads" % _host_threads(),
                              result_checksum=host_check),
             "note": "qlc_replay_sample_gather: Philox distinct ids drawn inside the gather kernel + s and s' stacks, ONE launch per call, device buffers, every rank on its own replay shard, max over ranks; "

@@ -805,6 +805,7 @@ static int32_t run_host_gather(qlc_env* env, HostGather& hg) {
         g.reward = scalars ? (float*)(pin + o_r) : nullptr; g.action = scalars ? pin + o_a : nullptr; g.done = scalars ? pin + o_d : nullptr;
         if (++env->flag_serial == 0) env->flag_serial = 1;
         g.cta_flags = (uint32_t*)(pin + o_f); g.flag_value = env->flag_serial;
+        const bool sampled = g.mode == GATHER_SAMPLE;
         if (g.mode == GATHER_SAMPLE) {        // the persistent kernel takes given indices: draw them first (into the staging, the caller wants them anyway)
             uint32_t* idx = (uint32_t*)(pin + o_i);
             if (g.sample_batch >= SAMPLE_BLOCK_MIN_BATCH) replay_sample_kernel<8><<<1, 256, 0, s>>>(idx, g.sample_batch, g.sample_len, g.seed, g.call0);
@@ -847,7 +848,10 @@ static int32_t run_host_gather(qlc_env* env, HostGather& hg) {
         const size_t missed = qlc_host::widen_stream(pieces.data(), pieces.size(), slices, (const volatile uint32_t*)(pin + o_f), g.flag_value,
                                                      [](void* st) { return cudaStreamQuery((cudaStream_t)st) == cudaErrorNotReady; }, (void*)s);
         const auto t2 = std::chrono::steady_clock::now();
-        CUDA_TRY(cudaStreamSynchronize(s));
+        // every flag is up: all pieces and (written earlier by the same threads, before their system-scope fences) all scalars have
+        // landed; the kernel is only exiting, and whatever comes next on this stream is ordered behind it. A missing piece means the
+        // stream ended without it: synchronize to surface the error.
+        if (missed || sampled) CUDA_TRY(cudaStreamSynchronize(s));      // (sampled: the index kernel's own stores carry no flag)
         if (timing) {
             const auto t3 = std::chrono::steady_clock::now();
             auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };

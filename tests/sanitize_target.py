@@ -1,5 +1,5 @@
 """Target for compute-sanitizer (memcheck / racecheck / synccheck): every hot kernel once or twice on a small shard, checked against
-the oracle like smoke().   compute-sanitizer --tool memcheck python tools/sanitize_target.py"""
+the oracle like smoke().   compute-sanitizer --tool memcheck python tests/sanitize_target.py"""
 import importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -7,6 +7,7 @@ for n in (1, 32):
     env = q.BreakoutEnvironment(n_envs=n, seed=1, replay_capacity=1 << 16)
     rb = q.ReplayBuffer(env)
     pa, pr, pd = q.PinnedArray((1, n), np.uint8), q.PinnedArray((1, n), np.float32), q.PinnedArray((1, n), np.uint8)
+    pa.array[:] = 0
     a_pageable = np.zeros((1, n), dtype=np.uint8)
     for name, fn in (("step_many pinned", lambda: env.step_many(pa.array, out=(pr.array, pd.array))),
                      ("step_many pageable", lambda: env.step_many(a_pageable))):
