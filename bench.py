@@ -714,7 +714,37 @@ def measure_qnet(q, torch, env, dev, stream):
     ms = e0.elapsed_time(e1) / reps
     peak, src = _tensor_peak()
     tf = QNET_FLOP_PER_OBS * n / (ms * 1e-3) / 1e12
+    # how often the bf16 tensor-core path picks the action a plain fp32 forward of the same Keras model picks - ALL envs, ties and
+    # near-ties included (library code, outside every timed region; TF32 off)
+    agree = None
+    try:
+        tio = importlib.import_module("q-learning_b200.torch_io")
+        F = torch.nn.functional
+        old_flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+        x = tio.observe(env, q.LAYOUT_F32_BXYH).permute(0, 3, 1, 2).contiguous()       # NCHW with H = x, W = y
+        for i, stride in ((1, 4), (2, 2), (3, 1)):
+            k = torch.from_numpy(w["conv%d_kernel" % i]).to(dev).permute(3, 2, 0, 1).contiguous()
+            x = torch.relu(F.conv2d(x, k, torch.from_numpy(w["conv%d_bias" % i]).to(dev), stride=stride))
+        x = x.permute(0, 2, 3, 1).reshape(n, -1)
+        x = torch.relu(x @ torch.from_numpy(w["dense1_kernel"]).to(dev) + torch.from_numpy(w["dense1_bias"]).to(dev))
+        ref = x @ torch.from_numpy(w["dense2_kernel"]).to(dev) + torch.from_numpy(w["dense2_bias"]).to(dev)
+        torch.cuda.synchronize()
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_flags
+        scale = float(ref.abs().max())
+        srt = ref.sort(dim=1).values
+        gap = (srt[:, 2] - srt[:, 1]) / max(scale, 1e-30)
+        same = ref.argmax(dim=1).to(torch.uint8) == acts[0]
+        agree = {"fraction_of_envs_with_the_fp32_greedy_action": float(same.float().mean()), "envs": n,
+                 "max_abs_q_error_over_max_abs_q": float((qv - ref).abs().max()) / max(scale, 1e-30),
+                 "fraction_where_top2_gap_exceeds_1e-2_of_max_abs_q": float((gap > 1e-2).float().mean()),
+                 "agreement_among_those": float(same[gap > 1e-2].float().mean()) if bool((gap > 1e-2).any()) else None,
+                 "note": "fp32 torch forward of the same random-init Keras model on the current observation of every env (cuDNN / cuBLAS, TF32 off) against "
+                         "the bf16-operand tcgen05 path; disagreements are near-ties (top-2 Q gap below the bf16 error)"}
+    except Exception as ex:   # a reporting extra must not take the bench line down
+        agree = {"error": str(ex)}
     out["qnet_forward"] = {"observations_per_sec": n / (ms * 1e-3), "ms_per_forward": ms, "batch": n, "dtype": "bf16 operands, f32 accumulate (TMEM)",
+                           "greedy_action_vs_fp32": agree,
                            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "peak_source": src,
                                         "note": "convs are shifted-window implicit GEMMs with N = 32/64: bound by the 128 B/clk shared-memory operand fetch "
                                                 "(40/48 cycles per MMA measured, tools/microbench/mma_rate.cu), not by the tensor pipe"},

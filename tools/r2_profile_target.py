@@ -1,7 +1,8 @@
 """Launch sequence for `ncu --set full` (round 2): every hot kernel a few times, in a fixed order, nothing else.
   3 x env_advance (4,096 envs x 64 steps, the bench launch)   3 x env_advance single step (4,096 envs)   3 x single step with the
   random policy drawn in the kernel   then, per layout (u8 [b][slot][y][x], f32 [b][x][y][slot]): 3 x one-launch sample+gather of
-  one minibatch of 32, of 512, of 256 minibatches of 32; 3 x gather with given indices (8,192 transitions); 3 x index-only sample."""
+  one minibatch of 32, of 512, of 256 minibatches of 32; 3 x gather with given indices (8,192 transitions); 3 x index-only sample of 512 and of 32; 3 x the host call
+  get_many(f32) for 32 and 512 (the streamed gather kernel)."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -34,5 +35,12 @@ for layout, dt in ((q.LAYOUT_U8_BHYX, torch.uint8), (q.LAYOUT_F32_BXYH, torch.fl
 idx = torch.empty((512,), dtype=torch.int32, device="cuda")
 for c in range(3):
     rb.sample_device(512, 1, c, idx.data_ptr(), s)
+    rb.sample_device(32, 1, c, idx.data_ptr(), s)
 torch.cuda.synchronize()
+# the reference-shaped host call: f32 tensors in host memory (gather_xyh_stream_kernel: bulk stores into page-locked memory + arrival flags)
+import numpy as np
+rng = np.random.default_rng(0)
+for batch in (32, 512):
+    for c in range(3):
+        rb.get_many(rng.choice(rb.len(), size=batch, replace=False).astype(np.uint32), q.LAYOUT_F32_BXYH, reuse=True)
 env.close()
