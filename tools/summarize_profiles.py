@@ -55,7 +55,8 @@ def kernels(tag, reps):
     per_kernel = collections.OrderedDict()
     fresh = {}
     for rep in reps:
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        # a .ncu-rep is exported here; a .csv is the same export done on the GPU box (a full capture can exceed what gpurun brings back)
+        raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units = rows[0], rows[1]
         for r in rows[2:]:
