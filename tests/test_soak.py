@@ -45,3 +45,37 @@ def test_soak_chunked_launches_and_full_trajectory_replay(qlb, O):
         ora[j].close()
     assert d.sum() > len(sub) * launches // 8          # hundreds of episodes per replayed env
     env.close()
+
+
+def test_soak_single_step_launches_every_env(qlb, O):
+    """The learner-driven mode at BASELINE configs[1] size: 4,096 envs advanced by 2,400 launches of 1, 2 or 3 steps (the shapes whose render
+    warps pre-draw the brick band and whose physics lanes request the action first), uniform random actions, every reward and done of
+    every step plus the final state and frame stacks of EVERY env against the oracle; then the same on a 65,536-env shard for 60 launches
+    (the persistent form: later items reuse the CTAs' frames)."""
+    import torch
+    for n, launches in ((4096, 2400), (65536, 60)):
+        seed = 123 + n
+        env = qlb.BreakoutEnvironment(n_envs=n, seed=seed, replay_capacity=n * 8)
+        ora = O.ShardedVecEnv(n, seed=seed)
+        lens = [1 + (i % 7 == 3) + 2 * (i % 11 == 5) for i in range(launches)]          # mostly 1, some 2, 3, a few 4 (the multi-step shape in between)
+        total = sum(lens)
+        acts = O.synthetic_actions(seed, 0, n, 0, total)
+        a_dev = torch.from_numpy(acts).cuda()
+        rew = torch.empty((total, n), dtype=torch.float32, device="cuda"); dn = torch.empty((total, n), dtype=torch.uint8, device="cuda")
+        s = torch.cuda.current_stream().cuda_stream
+        at = 0
+        for k in lens:
+            env.step_device(a_dev[at:].data_ptr(), k, rew[at:].data_ptr(), dn[at:].data_ptr(), s)
+            at += k
+        torch.cuda.synchronize()
+        r_o, d_o = ora.run(acts)
+        assert np.array_equal(rew.cpu().numpy(), r_o) and np.array_equal(dn.cpu().numpy(), d_o), "reward / done differ (n=%d)" % n
+        st, so = env.read_state(), ora.state()
+        for key in ("ball_cx", "ball_cy", "ball_dx", "ball_dy", "pad_min_x", "pad_max_x", "pad_speed"):
+            assert np.array_equal(st[key].view(np.uint32), so[key].view(np.uint32)), (n, key)
+        for key in ("bricks", "score", "episode_step", "err"):
+            assert np.array_equal(st[key], so[key]), (n, key)
+        assert np.array_equal(env.obs(qlb.LAYOUT_U8_BHYX), ora.obs_u8()), "frame stacks differ (n=%d)" % n
+        if n == 4096:
+            assert d_o.sum() > 4 * n    # several finished episodes per env: resets and fresh frames are covered
+        env.close(); ora.close()
