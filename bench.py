@@ -667,6 +667,20 @@ def measure_extras(q, torch, env, rb, dev, stream, peak, replay, cpu_baseline=Tr
     ms = e0.elapsed_time(e1) / 500
     out["single_step_launch"] = {"env_steps_per_sec": env.n_envs / (ms * 1e-3), "us_per_launch": ms * 1e3}
     out.update(measure_qnet(q, torch, env, dev, stream))
+    # the same drop-in calls from a COMPILED host (plain C against include/ql_cuda.h - what a Rust ql-cuda crate pays), without
+    # ctypes and numpy around them: its own process, its own env handles
+    try:
+        exe = q._build.build_c_host_tool()
+        if exe:
+            r = subprocess.run([exe, "--json"], capture_output=True, text=True, timeout=120)
+            if r.returncode == 0:
+                out["compiled_host_calls"] = dict(json.loads(r.stdout.strip().splitlines()[-1]),
+                                                  note="tools/cabi/c_abi_latency.c (C, gcc -O2) through the C ABI: one env stepped one call at a time; one state handle -> f32 tensor; "
+                                                       "qlc_replay_gather_host of a minibatch into page-locked host tensors on a 4,096-env shard with a 1 M ring; microseconds per call")
+            else:
+                out["compiled_host_calls"] = {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as ex:
+        out["compiled_host_calls"] = {"error": str(ex)}
     return out
 
 

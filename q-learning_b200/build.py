@@ -86,5 +86,24 @@ def build(force=False, verbose=False):
     return SO_PATH
 
 
+def build_c_host_tool():
+    """tools/cabi/c_abi_latency: the drop-in calls timed from a compiled host (plain C against include/ql_cuda.h, linked to the library).
+    Returns the path, or None if it cannot be built (no gcc)."""
+    root = os.path.dirname(_HERE)
+    src, exe = os.path.join(root, "tools", "cabi", "c_abi_latency.c"), os.path.join(root, "tools", "cabi", "c_abi_latency")
+    if os.path.exists(exe) and os.path.getmtime(exe) >= max(os.path.getmtime(src), os.path.getmtime(os.path.join(root, "include", "ql_cuda.h"))):
+        return exe
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        return None
+    env = dict(os.environ); env.pop("CC", None)
+    res = subprocess.run([cc, "-O2", "-I", os.path.join(root, "include"), src, "-L", _HERE, "-lqlcuda", "-Wl,-rpath,$ORIGIN/../../q-learning_b200", "-o", exe],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError("gcc failed on tools/cabi/c_abi_latency.c:\n" + res.stdout)
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_c_host_tool())

@@ -202,9 +202,24 @@ struct Pool {
             std::fprintf(stderr, "[qlc host stream] %zu pieces: first flag %.1f us after publish, last flag seen at %.1f us, widening %.1f us (1 thread)\n", count, first, last, work);
             return 0;
         }
-        pieces = ps; flags = fl; flag_value = value; n_pieces = count; group = grp ? grp : 1; n_items = (count + group - 1) / group;
         size_t out_bytes = 0;
         for (size_t i = 0; i < count; ++i) if (ps[i].dst) out_bytes += (size_t)ps[i].n * 4;
+        if (n_threads == 1 || out_bytes <= 2 * CHUNK * 4) {
+            // a stack or two (predict_action's single observation): waking the pool costs more than the widening
+            size_t lost = 0;
+            for (size_t i = 0; i < count; ++i) {
+                if (!ps[i].dst) continue;
+                unsigned spins = 0; bool landed = true;
+                while (__atomic_load_n(const_cast<const uint32_t*>(&fl[i]), __ATOMIC_ACQUIRE) != value) {
+                    if ((++spins & 255u) == 0 && !still_running(ctx)) { landed = __atomic_load_n(const_cast<const uint32_t*>(&fl[i]), __ATOMIC_ACQUIRE) == value; break; }
+                    cpu_relax();
+                }
+                if (!landed) { ++lost; continue; }
+                if (out_bytes >= NT_MIN_BYTES) widen_nt(ps[i].src, ps[i].dst, ps[i].n); else widen_range(ps[i].src, ps[i].dst, ps[i].n);
+            }
+            return lost;
+        }
+        pieces = ps; flags = fl; flag_value = value; n_pieces = count; group = grp ? grp : 1; n_items = (count + group - 1) / group;
         nt = out_bytes >= NT_MIN_BYTES;
         abandon.store(false, std::memory_order_relaxed); missed.store(0, std::memory_order_relaxed);
         const uint64_t job = publish();

@@ -93,6 +93,32 @@ int main() {
         qlc_host::widen_u8_f32(src.data(), d2.data(), src.size());
         CHECK(d2[123] == 3.0f && d2.back() == 3.0f);
     }
+    // 4. a request of a stack or two is widened on the calling thread (no pool dispatch): arrival order, and a producer that stops early
+    {
+        const size_t n_pieces = 4, per = 7056;
+        std::vector<uint8_t> src(n_pieces * per);
+        for (auto& v : src) v = (uint8_t)rng();
+        std::vector<float> dst(n_pieces * per, -2.0f);
+        std::vector<uint32_t> flags(n_pieces, 0);
+        std::vector<qlc_host::StreamPiece> pieces(n_pieces);
+        for (size_t i = 0; i < n_pieces; ++i) pieces[i] = qlc_host::StreamPiece{src.data() + i * per, dst.data() + i * per, (uint32_t)per};
+        Producer prod;
+        std::thread t([&] {
+            for (size_t k : {size_t(2), size_t(0), size_t(3), size_t(1)}) { std::this_thread::sleep_for(std::chrono::microseconds(30)); __atomic_store_n(&flags[k], 4u, __ATOMIC_RELEASE); }
+            prod.alive.store(false);
+        });
+        CHECK(qlc_host::widen_stream(pieces.data(), n_pieces, 2, flags.data(), 4u, still_running, &prod) == 0);
+        t.join();
+        bool ok = true;
+        for (size_t i = 0; i < src.size(); i += 7) ok &= dst[i] == (float)src[i];
+        CHECK(ok);
+        std::fill(flags.begin(), flags.end(), 0u); std::fill(dst.begin(), dst.end(), -2.0f);
+        Producer prod2;
+        std::thread t2([&] { __atomic_store_n(&flags[0], 6u, __ATOMIC_RELEASE); std::this_thread::sleep_for(std::chrono::milliseconds(1)); prod2.alive.store(false); });
+        CHECK(qlc_host::widen_stream(pieces.data(), n_pieces, 2, flags.data(), 6u, still_running, &prod2) == 3);
+        t2.join();
+        CHECK(dst[0] == (float)src[0] && dst[per] == -2.0f);
+    }
     std::printf(fails ? "host pool: %d check(s) FAILED\n" : "host pool ok (%d threads)\n", fails ? fails : qlc_host::pool_threads());
     return fails ? 1 : 0;
 }
