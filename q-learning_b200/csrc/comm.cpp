@@ -34,6 +34,7 @@ void load() {
         *s.slot = dlsym(h, s.name);
         if (!*s.slot) { g_why = std::string("NCCL symbol missing: ") + s.name; return; }
     }
+    g_api.CommInitRankConfig = (int (*)(Comm*, int, UniqueId, int, void*))dlsym(h, "ncclCommInitRankConfig");   // optional
     g_ok = true;
 }
 }  // namespace

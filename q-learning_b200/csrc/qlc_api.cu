@@ -1052,7 +1052,16 @@ int32_t qlc_comm_init(qlc_env* env, int32_t rank, int32_t world, const uint8_t* 
         const qlc_comm::Api* nccl = qlc_comm::api(&why);
         if (!nccl) return bail(QLC_ERR_COMM, why);
         qlc_comm::UniqueId id; memcpy(id.internal, id128, QLC_COMM_ID_BYTES);
-        const int r = nccl->CommInitRank(&c->nccl, world, id, rank);
+        // one CTA for the collective (QLC_COMM_CTAS=0: NCCL's own choice); a library without ncclCommInitRankConfig, or one that
+        // refuses the config, gets the plain call
+        static const bool one_cta = getenv("QLC_COMM_CTAS") ? atoi(getenv("QLC_COMM_CTAS")) == 1 : true;
+        int r = -1;
+        if (one_cta && nccl->CommInitRankConfig) {
+            qlc_comm::Config cfg = qlc_comm::one_cta_config();
+            r = nccl->CommInitRankConfig(&c->nccl, world, id, rank, &cfg);
+            if (r != 0) c->nccl = nullptr;
+        }
+        if (r != 0) r = nccl->CommInitRank(&c->nccl, world, id, rank);
         if (r != 0) { c->nccl = nullptr; return bail(QLC_ERR_COMM, std::string("ncclCommInitRank: ") + nccl->GetErrorString(r)); }
     }
     cudaError_t e = cudaSuccess;
