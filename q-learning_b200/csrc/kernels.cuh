@@ -588,7 +588,10 @@ constexpr uint32_t SAMPLE_MAX_ROUNDS = 1u << 19;         // x 128 stream positio
 
 constexpr uint32_t SAMPLE_BLOCK_MIN_BATCH = 129;    // from this batch size on a CTA's warps walk the stream side by side (sample_distinct_block)
 __host__ __device__ __forceinline__ uint32_t sample_table_size(uint32_t batch) {   // slots: power of two >= 4 * (batch + 128)
-    if (batch >= SAMPLE_BLOCK_MIN_BATCH) return 4096u;                              // batch + 8 * 128 entries at most: load <= 0.5
+    // CTA-wide sampler: any size works (multiply-shift slot, wrap-around probing). 3,528 slots x 8 B = the 28,224 bytes of the four
+    // staged frames the [b][x][y][slot] gather borrows the table from - a 32 KB table cost that kernel its 7th CTA per SM, i.e. a second
+    // partial wave for one minibatch of 512 (1,024 CTAs). batch + 8 * 128 entries at most: load <= 0.58
+    if (batch >= SAMPLE_BLOCK_MIN_BATCH) return 3528u;
     uint32_t n = 1024;
     while (n < 4u * (batch + 128u) && n < 4096u) n <<= 1;
     return n;                                                                       // <= 4096 slots x (value, position) = 32 KB
@@ -685,7 +688,6 @@ __device__ __forceinline__ void sample_distinct_block(uint32_t* table, uint32_t 
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t thresh = (uint32_t)((0x100000000ull - (uint64_t)len) % (uint64_t)len);
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    const uint32_t tmask = tsize - 1u;
     uint32_t* tval = table; uint32_t* tpos = table + tsize;
     uint32_t kept = 0;
     for (uint32_t pass = 0; pass < SAMPLE_MAX_ROUNDS / NW; ++pass) {
@@ -698,13 +700,13 @@ __device__ __forceinline__ void sample_distinct_block(uint32_t* table, uint32_t 
             const uint64_t m = (uint64_t)raw[w] * (uint64_t)len;
             valid[w] = !((uint32_t)m < thresh);
             val[w] = (uint32_t)(m >> 32);
-            slot[w] = ((val[w] * 0x9E3779B1u) >> 12) & tmask;
+            slot[w] = __umulhi(val[w] * 0x9E3779B1u, tsize);           // multiply-shift into [0, tsize): the size need not be a power of two
         }
         #pragma unroll
         for (int w = 0; w < 4; ++w) {
             if (valid[w]) {
                 uint32_t old = atomicCAS(&tval[slot[w]], SAMPLE_EMPTY, val[w]);
-                while (old != SAMPLE_EMPTY && old != val[w]) { slot[w] = (slot[w] + 1u) & tmask; old = atomicCAS(&tval[slot[w]], SAMPLE_EMPTY, val[w]); }
+                while (old != SAMPLE_EMPTY && old != val[w]) { slot[w] = slot[w] + 1u == tsize ? 0u : slot[w] + 1u; old = atomicCAS(&tval[slot[w]], SAMPLE_EMPTY, val[w]); }
                 atomicMin(&tpos[slot[w]], ctr * 4u + (uint32_t)w);          // positions start as SAMPLE_EMPTY = the largest value
             }
         }
