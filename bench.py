@@ -148,7 +148,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": _config(args.envs, args.steps_per_launch, args.replay_capacity, 1),
+        "config": _config(args.envs, args.steps_per_launch, args.replay_capacity, max(1, args.gpus)),      # the B200 arm's config at this N, verbatim
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
