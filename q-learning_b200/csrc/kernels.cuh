@@ -42,10 +42,12 @@ struct RasterTables;
 // Timeline of a launch (profiling builds only, QLC_TIMELINE_FILE): clock64 stamps of CTA b at fixed points, 16 slots per CTA.
 #ifdef QLC_PROFILING
 #define QLC_STAMP(p, slot) do { if ((p).timeline && blockIdx.x < 1024u) (p).timeline[blockIdx.x * 16u + (slot)] = (unsigned long long)clock64(); } while (0)
+#define QLC_STAMP_SEQ(p) ((p).debug_skip >= 16u ? (p).debug_skip - 16u : 0u)     /* which step of the launch the per-step stamps are taken at */
 #define QLC_STAMP_GT(p, slot) do { if ((p).timeline && blockIdx.x < 1024u) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); (p).timeline[blockIdx.x * 16u + (slot)] = t_; } } while (0)
 #else
 #define QLC_STAMP(p, slot) do { } while (0)
 #define QLC_STAMP_GT(p, slot) do { } while (0)
+#define QLC_STAMP_SEQ(p) 0u
 #endif
 
 struct StepParams {
@@ -301,10 +303,10 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             if (active && p.actions_out) p.actions_out[(size_t)s * p.n_envs + e] = (uint8_t)action;
             if (action >= 3u) { env.err |= ENVERR_ACTION; action = 0u; }
             const uint32_t score_before = env.score;
-            if (lane == 0 && seq == 0) QLC_STAMP(p, 4);
+            if (lane == 0 && seq == QLC_STAMP_SEQ(p)) QLC_STAMP(p, 4);
             if (active && !QLC_DEBUG_SKIP_IS(p, 1u)) time_step(env, action, mc);
             __syncwarp();
-            if (lane == 0 && seq == 0) QLC_STAMP(p, 5);
+            if (lane == 0 && seq == QLC_STAMP_SEQ(p)) QLC_STAMP(p, 5);
             if (seq >= (uint32_t)D) mbar_wait(&S.empty[q], ((seq / D) - 1) & 1);
             if (active) {
                 RenderRec rr;
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.full[q]);
-            if (lane == 0 && seq == 0) QLC_STAMP(p, 6);
+            if (lane == 0 && seq == QLC_STAMP_SEQ(p)) QLC_STAMP(p, 6);
             action = next_action;
         }
         if (active) {
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
             mbar_wait(&S.full[q], (seq / D) & 1);
             const uint32_t env0 = S.item_env0[q], n_here = S.item_n[q], s = S.item_step[q];
             if (n_here == 0u) break;                       // the physics warp found no more env batches
-            if (rw == 0 && lane == 0 && seq == 0) QLC_STAMP(p, 8);
+            if (rw == 0 && lane == 0 && seq == QLC_STAMP_SEQ(p)) QLC_STAMP(p, 8);
             RenderRec rr[NE];
             #pragma unroll
             for (int i = 0; i < NE; ++i) {
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
                     }
                 }
                 __syncwarp();
-                if (rw == 0 && lane == 0 && seq == 0 && g == 0) QLC_STAMP(p, 9);
+                if (rw == 0 && lane == 0 && seq == QLC_STAMP_SEQ(p) && g == 0) QLC_STAMP(p, 9);
                 // ---- phase 2: ball ring on top of bricks, under the paddle ----
                 #pragma unroll
                 for (int f = 0; f < FPG; ++f) {
@@ -522,10 +524,10 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
                         }
                     }
                 }
-                if (rw == 0 && lane == 0 && seq == 0 && g == 0) QLC_STAMP(p, 10);
+                if (rw == 0 && lane == 0 && seq == QLC_STAMP_SEQ(p) && g == 0) QLC_STAMP(p, 10);
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (rw == 0 && lane == 0 && seq == 0 && g == 0) QLC_STAMP(p, 14);
+                if (rw == 0 && lane == 0 && seq == QLC_STAMP_SEQ(p) && g == 0) QLC_STAMP(p, 14);
                 // ---- the group's frames leave as one bulk group (committed even when empty, so the count stays uniform) ----
                 if (lane == 0) {
                     if (!QLC_DEBUG_SKIP_IS(p, 2u)) {
@@ -537,7 +539,7 @@ __global__ void __launch_bounds__(32 * (R + 1), MINB) env_advance_kernel(EnvArra
                         }
                     }
                     bulk_commit();
-                    if (rw == 0 && seq == 0 && g == 0) QLC_STAMP(p, 15);
+                    if (rw == 0 && seq == QLC_STAMP_SEQ(p) && g == 0) QLC_STAMP(p, 15);
                 }
             }
         }

@@ -15,7 +15,8 @@ if sys.argv[1] == "run":
     gen = torch.Generator(device="cuda"); gen.manual_seed(1)
     acts = torch.randint(0, 3, (64, n), dtype=torch.uint8, device="cuda", generator=gen)
     for _ in range(20): env.step_device(acts.data_ptr(), 64, None, None, s)          # a lived-in state: random policy for 1,280 steps
-    for i in range(200): env.step_device(acts[i % 64:].data_ptr(), 1, None, None, s)     # back-to-back single steps; the last one is recorded
+    k = int(sys.argv[3]) if len(sys.argv) > 3 else 1                                      # steps per launch (QLC_DEBUG_SKIP=16+j: stamps at step j)
+    for i in range(200): env.step_device(acts[i % 32:].data_ptr(), k, None, None, s)     # back-to-back launches; the last one is recorded
     torch.cuda.synchronize()
     env.close()
 else:
