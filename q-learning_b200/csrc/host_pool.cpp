@@ -69,6 +69,7 @@ inline void cpu_relax() {
 }
 
 struct Pool {
+    std::mutex job_mutex;                    // one job at a time: env handles on different host threads (one per GPU) share this pool
     std::mutex m;
     std::condition_variable cv;
     std::vector<std::thread> workers;
@@ -176,6 +177,7 @@ struct Pool {
 
     void widen(const uint8_t* s, float* d, size_t count) {
         if (count == 0) return;
+        std::lock_guard<std::mutex> one_job(job_mutex);
         if (n_threads == 1 || count <= 2 * CHUNK) { if (count * 4 >= NT_MIN_BYTES) widen_nt(s, d, count); else widen_range(s, d, count); return; }
         pieces = nullptr; src = s; dst = d; n = count; n_items = (count + CHUNK - 1) / CHUNK; nt = count * 4 >= NT_MIN_BYTES;
         const uint64_t job = publish();
@@ -186,6 +188,7 @@ struct Pool {
 
     size_t stream(const qlc_host::StreamPiece* ps, size_t count, size_t grp, const volatile uint32_t* fl, uint32_t value, bool (*still_running)(void*), void* ctx) {
         if (count == 0) return 0;
+        std::lock_guard<std::mutex> one_job(job_mutex);
         static const bool timing = getenv("QLC_HOST_TIMING") != nullptr;
         const auto t_pub = std::chrono::steady_clock::now();
         if (timing) {      // one thread, in order: when does the first / the last flag come up, how long does the widening take behind it

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <random>
 #include <thread>
 #include <vector>
@@ -118,6 +119,24 @@ int main() {
         CHECK(qlc_host::widen_stream(pieces.data(), n_pieces, 2, flags.data(), 6u, still_running, &prod2) == 3);
         t2.join();
         CHECK(dst[0] == (float)src[0] && dst[per] == -2.0f);
+    }
+    // 5. two host threads (two env handles, e.g. one per GPU) use the pool at the same time
+    {
+        const size_t n = (size_t)40 * 28224;
+        std::vector<uint8_t> s1(n), s2(n);
+        for (size_t i = 0; i < n; ++i) { s1[i] = (uint8_t)rng(); s2[i] = (uint8_t)rng(); }
+        std::vector<float> d1(n), d2(n);
+        bool ok1 = true, ok2 = true;
+        auto job = [&](const std::vector<uint8_t>& s, std::vector<float>& d, bool& ok) {
+            for (int rep = 0; rep < 30; ++rep) {
+                std::fill(d.begin(), d.end(), -1.0f);
+                qlc_host::widen_u8_f32(s.data(), d.data(), n);
+                for (size_t i = 0; i < n; i += 101) ok &= d[i] == (float)s[i];
+            }
+        };
+        std::thread a(job, std::cref(s1), std::ref(d1), std::ref(ok1)), b(job, std::cref(s2), std::ref(d2), std::ref(ok2));
+        a.join(); b.join();
+        CHECK(ok1 && ok2);
     }
     std::printf(fails ? "host pool: %d check(s) FAILED\n" : "host pool ok (%d threads)\n", fails ? fails : qlc_host::pool_threads());
     return fails ? 1 : 0;
