@@ -93,6 +93,22 @@ int main(int argc, char** argv) {
             report(bi ? "gather_host_512_u8_us" : "gather_host_32_u8_us", bi ? "4,096 envs, qlc_replay_gather_host(512, u8 [b][slot][y][x]), per minibatch:" : "4,096 envs, qlc_replay_gather_host( 32, u8 [b][slot][y][x]), per minibatch:", total / reps);
             qlc_host_free(s); qlc_host_free(sn); free(idx); free(rw); free(ac); free(dn);
         }
+        /* what the unchanged learner's model does twice per train step: batch_to_multi_dim_array of 32 state handles -> ONE f32 tensor */
+        {
+            const uint32_t batch = 32; const size_t per = (size_t)4 * 84 * 84;
+            float* s; CHECK(qlc_host_alloc(batch * per * sizeof(float), (void**)&s));
+            uint64_t t = 0; CHECK(qlc_env_time(env, &t));
+            qlc_obs_handle h[32];
+            double total = 0; const int reps = 1000;
+            for (int it = -20; it < reps; ++it) {
+                for (uint32_t i = 0; i < batch; ++i) { h[i].time = t - (rnd() % 200); h[i].k = 4 + (rnd() % 4); h[i].env = rnd() % n; }
+                const double t0 = now_us();
+                CHECK(qlc_obs_gather_host(env, h, batch, QLC_LAYOUT_F32_BXYH, s));
+                if (it >= 0) total += now_us() - t0;
+            }
+            report("obs_gather_host_32_handles_f32_us", "4,096 envs, qlc_obs_gather_host(32 handles, f32), per call (one tensor):", total / reps);
+            qlc_host_free(s);
+        }
         qlc_host_free(a);
         CHECK(qlc_env_destroy(env));
     }
