@@ -2,7 +2,7 @@
 with given indices, single-step launches, and the actor-loop iteration. CUDA events around back-to-back calls, after warm-up."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 q = importlib.import_module("q-learning_b200")
 PEAK = 6537.3
 

@@ -1,6 +1,6 @@
 """Scratch (torchrun, N ranks): cost of qlc_stats_allreduce after every bench step, for QLC_COMM_RESERVE_SMS values (read once per process:
 one torchrun per value)."""
-import importlib, json, os, sys
+import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 import bench
